@@ -1,0 +1,23 @@
+"""isoext_b200 -- Blackwell-native iso-surface extraction behind the isoext Python API.
+
+Same public names as the reference package (src/isoext/__init__.py:6-26).  The extension names
+(``UniformGrid`` ... ``marching_cubes``) are backed by hand-written sm_100a CUDA kernels reached
+through the C-ABI library ``libisoext_b200.so`` (include/isoext_b200.h); there is no CPU path.
+"""
+import importlib.util
+
+if importlib.util.find_spec("torch") is None:  # same guard as the reference (src/isoext/__init__.py:3-4)
+    raise ImportError("PyTorch is required but not installed. Please install PyTorch with CUDA support.\n")
+
+from . import sdf, utils  # noqa: E402,F401
+from .grid import Grid, UniformGrid  # noqa: E402,F401
+from .mc import marching_cubes  # noqa: E402,F401
+from .utils import gaussian_smooth, make_grid, write_obj  # noqa: E402,F401
+
+__all__ = [
+    "UniformGrid",
+    "gaussian_smooth",
+    "marching_cubes",
+    "make_grid",
+    "write_obj",
+]

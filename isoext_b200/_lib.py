@@ -1,0 +1,68 @@
+"""ctypes loader of the C-ABI library ``libisoext_b200.so`` (declared in include/isoext_b200.h).
+
+There is no CPU fallback and no alternative backend: if the CUDA library is missing or a call
+fails, this module raises.  Nothing under ``oracle/`` is ever imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libisoext_b200.so"
+
+E_CAPACITY = -4
+E_METHOD = -5
+
+_i64, _f32, _sz, _vp, _int = C.c_int64, C.c_float, C.c_size_t, C.c_void_p, C.c_int
+_f3 = C.POINTER(C.c_float)
+_pi64 = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); mirrors include/isoext_b200.h one to one
+SIGNATURES = {
+    "isoext_last_error": (C.c_char_p, []),
+    "isoext_build_info": (C.c_char_p, []),
+    "isoext_abi_version": (_int, []),
+    "isoext_grid_points_dense": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp]),
+    "isoext_mc_dense_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "isoext_mc_dense_scratch_bytes": (_sz, [_i64]),
+    "isoext_mc_dense_count": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
+                                     _vp, _sz, _i64, _vp, _pi64]),
+    "isoext_mc_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
+                                    _vp, _sz, _i64, _vp, _sz, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
+    "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises ImportError with build instructions if it is absent."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} not found: the sm_100a CUDA library has not been built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` (or `make -C isoext_b200/csrc`). "
+                "isoext_b200 has no CPU fallback.")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().isoext_last_error().decode()
+
+
+def check(rc: int) -> None:
+    """Raise RuntimeError (the class the reference's std::runtime_error maps to) on failure."""
+    if rc != 0:
+        raise RuntimeError(last_error() or f"isoext_b200 call failed with status {rc}")
+
+
+def f3(values):
+    a = (C.c_float * 3)(*[float(v) for v in values])
+    return a

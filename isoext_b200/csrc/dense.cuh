@@ -1,0 +1,298 @@
+// dense.cuh -- shared front end of the dense-grid pipelines (marching cubes, intersections, DC).
+//
+// Replaces, without materialising points (12 B/pt) or cells (32 B/cell), the reference's
+//   get_values/get_points/get_cells + get_case_num_op + remove_if compaction
+//   (src/mc/mc.cu:19-42, src/its.cu:94-126, include/utils.cuh:32-102 of the reference).
+//
+// Data layout in HBM
+//   values    (X,Y,Z) f32, z fastest (index = x*Y*Z + y*Z + z)          caller-owned, read ONCE by k_signbits
+//   bits      1 bit per point, flat (bit n <-> point n): [values[n] - level < 0]      P/8 bytes
+//   entries   ordered list of "active points": a point is active if the cell whose corner 0 it is
+//             crosses the surface, or if it owns (+z,+y,+x edge from it) a sign-change edge.
+//             uint2 { row = x*Y + y,  z | case<<16 | own<<24 | cellvalid<<27 }             8 B each
+//   row_start first entry of every point row (x,y), X*Y+1 u32: the only neighbour-lookup structure
+//             (an edge shared by 4 cells is owned by exactly one entry; no hash pass, no dense map)
+#pragma once
+#include "common.cuh"
+
+namespace isx {
+
+// counters (u32) shared by the pipelines
+enum Counter : int {
+    C_TICKET_A = 0,   // k_compact tiles
+    C_S = 1,          // number of entries
+    C_TICKET_B = 2,   // entry scan tiles
+    C_T = 3,          // triangles
+    C_VC = 4,         // vertex candidates (edge-unique, before positional welding)
+    C_TICKET_C = 5,   // unique scan tiles
+    C_V = 6,          // welded vertices
+    C_NLO = 7,        // welded vertices with x <  slab lower threshold
+    C_NHI = 8,        // welded vertices with x <  slab upper threshold
+    C_I = 9,          // intersections (DC)
+    C_Q = 10,         // quads (DC)
+    C_TICKET_D = 11,
+    C_TICKET_E = 12,
+    C_COUNT = 16
+};
+
+struct DenseParams {
+    Geom g;
+    i64 P;       // X*Y*Z
+    i64 YZ;      // Y*Z
+    u32 CPR;     // 32-point chunks per row
+    u32 NQ;      // total chunks = X*Y*CPR
+    u32 R;       // rows = X*Y
+    float level;
+    u32 emit_lo, emit_hi;   // local cell-x range [lo,hi) whose faces / quads are emitted
+};
+
+constexpr u32 ENT_Z_MASK = 0xffffu;
+__device__ __forceinline__ u32 ent_z(u32 w) { return w & ENT_Z_MASK; }
+__device__ __forceinline__ u32 ent_case(u32 w) { return (w >> 16) & 0xffu; }
+__device__ __forceinline__ u32 ent_own(u32 w) { return (w >> 24) & 7u; }   // bit0 +z, bit1 +y, bit2 +x
+__device__ __forceinline__ u32 ent_cell(u32 w) { return (w >> 27) & 1u; }
+
+// corner pairs of the 12 cell edges (cell convention of the reference, include/shared_luts.cuh:3-38);
+// constexpr so that unrolled loops over e fold them to immediates
+__host__ __device__ constexpr int edge_c0(int e) {
+    constexpr int t[12] = {0, 1, 2, 0, 4, 5, 6, 4, 0, 1, 3, 2};
+    return t[e];
+}
+__host__ __device__ constexpr int edge_c1(int e) {
+    constexpr int t[12] = {1, 3, 3, 2, 5, 7, 7, 6, 4, 5, 7, 6};
+    return t[e];
+}
+
+// sign-change mask of the 12 edges for a case (== the reference's edge_status_table, see tools/gen_luts.py)
+__device__ __forceinline__ u32 edge_mask_of_case(u32 c) {
+    u32 m = 0;
+#pragma unroll
+    for (int e = 0; e < 12; e++) {
+        m |= (((c >> edge_c0(e)) ^ (c >> edge_c1(e))) & 1u) << e;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: values -> sign bits.  The one volume-sized HBM stream of the whole pipeline (4 B/voxel read,
+// 1/8 B/voxel written).  Each lane loads one float4 (a warp covers 128 consecutive z, 512 B,
+// fully coalesced), builds a nibble, and 8-lane OR-reductions assemble 32-bit words.
+// ---------------------------------------------------------------------------------------------
+constexpr int SB_UNROLL = 4;
+
+__device__ __forceinline__ u32 nibble_of(float4 a, float level) {
+    return (u32) (__fsub_rn(a.x, level) < 0.0f) | ((u32) (__fsub_rn(a.y, level) < 0.0f) << 1) |
+           ((u32) (__fsub_rn(a.z, level) < 0.0f) << 2) | ((u32) (__fsub_rn(a.w, level) < 0.0f) << 3);
+}
+__device__ __forceinline__ u32 gather_word(u32 nib, u32 lane) {
+    u32 w = nib << (4 * (lane & 7));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    return w;
+}
+
+__global__ void __launch_bounds__(256) k_signbits(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level) {
+    const u32 lane = threadIdx.x & 31;
+    const i64 ngroups = P >> 7;   // full groups of 128 points
+    const i64 nwarps = ((i64) gridDim.x * blockDim.x) >> 5;
+    const i64 wg = ((i64) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (i64 g = wg * SB_UNROLL; g < ngroups; g += nwarps * SB_UNROLL) {
+        float4 a[SB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SB_UNROLL; u++)
+            if (g + u < ngroups) a[u] = ld_stream_f4(v + ((g + u) << 7) + lane * 4);
+#pragma unroll
+        for (int u = 0; u < SB_UNROLL; u++)
+            if (g + u < ngroups) {
+                u32 w = gather_word(nibble_of(a[u], level), lane);
+                if ((lane & 7) == 0) bits[((g + u) << 2) + (lane >> 3)] = w;
+            }
+    }
+    // tail group (possibly empty) + one zero group of padding so that readers may over-fetch
+    if (wg == 0) {
+        i64 base = ngroups << 7;
+        u32 nib = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            i64 i = base + lane * 4 + k;
+            if (i < P) nib |= (u32) (__fsub_rn(v[i], level) < 0.0f) << k;
+        }
+        u32 w = gather_word(nib, lane);
+        if ((lane & 7) == 0) {
+            bits[(ngroups << 2) + (lane >> 3)] = w;
+            bits[((ngroups + 1) << 2) + (lane >> 3)] = 0u;
+        }
+    }
+}
+static inline size_t signbits_words(i64 P) { return (size_t) (((P >> 7) + 2) << 2); }
+
+// bits n..n+31 -> b0 ; bits n+1..n+32 -> b1
+__device__ __forceinline__ void fetch33(const u32 *__restrict__ bits, i64 n, u32 &b0, u32 &b1) {
+    const i64 w = n >> 5;
+    const u32 sh = (u32) n & 31u;
+    u32 w0 = __ldg(bits + w), w1 = __ldg(bits + w + 1), w2 = __ldg(bits + w + 2);
+    b0 = __funnelshift_r(w0, w1, sh);
+    u32 hi = __funnelshift_r(w1, w2, sh);
+    b1 = (b0 >> 1) | (hi << 31);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: sign bits -> ordered entry list + row_start, in ONE pass (decoupled look-back scan).
+// One thread per 32-point chunk of a row; warp-free bit tricks give the active-cell mask and the
+// owned sign-change edges of 32 points at once.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
+                                                 u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
+                                                 u32 *__restrict__ counters) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_A], 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 q = tile * 256u + threadIdx.x;
+    const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    u32 m = 0, a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, ez = 0, ey = 0, ex = 0, cellact = 0;
+    u32 r = 0, c = 0, z0 = 0;
+    if (q < p.NQ) {
+        r = q / p.CPR;
+        c = q - r * p.CPR;
+        const u32 x = r / Y, y = r - x * Y;
+        z0 = c * 32u;
+        const i64 n0 = (i64) r * Z + z0;
+        const u32 nvalid = min(32u, Z - z0);              // points of this chunk inside the row
+        const u32 nv1 = min(32u, Z - z0 - 1u);            // ... that also have a z+1 neighbour
+        const u32 mz = nvalid == 32u ? 0xffffffffu : ((1u << nvalid) - 1u);
+        const u32 mz1 = nv1 == 32u ? 0xffffffffu : ((1u << nv1) - 1u);
+        const bool hasY = y + 1u < Y, hasX = x + 1u < X;
+        fetch33(bits, n0, a0, a1);
+        ez = (a0 ^ a1) & mz1;
+        if (hasY) {
+            fetch33(bits, n0 + Z, b0, b1);
+            ey = (a0 ^ b0) & mz;
+        }
+        if (hasX) {
+            fetch33(bits, n0 + p.YZ, c0, c1);
+            ex = (a0 ^ c0) & mz;
+        }
+        if (hasX && hasY) {
+            fetch33(bits, n0 + p.YZ + Z, d0, d1);
+            u32 any = a0 | a1 | b0 | b1 | c0 | c1 | d0 | d1;
+            u32 all = a0 & a1 & b0 & b1 & c0 & c1 & d0 & d1;
+            cellact = any & ~all & mz1;
+        }
+        m = cellact | ez | ey | ex;
+    }
+    const u32 cnt = __popc(m);
+    u32 total;
+    const u32 excl = block_exclusive_scan(cnt, &total, sw);
+    if (threadIdx.x < 32) {
+        u32 pre = lookback_exclusive(desc, 1, tile, total, 1u);
+        if (threadIdx.x == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    u32 off = s_prefix + excl;
+    if (q < p.NQ) {
+        if (c == 0) row_start[r] = off;
+        if (q == p.NQ - 1) {
+            row_start[p.R] = off + cnt;
+            counters[C_S] = off + cnt;
+        }
+        const bool cellrow = (r / Y + 1u < X) && (r % Y + 1u < Y);
+        while (m) {
+            const u32 k = __ffs(m) - 1;
+            m &= m - 1;
+            if (off < cap) {
+                u32 cs = ((a0 >> k) & 1u) | (((a1 >> k) & 1u) << 1) | (((b0 >> k) & 1u) << 2) | (((b1 >> k) & 1u) << 3) |
+                         (((c0 >> k) & 1u) << 4) | (((c1 >> k) & 1u) << 5) | (((d0 >> k) & 1u) << 6) | (((d1 >> k) & 1u) << 7);
+                u32 own = ((ez >> k) & 1u) | (((ey >> k) & 1u) << 1) | (((ex >> k) & 1u) << 2);
+                u32 cv = (cellrow && (z0 + k + 1u < Z)) ? 1u : 0u;
+                entries[off] = make_uint2(r, (z0 + k) | (cs << 16) | (own << 24) | (cv << 27));
+            }
+            off++;
+        }
+    }
+}
+
+// first entry of row [lo,hi) whose z is >= z
+__device__ __forceinline__ u32 row_lower_bound(const uint2 *__restrict__ entries, u32 lo, u32 hi, u32 z) {
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (ent_z(entries[mid].y) < z) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Cell-local data: 8 corner values + the 6 axis positions.
+struct CellData {
+    float v[8];
+    float px[2], py[2], pz[2];
+};
+
+__device__ __forceinline__ void load_cell(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, CellData &c) {
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 x = r / Y, y = r - x * Y;
+    const i64 n = (i64) r * Z + z;
+    c.v[0] = __ldg(values + n);
+    c.v[1] = __ldg(values + n + 1);
+    c.v[2] = __ldg(values + n + Z);
+    c.v[3] = __ldg(values + n + Z + 1);
+    c.v[4] = __ldg(values + n + p.YZ);
+    c.v[5] = __ldg(values + n + p.YZ + 1);
+    c.v[6] = __ldg(values + n + p.YZ + Z);
+    c.v[7] = __ldg(values + n + p.YZ + Z + 1);
+    const u32 xg = x + (u32) p.g.x_off;
+    c.px[0] = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+    c.px[1] = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+    c.py[0] = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
+    c.py[1] = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
+    c.pz[0] = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
+    c.pz[1] = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
+}
+
+// position of the iso-crossing on cell edge e (exact reference arithmetic, see common.cuh)
+__device__ __forceinline__ void cell_edge_point(const CellData &c, int e, float level, float &ox, float &oy, float &oz) {
+    const int p0 = edge_c0(e), p1 = edge_c1(e);
+    const float t = edge_t(c.v[p0], c.v[p1], level);
+    ox = lerp_ref(t, c.px[(p0 >> 2) & 1], c.px[(p1 >> 2) & 1]);
+    oy = lerp_ref(t, c.py[(p0 >> 1) & 1], c.py[(p1 >> 1) & 1]);
+    oz = lerp_ref(t, c.pz[p0 & 1], c.pz[p1 & 1]);
+}
+
+// Owner entry + axis of each of the 12 edges of the cell at entry s.
+//   lbY / lbX / lbXY: lower bounds of z in rows (x,y+1), (x+1,y), (x+1,y+1).
+// slot id = 3*entry + axis (axis: 0 = +z, 1 = +y, 2 = +x).  Only meaningful for sign-change edges.
+__device__ __forceinline__ void cell_edge_slots(const uint2 *__restrict__ entries, u32 s, u32 z, u32 lbY, u32 lbX, u32 lbXY,
+                                                u32 n_entries, u32 slot[12]) {
+    const u32 iY1 = lbY + ((lbY < n_entries && ent_z(entries[lbY].y) == z) ? 1u : 0u);
+    const u32 iX1 = lbX + ((lbX < n_entries && ent_z(entries[lbX].y) == z) ? 1u : 0u);
+    slot[0] = 3 * s + 0;        // e0  v0-v1  +z from corner 0
+    slot[3] = 3 * s + 1;        // e3  v0-v2  +y from corner 0
+    slot[8] = 3 * s + 2;        // e8  v0-v4  +x from corner 0
+    slot[1] = 3 * (s + 1) + 1;  // e1  v1-v3  +y from corner 1 (x,y,z+1): the next entry of the row
+    slot[9] = 3 * (s + 1) + 2;  // e9  v1-v5  +x from corner 1
+    slot[2] = 3 * lbY + 0;      // e2  v2-v3  +z from corner 2 (x,y+1,z)
+    slot[11] = 3 * lbY + 2;     // e11 v2-v6  +x from corner 2
+    slot[10] = 3 * iY1 + 2;     // e10 v3-v7  +x from corner 3 (x,y+1,z+1)
+    slot[4] = 3 * lbX + 0;      // e4  v4-v5  +z from corner 4 (x+1,y,z)
+    slot[7] = 3 * lbX + 1;      // e7  v4-v6  +y from corner 4
+    slot[5] = 3 * iX1 + 1;      // e5  v5-v7  +y from corner 5 (x+1,y,z+1)
+    slot[6] = 3 * lbXY + 0;     // e6  v6-v7  +z from corner 6 (x+1,y+1,z)
+}
+
+// grid point positions, (X,Y,Z,3) f32 -- replaces get_vtx_pos_op (include/utils.cuh:62-80)
+__global__ void __launch_bounds__(256) k_grid_points(Geom g, float *__restrict__ out) {
+    const i64 P = g.X * g.Y * g.Z;
+    const u32 Y = (u32) g.Y, Z = (u32) g.Z;
+    for (i64 n = (i64) blockIdx.x * blockDim.x + threadIdx.x; n < P; n += (i64) gridDim.x * blockDim.x) {
+        u32 z = (u32) (n % Z);
+        i64 r = n / Z;
+        u32 y = (u32) (r % Y), x = (u32) (r / Y);
+        float *o = out + 3 * n;
+        o[0] = axis_pos(x + (u32) g.x_off, (u32) g.Xg - 1, g.amin[0], g.asize[0]);
+        o[1] = axis_pos(y, Y - 1, g.amin[1], g.asize[1]);
+        o[2] = axis_pos(z, Z - 1, g.amin[2], g.asize[2]);
+    }
+}
+
+}   // namespace isx

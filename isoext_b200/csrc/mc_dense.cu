@@ -1,0 +1,528 @@
+// mc_dense.cu -- dense-grid marching cubes for sm_100a.
+//
+// Replaces mc::marching_cubes on a UniformGrid (src/mc/mc.cu:17-68, src/mc/nagae.cu:34-102,
+// src/mc/lorensen.cu:34-103, src/utils.cu:32-59 of the reference) with:
+//   k_signbits   (dense.cuh)  one streaming read of the field, 4 B/voxel            [HBM-bound]
+//   k_compact    (dense.cuh)  bit-parallel active-point compaction, look-back scan
+//   k_cell_tris               per active cell: edge crossings, LUT triangles, degenerate drop,
+//                             marks the edge-owned vertex slots that a kept triangle references
+//   k_scan_entries            look-back scan: triangle offsets + vertex candidate ids
+//   k_cand_pos                one position per used edge slot (edge-keyed welding, no hash pass)
+//   radix_sort96 (radix.cuh)  reference vertex order = lexicographic (x,y,z) of positions
+//   k_unique                  positional welding of candidates that snapped onto a shared corner
+//   k_emit_faces              LUT-driven face emission with final vertex ids
+// Every arithmetic step that decides a bit of the output uses explicit _rn intrinsics.
+#include "dense.cuh"
+#include "radix.cuh"
+
+#include <cstring>
+
+#define ISX_LUT_QUAL __device__
+#include "mc_luts.inc"
+
+namespace isx {
+
+__device__ __forceinline__ u64 tri_word(int method, u32 cs) {
+    return method == 0 ? kTriWords_nagae[cs] : kTriWords_lorensen[cs];
+}
+
+struct McBuffers {
+    // phase 1 (sized by the grid and the entry capacity)
+    u32 *bits;
+    u32 *row_start;
+    u64 *descA;
+    u32 *counters;
+    uint2 *entries;
+    u32 *nb;            // 3 per entry: lower bounds in rows (x,y+1), (x+1,y), (x+1,y+1)
+    unsigned char *ntri, *trimask;
+    unsigned char *used;   // 3 per entry
+    u32 *tri_off, *cand_info;
+    u64 *descT, *descU;
+};
+
+static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *out) {
+    McBuffers b;
+    b.counters = c.take<u32>(C_COUNT);
+    b.bits = c.take<u32>(signbits_words(p.P));
+    b.row_start = c.take<u32>((size_t) p.R + 2);
+    b.descA = c.take<u64>((size_t) (p.NQ + 255) / 256 + 1);
+    b.entries = c.take<uint2>(cap + 1);
+    b.nb = c.take<u32>(3 * cap);
+    b.ntri = c.take<unsigned char>(cap);
+    b.trimask = c.take<unsigned char>(cap);
+    b.used = c.take<unsigned char>(3 * (cap + 2));
+    b.tri_off = c.take<u32>(cap);
+    b.cand_info = c.take<u32>(cap + 1);
+    b.descT = c.take<u64>((cap + 255) / 256 + 1);
+    b.descU = c.take<u64>((cap + 255) / 256 + 1);
+    if (out) *out = b;
+    return c.bytes();
+}
+
+struct McScratch {
+    u32 *kx, *ky, *kz;
+    u32 *cand_rank;
+    u64 *descV;
+    RadixBuffers radix;
+};
+
+static size_t carve_mc_scratch(Carver &c, size_t nc, McScratch *out) {
+    McScratch s;
+    s.kx = c.take<u32>(nc);
+    s.ky = c.take<u32>(nc);
+    s.kz = c.take<u32>(nc);
+    s.cand_rank = c.take<u32>(nc);
+    s.descV = c.take<u64>((nc + 255) / 256 + 1);
+    RadixBuffers::carve(c, nc, &s.radix);
+    if (out) *out = s;
+    return c.bytes();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: one thread per entry that is a valid cell.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ values, DenseParams p, int method,
+                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ row_start,
+                                                   u32 cap, const u32 *__restrict__ counters, u32 *__restrict__ nb,
+                                                   unsigned char *__restrict__ ntri, unsigned char *__restrict__ trimask,
+                                                   unsigned char *__restrict__ used) {
+    const u32 S = counters[C_S];
+    if (S > cap) return;
+    const u32 Y = (u32) p.g.Y;
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const uint2 e = entries[s];
+        const u32 w = e.y;
+        if (!ent_cell(w) || ent_case(w) == 0u || ent_case(w) == 255u) {
+            ntri[s] = 0;
+            trimask[s] = 0;
+            continue;
+        }
+        const u32 r = e.x, z = ent_z(w), cs = ent_case(w);
+        const u32 lbY = row_lower_bound(entries, row_start[r + 1], row_start[r + 2], z);
+        const u32 lbX = row_lower_bound(entries, row_start[r + Y], row_start[r + Y + 1], z);
+        const u32 lbXY = row_lower_bound(entries, row_start[r + Y + 1], row_start[r + Y + 2], z);
+        nb[3 * s + 0] = lbY;
+        nb[3 * s + 1] = lbX;
+        nb[3 * s + 2] = lbXY;
+
+        CellData c;
+        load_cell(values, p, r, z, c);
+        const u32 status = edge_mask_of_case(cs);
+        float ex[12], ey[12], ez[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++)
+            if ((status >> k) & 1u) cell_edge_point(c, k, p.level, ex[k], ey[k], ez[k]);
+        u32 slot[12];
+        cell_edge_slots(entries, s, z, lbY, lbX, lbXY, S, slot);
+
+        const u64 word = tri_word(method, cs);
+        const u32 nt = (u32) (word >> 60);
+        u32 mask = 0, cnt = 0;
+        for (u32 k = 0; k < nt; k++) {
+            const u32 a = (u32) (word >> (12 * k)) & 15u, b = (u32) (word >> (12 * k + 4)) & 15u,
+                      d = (u32) (word >> (12 * k + 8)) & 15u;
+            // reference drops a triangle when two corners are bit-equal (src/mc/nagae.cu:71)
+            const bool ab = ex[a] != ex[b] || ey[a] != ey[b] || ez[a] != ez[b];
+            const bool ad = ex[a] != ex[d] || ey[a] != ey[d] || ez[a] != ez[d];
+            const bool bd = ex[b] != ex[d] || ey[b] != ey[d] || ez[b] != ez[d];
+            if (ab && ad && bd) {
+                mask |= 1u << k;
+                cnt++;
+                used[slot[a]] = 1;
+                used[slot[b]] = 1;
+                used[slot[d]] = 1;
+            }
+        }
+        const u32 x = r / Y;
+        const bool emit = x >= p.emit_lo && x < p.emit_hi;
+        ntri[s] = emit ? (unsigned char) cnt : 0;
+        trimask[s] = emit ? (unsigned char) mask : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: exclusive scans over the entries (triangle offsets, candidate ids), persistent + look-back.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__ counters, const unsigned char *__restrict__ ntri,
+                                                      const unsigned char *__restrict__ used, u32 *__restrict__ tri_off,
+                                                      u32 *__restrict__ cand_info, u64 *__restrict__ descT, u64 *__restrict__ descU) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_tile, s_preT, s_preU;
+    const u32 S = counters[C_S];
+    if (S > cap) return;
+    const u32 ntiles = (S + 255) / 256;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_B], 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u32 s = tile * 256 + threadIdx.x;
+        u32 nt = 0, um = 0;
+        if (s < S) {
+            nt = ntri[s];
+            um = (used[3 * s] ? 1u : 0u) | (used[3 * s + 1] ? 2u : 0u) | (used[3 * s + 2] ? 4u : 0u);
+        }
+        const u32 nu = __popc(um);
+        u32 totT, totU;
+        const u32 exT = block_exclusive_scan(nt, &totT, sw);
+        const u32 exU = block_exclusive_scan(nu, &totU, sw);
+        const u32 warp = threadIdx.x >> 5;
+        if (warp == 0) {
+            u32 pre = lookback_exclusive(descT, 1, tile, totT, 1u);
+            if (threadIdx.x == 0) s_preT = pre;
+        } else if (warp == 1) {
+            u32 pre = lookback_exclusive(descU, 1, tile, totU, 1u);
+            if ((threadIdx.x & 31) == 0) s_preU = pre;
+        }
+        __syncthreads();
+        if (s < S) {
+            tri_off[s] = s_preT + exT;
+            cand_info[s] = (s_preU + exU) | (um << 29);
+            if (s == S - 1) {
+                counters[C_T] = s_preT + exT + nt;
+                counters[C_VC] = s_preU + exU + nu;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: positions (as sortable keys) of the used edge slots, computed once by the owning entry.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
+                                                  const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
+                                                  const u32 *__restrict__ cand_info, u32 *__restrict__ kx,
+                                                  u32 *__restrict__ ky, u32 *__restrict__ kz) {
+    const u32 S = counters[C_S];
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const u32 ci = cand_info[s];
+        const u32 um = ci >> 29;
+        if (!um) continue;
+        u32 id = ci & 0x1fffffffu;
+        const uint2 e = entries[s];
+        const u32 r = e.x, z = ent_z(e.y);
+        const u32 x = r / Y, y = r - x * Y;
+        const i64 n = (i64) r * Z + z;
+        const float v0 = __ldg(values + n);
+        const u32 xg = x + (u32) p.g.x_off;
+        const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+        const float py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
+        const float pz0 = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
+        if (um & 1u) {   // +z edge
+            const float t = edge_t(v0, __ldg(values + n + 1), p.level);
+            const float pz1 = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
+            kx[id] = float_key(lerp_ref(t, px0, px0));
+            ky[id] = float_key(lerp_ref(t, py0, py0));
+            kz[id] = float_key(lerp_ref(t, pz0, pz1));
+            id++;
+        }
+        if (um & 2u) {   // +y edge
+            const float t = edge_t(v0, __ldg(values + n + Z), p.level);
+            const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
+            kx[id] = float_key(lerp_ref(t, px0, px0));
+            ky[id] = float_key(lerp_ref(t, py0, py1));
+            kz[id] = float_key(lerp_ref(t, pz0, pz0));
+            id++;
+        }
+        if (um & 4u) {   // +x edge
+            const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
+            const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+            kx[id] = float_key(lerp_ref(t, px0, px1));
+            ky[id] = float_key(lerp_ref(t, py0, py0));
+            kz[id] = float_key(lerp_ref(t, pz0, pz0));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: weld = unique over the sorted candidates (look-back scan of "differs from predecessor").
+// Also counts how many welded vertices lie below the slab thresholds (multi-GPU ownership).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restrict__ perm, const u32 *__restrict__ kx,
+                                                const u32 *__restrict__ ky, const u32 *__restrict__ kz,
+                                                u32 *__restrict__ cand_rank, float *__restrict__ V, u32 *__restrict__ counters,
+                                                u64 *__restrict__ desc, u32 key_lo, u32 key_hi) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_tile, s_pre;
+    const u32 ntiles = (n + 255) / 256;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_C], 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u32 i = tile * 256 + threadIdx.x;
+        u32 isnew = 0, c = 0, x = 0, y = 0, z = 0;
+        if (i < n) {
+            c = perm[i];
+            x = kx[c]; y = ky[c]; z = kz[c];
+            if (i == 0) isnew = 1;
+            else {
+                const u32 pc = perm[i - 1];
+                isnew = (kx[pc] != x || ky[pc] != y || kz[pc] != z) ? 1u : 0u;
+            }
+        }
+        u32 tot;
+        const u32 ex = block_exclusive_scan(isnew, &tot, sw);
+        if (threadIdx.x < 32) {
+            u32 pre = lookback_exclusive(desc, 1, tile, tot, 1u);
+            if (threadIdx.x == 0) s_pre = pre;
+        }
+        // per-warp counts of new vertices under the thresholds
+        const u32 blo = __ballot_sync(0xffffffffu, isnew && x < key_lo);
+        const u32 bhi = __ballot_sync(0xffffffffu, isnew && x < key_hi);
+        if ((threadIdx.x & 31) == 0) {
+            if (blo) atomicAdd(&counters[C_NLO], (u32) __popc(blo));
+            if (bhi) atomicAdd(&counters[C_NHI], (u32) __popc(bhi));
+        }
+        __syncthreads();
+        if (i < n) {
+            const u32 rank = s_pre + ex + isnew - 1;
+            cand_rank[c] = rank;
+            if (isnew) {
+                V[3 * (size_t) rank + 0] = key_float(x);
+                V[3 * (size_t) rank + 1] = key_float(y);
+                V[3 * (size_t) rank + 2] = key_float(z);
+            }
+            if (i == n - 1) counters[C_V] = rank + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: faces.  One thread per emitting cell; triangle k of the LUT row goes to tri_off[s] + (#kept before k).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, const uint2 *__restrict__ entries,
+                                                    const u32 *__restrict__ counters, const u32 *__restrict__ nb,
+                                                    const unsigned char *__restrict__ trimask, const u32 *__restrict__ tri_off,
+                                                    const u32 *__restrict__ cand_info, const u32 *__restrict__ cand_rank,
+                                                    int *__restrict__ F) {
+    const u32 S = counters[C_S];
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const u32 mask = trimask[s];
+        if (!mask) continue;
+        const uint2 e = entries[s];
+        const u32 z = ent_z(e.y), cs = ent_case(e.y);
+        u32 slot[12];
+        cell_edge_slots(entries, s, z, nb[3 * s], nb[3 * s + 1], nb[3 * s + 2], S, slot);
+        const u64 word = tri_word(method, cs);
+        const u32 nt = (u32) (word >> 60);
+        size_t o = 3 * (size_t) tri_off[s];
+        for (u32 k = 0; k < nt; k++) {
+            if (!((mask >> k) & 1u)) continue;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const u32 edge = (u32) (word >> (12 * k + 4 * j)) & 15u;
+                const u32 sl = slot[edge];
+                const u32 ent = sl / 3, axis = sl - 3 * ent;
+                const u32 ci = cand_info[ent];
+                const u32 cand = (ci & 0x1fffffffu) + __popc((ci >> 29) & ((1u << axis) - 1u));
+                F[o + j] = (int) cand_rank[cand];
+            }
+            o += 3;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int make_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin, const float *amax, float level,
+                       i64 emit_lo, i64 emit_hi, DenseParams *out) {
+    if (X < 1 || Y < 1 || Z < 1) return fail(E_INVALID, "grid shape must be positive");
+    if (Z > 65535) return fail(E_INVALID, "Z (points along the last axis) must be <= 65535");
+    if (X * Y >= (i64) 1 << 31) return fail(E_INVALID, "X*Y must be < 2^31");
+    DenseParams p;
+    p.g.X = X; p.g.Y = Y; p.g.Z = Z;
+    p.g.x_off = x_off;
+    p.g.Xg = Xg;
+    for (int a = 0; a < 3; a++) {
+        p.g.amin[a] = amin[a];
+        p.g.asize[a] = amax[a] - amin[a];   // float subtraction, as the reference does on the host
+    }
+    p.P = X * Y * Z;
+    p.YZ = Y * Z;
+    p.CPR = (u32) ((Z + 31) / 32);
+    i64 nq = X * Y * (i64) p.CPR;
+    if (nq >= (i64) 1 << 31) return fail(E_INVALID, "grid too large for one slab (X*Y*ceil(Z/32) must be < 2^31)");
+    p.NQ = (u32) nq;
+    p.R = (u32) (X * Y);
+    p.level = level;
+    p.emit_lo = (u32) (emit_lo < 0 ? 0 : emit_lo);
+    p.emit_hi = (u32) (emit_hi < 0 ? 0 : emit_hi);
+    *out = p;
+    return OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}   // namespace isx
+
+using namespace isx;
+
+extern "C" {
+
+size_t isoext_mc_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t cap_entries) {
+    DenseParams p;
+    float z3[3] = {0, 0, 0}, o3[3] = {1, 1, 1};
+    if (make_params(X, Y, Z, 0, X, z3, o3, 0.f, 0, X - 1, &p) != OK) return 0;
+    Carver c(nullptr);
+    return carve_mc(c, p, (size_t) cap_entries, nullptr);
+}
+
+size_t isoext_mc_dense_scratch_bytes(int64_t n_candidates) {
+    Carver c(nullptr);
+    return carve_mc_scratch(c, (size_t) (n_candidates > 0 ? n_candidates : 1), nullptr);
+}
+
+// Phase 1: classify + compact + per-cell triangle analysis + scans.
+// counts_out[0..2] = entries S, triangles T, vertex candidates Vc (upper bound of the vertex count).
+int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                          const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
+                          int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries,
+                          void *stream_, int64_t *counts_out) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
+    DenseParams p;
+    int rc = make_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
+    if (rc != OK) return rc;
+    if ((reinterpret_cast<uintptr_t>(values) & 15u) != 0) return fail(E_INVALID, "values must be 16-byte aligned");
+    if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
+    Carver c(workspace);
+    McBuffers b;
+    if (carve_mc(c, p, (size_t) cap_entries, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
+    const u32 cap = (u32) cap_entries;
+
+    ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
+    ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) (p.NQ + 255) / 256 + 1) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(b.descT, 0, ((size_t) (cap + 255) / 256 + 1) * sizeof(u64) , stream));
+    ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) (cap + 255) / 256 + 1) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(b.used, 0, 3 * ((size_t) cap + 2), stream));
+
+    const int sms = num_sms();
+    {
+        i64 groups = p.P >> 7;
+        i64 want = (groups + 8 * SB_UNROLL - 1) / (8 * SB_UNROLL);   // 8 warps per block
+        int blocks = (int) (want < 1 ? 1 : (want > (i64) sms * 8 ? (i64) sms * 8 : want));
+        k_signbits<<<blocks, 256, 0, stream>>>(values, b.bits, p.P, level);
+    }
+    k_compact<<<(p.NQ + 255) / 256, 256, 0, stream>>>(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+    k_cell_tris<<<sms * 8, 128, 0, stream>>>(values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+                                             b.trimask, b.used);
+    k_scan_entries<<<sms * 4, 256, 0, stream>>>(cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU);
+    ISX_CUDA(cudaGetLastError());
+    u32 h[C_COUNT];
+    ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    ISX_CUDA(cudaStreamSynchronize(stream));
+    counts_out[0] = h[C_S];
+    counts_out[1] = h[C_T];
+    counts_out[2] = h[C_VC];
+    if (h[C_S] > cap) return fail(E_CAPACITY, "entry capacity exceeded; retry with cap_entries >= counts_out[0]");
+    return OK;
+}
+
+// Phase 2: vertex positions, reference ordering, welding, faces.
+//   V: capacity counts[2] x 3 floats; F: counts[1] x 3 int32 (local vertex ids, see counts_out).
+//   x_lo_threshold / x_hi_threshold: welded vertices are classified by their x position into
+//   [-inf, lo) | [lo, hi) | [hi, +inf) -- the slab ownership rule (pass -inf / +inf on one GPU).
+//   counts_out[0..2] = welded vertices V, #with x < lo, #with x < hi.
+int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                         const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
+                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
+                         size_t scratch_bytes, int64_t n_candidates, float x_lo_threshold, float x_hi_threshold,
+                         float *V, int32_t *F, void *stream_, int64_t *counts_out) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
+    DenseParams p;
+    int rc = make_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
+    if (rc != OK) return rc;
+    Carver c(workspace);
+    McBuffers b;
+    if (carve_mc(c, p, (size_t) cap_entries, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
+    counts_out[0] = counts_out[1] = counts_out[2] = 0;
+    if (n_candidates <= 0) return OK;
+    if (n_candidates >= ((i64) 1 << 29)) return fail(E_INVALID, "too many vertex candidates for one slab (>= 2^29)");
+    Carver cs(scratch);
+    McScratch s;
+    if (carve_mc_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
+    const u32 nc = (u32) n_candidates;
+    const int sms = num_sms();
+
+    ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) (nc + 255) / 256 + 1) * sizeof(u64), stream));
+    k_cand_pos<<<sms * 8, 256, 0, stream>>>(values, p, b.entries, b.counters, b.cand_info, s.kx, s.ky, s.kz);
+    ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
+    // thresholds as keys: x < thr  <=>  key(x) < key(thr) for non-NaN values
+    u32 klo, khi;
+    {
+        auto hkey = [](float f) {
+            u32 bts;
+            memcpy(&bts, &f, 4);
+            if ((bts << 1) == 0u) bts = 0u;
+            return (bts & 0x80000000u) ? ~bts : (bts | 0x80000000u);
+        };
+        klo = hkey(x_lo_threshold);
+        khi = hkey(x_hi_threshold);
+    }
+    k_unique<<<sms * 4, 256, 0, stream>>>(nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV, klo, khi);
+    k_emit_faces<<<sms * 8, 128, 0, stream>>>(p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
+                                              s.cand_rank, F);
+    ISX_CUDA(cudaGetLastError());
+    u32 h[C_COUNT];
+    ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    ISX_CUDA(cudaStreamSynchronize(stream));
+    counts_out[0] = h[C_V];
+    counts_out[1] = h[C_NLO];
+    counts_out[2] = h[C_NHI];
+    return OK;
+}
+
+// (X,Y,Z,3) grid point positions.
+int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
+                             const float *aabb_max, float *out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Geom g;
+    g.X = X; g.Y = Y; g.Z = Z; g.x_off = x_offset; g.Xg = X_global;
+    for (int a = 0; a < 3; a++) { g.amin[a] = aabb_min[a]; g.asize[a] = aabb_max[a] - aabb_min[a]; }
+    i64 P = X * Y * Z;
+    if (P <= 0) return OK;
+    i64 want = (P + 255) / 256;
+    int blocks = (int) (want > (i64) num_sms() * 16 ? (i64) num_sms() * 16 : want);
+    k_grid_points<<<blocks, 256, 0, stream>>>(g, out);
+    ISX_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// Map local (extended-slab) vertex ids in F to global ids after the count all-gather:
+//   id <  n_lo         -> base_mine - (n_lo - id)      (owned by the previous rank: tail of its range)
+//   n_lo <= id < n_hi  -> base_mine + (id - n_lo)
+//   id >= n_hi         -> base_next + (id - n_hi)      (owned by the next rank: head of its range)
+__global__ void k_relabel_faces(int *F, i64 n, i64 n_lo, i64 n_hi, i64 base_mine, i64 base_next) {
+    for (i64 i = (i64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64) gridDim.x * blockDim.x) {
+        i64 id = F[i];
+        i64 g = id < n_lo ? base_mine - (n_lo - id) : (id < n_hi ? base_mine + (id - n_lo) : base_next + (id - n_hi));
+        F[i] = (int) g;
+    }
+}
+int isoext_relabel_faces(int32_t *F, int64_t n_ids, int64_t n_lo, int64_t n_hi, int64_t base_mine, int64_t base_next,
+                         void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_ids <= 0) return OK;
+    i64 want = (n_ids + 255) / 256;
+    int blocks = (int) (want > 148 * 16 ? 148 * 16 : want);
+    k_relabel_faces<<<blocks, 256, 0, stream>>>(F, n_ids, n_lo, n_hi, base_mine, base_next);
+    ISX_CUDA(cudaGetLastError());
+    return OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,89 @@
+"""``marching_cubes`` -- host-side mirror of the reference binding (src/isoext_ext.cu:95-109) over
+the sm_100a kernels in csrc/mc_dense.cu (dense) and csrc/sparse.cu (sparse)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .grid import UniformGrid, _stream_ptr
+
+METHODS = {"nagae": 0, "lorensen": 1}
+
+
+def _method_id(method: str) -> int:
+    if method not in METHODS:
+        raise RuntimeError("Unknown method: " + str(method))  # src/mc/base.cu:23-25
+    return METHODS[method]
+
+
+def _initial_cap(shape) -> int:
+    X, Y, Z = shape
+    return int(min(X * Y * Z, max(1 << 16, 4 * (X * Y + Y * Z + X * Z))))
+
+
+def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_id, ws, cap_hint=0, x_offset=0,
+                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf)):
+    """Run the dense pipeline on a (X,Y,Z) float32 CUDA tensor.
+
+    Returns ``(V_ext, F, n_lo, n_hi, cap_used)``: ``V_ext`` (n,3) position-sorted welded vertices of
+    the slab, ``F`` (T,3) int32 ids into ``V_ext``; ``n_lo``/``n_hi`` split ``V_ext`` by the x
+    thresholds (slab ownership; 0 and n on a single GPU).  ``(None, None, 0, 0, cap)`` if empty.
+    """
+    lib = _lib.lib()
+    X, Y, Z = shape
+    xg = X if x_global is None else x_global
+    lo, hi = (0, X - 1) if emit_range is None else emit_range
+    amin, amax = _lib.f3(aabb_min), _lib.f3(aabb_max)
+    dev = values.device
+    stream = _stream_ptr()
+    counts = (C.c_int64 * 4)()
+    cap = max(int(cap_hint), _initial_cap(shape))
+    while True:
+        nbytes = lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap)
+        if nbytes == 0:
+            raise RuntimeError(_lib.last_error())
+        wsbuf = ws.get("mc_ws", nbytes, dev)
+        rc = lib.isoext_mc_dense_count(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
+                                       lo, hi, wsbuf.data_ptr(), wsbuf.numel(), cap, stream, counts)
+        if rc == _lib.E_CAPACITY:
+            cap = int(counts[0]) + 1024
+            continue
+        _lib.check(rc)
+        break
+    S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
+    if T == 0:
+        return None, None, 0, 0, cap
+    sbytes = lib.isoext_mc_dense_scratch_bytes(Vc)
+    scratch = ws.get("mc_scratch", sbytes, dev)
+    V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
+    F = torch.empty((T, 3), dtype=torch.int32, device=dev)
+    out = (C.c_int64 * 4)()
+    _lib.check(lib.isoext_mc_dense_emit(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
+                                        lo, hi, wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(),
+                                        Vc, float(x_thresholds[0]), float(x_thresholds[1]), V.data_ptr(), F.data_ptr(),
+                                        stream, out))
+    nV, n_lo, n_hi = int(out[0]), int(out[1]), int(out[2])
+    return V[:nV], F, n_lo, n_hi, max(cap, S)
+
+
+def marching_cubes(grid, level: float = 0.0, method: str = "nagae"):
+    """Extract the ``level`` iso-surface of ``grid`` (src/isoext_ext.cu:95-109).
+
+    Returns ``(v, f)``: ``v`` (V, 3) float32 positions in the reference's order (lexicographic
+    (x, y, z) of the welded positions, src/utils.cu:49-55), ``f`` (T, 3) int32 in ascending-cell x
+    LUT order -- or ``(None, None)`` when no triangle exists (src/isoext_ext.cu:47-49).
+    """
+    mid = _method_id(method)
+    if isinstance(grid, UniformGrid):
+        with torch.cuda.device(grid.device):
+            v, f, _, _, cap = mc_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, mid, grid._ws,
+                                           cap_hint=grid._cap_hint)
+        grid._cap_hint = cap
+        return v, f
+    from .sparse import SparseGrid, mc_sparse
+    if isinstance(grid, SparseGrid):
+        return mc_sparse(grid, level, mid)
+    raise TypeError("marching_cubes: grid must be a UniformGrid or SparseGrid")

@@ -153,10 +153,11 @@ def unpack(word: int) -> list[int]:
 def emit(tables: dict[str, list[list[int]]]) -> None:
     inc = ["// GENERATED by tools/gen_luts.py -- do not edit.",
            "// One uint64 per case: nibble k (k < 15) = k-th edge id of the triangle list (0xF = none);",
-           "// bits 60..63 = number of triangles.  Method order: 0 = nagae, 1 = lorensen."]
+           "// bits 60..63 = number of triangles.  The includer defines ISX_LUT_QUAL (e.g. __device__).",
+           "#ifndef ISX_LUT_QUAL", "#define ISX_LUT_QUAL static", "#endif"]
     for name in ("nagae", "lorensen"):
         words = [pack(r) for r in tables[name]]
-        inc.append(f"static const unsigned long long kTriWords_{name}[256] = {{")
+        inc.append(f"ISX_LUT_QUAL const unsigned long long kTriWords_{name}[256] = {{")
         for i in range(0, 256, 4):
             inc.append("    " + ", ".join(f"0x{w:016x}ull" for w in words[i:i + 4]) + ",")
         inc.append("};")
