@@ -1,0 +1,90 @@
+/* isoext_b200.h -- C-ABI of libisoext_b200.so: the drop-in boundary of the B200-native
+ * iso-surface extraction core.
+ *
+ * It replaces the reference's nanobind module `isoext_ext` (src/isoext_ext.cu:93-384 of
+ * GuangyanCai/isoext v0.5.1): every entry point below names the reference interface it stands in
+ * for.  Conventions:
+ *   - plain C types only; every pointer named d_* / values / workspace / scratch / V / F is a
+ *     DEVICE pointer allocated by the caller (the Python host layer uses torch storage);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it; functions that return
+ *     counts synchronise that stream before returning (the reference is fully synchronous on the
+ *     legacy default stream);
+ *   - return value 0 = success, negative = error (ISOEXT_E_*); isoext_last_error() gives the
+ *     message (thread-local).  The reference's std::runtime_error maps to these codes and the
+ *     host layer re-raises RuntimeError with the same message text;
+ *   - two-phase protocol (count, then emit) so that the caller allocates exact-size outputs;
+ *   - grids are addressed as a local slab of a global grid (x_offset, X_global) so that the same
+ *     entry points serve the single-GPU path (x_offset = 0, X_global = X) and the slab-sharded
+ *     multi-GPU path.
+ * Index conventions are the reference's: value index = x*Y*Z + y*Z + z (src/utils.cu:21-24),
+ * cell index = x*(Y-1)*(Z-1) + y*(Z-1) + z (include/utils.cuh:43-47), corner/edge numbering of
+ * include/shared_luts.cuh:3-38, `shape` = POINTS per axis (src/grid/uniform.cu:11-12).
+ */
+#ifndef ISOEXT_B200_H
+#define ISOEXT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISOEXT_OK 0
+#define ISOEXT_E_INVALID (-1)   /* bad argument                                           */
+#define ISOEXT_E_CUDA (-2)      /* CUDA runtime error                                     */
+#define ISOEXT_E_WORKSPACE (-3) /* workspace / scratch too small                          */
+#define ISOEXT_E_CAPACITY (-4)  /* entry capacity exceeded: counts_out[0] = needed size   */
+#define ISOEXT_E_METHOD (-5)    /* unknown MC method (src/mc/base.cu:23-25)               */
+
+#define ISOEXT_METHOD_NAGAE 0    /* include/mc/nagae.cuh    (default, src/isoext_ext.cu:101) */
+#define ISOEXT_METHOD_LORENSEN 1 /* include/mc/lorensen.cuh                                  */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char *isoext_last_error(void);
+const char *isoext_build_info(void);
+int isoext_abi_version(void);
+
+/* ---- UniformGrid.get_points  (src/grid/uniform.cu:22-30, include/utils.cuh:62-80) ----------
+ * out: (X,Y,Z,3) f32.  Positions use the global index: pos_x = fma((x+x_offset)/(X_global-1), ...). */
+int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                             const float *aabb_min, const float *aabb_max, float *d_out, void *stream);
+
+/* ---- marching_cubes on a UniformGrid  (src/mc/mc.cu:17-68, src/isoext_ext.cu:95-109) --------
+ * workspace_bytes: size of the phase-1 workspace for a slab of X*Y*Z points and at most
+ * cap_entries active points.  scratch_bytes: size of the phase-2 scratch for n_candidates. */
+size_t isoext_mc_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t cap_entries);
+size_t isoext_mc_dense_scratch_bytes(int64_t n_candidates);
+
+/* Phase 1.  values: (X,Y,Z) f32, 16-byte aligned, read exactly once from HBM.
+ * emit_x_lo/hi: local cell-x range [lo,hi) whose triangles are emitted (whole slab: 0, X-1);
+ * cells outside it still decide which shared-plane vertices exist (slab halo layers).
+ * counts_out[0..2] = active entries S, triangles T, vertex candidates Vc (>= welded vertex count). */
+int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                          const float *aabb_min, const float *aabb_max, float level, int method,
+                          int64_t emit_x_lo, int64_t emit_x_hi, void *workspace, size_t workspace_bytes,
+                          int64_t cap_entries, void *stream, int64_t *counts_out);
+
+/* Phase 2 (same arguments + the phase-1 workspace untouched in between).
+ * V: capacity Vc x 3 f32, receives the welded vertices in the reference's order (lexicographic
+ * (x,y,z), src/utils.cu:49-55).  F: T x 3 int32 ids into V, in ascending-cell x LUT order.
+ * x_lo_threshold / x_hi_threshold classify V by x position for slab ownership
+ * (-INFINITY / +INFINITY on a single GPU).
+ * counts_out[0..2] = welded vertices, #vertices with x < lo, #vertices with x < hi. */
+int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                         const float *aabb_min, const float *aabb_max, float level, int method,
+                         int64_t emit_x_lo, int64_t emit_x_hi, void *workspace, size_t workspace_bytes,
+                         int64_t cap_entries, void *scratch, size_t scratch_bytes, int64_t n_candidates,
+                         float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
+                         int64_t *counts_out);
+
+/* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
+ * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->
+ * base_mine + (id - n_lo); id >= n_hi -> base_next + (id - n_hi). */
+int isoext_relabel_faces(int32_t *F, int64_t n_ids, int64_t n_lo, int64_t n_hi, int64_t base_mine,
+                         int64_t base_next, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISOEXT_B200_H */

@@ -1,7 +1,7 @@
 """ctypes loader of the C-ABI library ``libisoext_b200.so`` (declared in include/isoext_b200.h).
 
 There is no CPU fallback and no alternative backend: if the CUDA library is missing or a call
-fails, this module raises.  Nothing under ``oracle/`` is ever imported from here.
+fails, this module raises.  The test-only checker package is never imported from here.
 """
 from __future__ import annotations
 

@@ -142,6 +142,50 @@ __device__ __forceinline__ void fetch33(const u32 *__restrict__ bits, i64 n, u32
 // One thread per 32-point chunk of a row; warp-free bit tricks give the active-cell mask and the
 // owned sign-change edges of 32 points at once.
 // ---------------------------------------------------------------------------------------------
+constexpr int CP_ITEMS = 8;                 // consecutive 32-point chunks per thread
+constexpr int CP_TILE = 256 * CP_ITEMS;     // chunks per block
+
+struct ChunkBits {
+    u32 a0, a1, b0, b1, c0, c1, d0, d1;   // sign bits of rows (x,y),(x,y+1),(x+1,y),(x+1,y+1) at z / z+1
+    u32 ez, ey, ex, cellact;              // owned sign-change edges, active cells
+    u32 r, z0;
+    bool cellrow;
+};
+
+__device__ __forceinline__ u32 chunk_classify(const u32 *__restrict__ bits, const DenseParams &p, u32 q, ChunkBits &k) {
+    const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    k.a0 = k.a1 = k.b0 = k.b1 = k.c0 = k.c1 = k.d0 = k.d1 = 0;
+    k.ez = k.ey = k.ex = k.cellact = 0;
+    k.r = q / p.CPR;
+    const u32 c = q - k.r * p.CPR;
+    const u32 x = k.r / Y, y = k.r - x * Y;
+    k.z0 = c * 32u;
+    const i64 n0 = (i64) k.r * Z + k.z0;
+    const u32 nvalid = min(32u, Z - k.z0);            // points of this chunk inside the row
+    const u32 nv1 = min(32u, Z - k.z0 - 1u);          // ... that also have a z+1 neighbour
+    const u32 mz = nvalid == 32u ? 0xffffffffu : ((1u << nvalid) - 1u);
+    const u32 mz1 = nv1 == 32u ? 0xffffffffu : ((1u << nv1) - 1u);
+    const bool hasY = y + 1u < Y, hasX = x + 1u < X;
+    k.cellrow = hasX && hasY;
+    fetch33(bits, n0, k.a0, k.a1);
+    k.ez = (k.a0 ^ k.a1) & mz1;
+    if (hasY) {
+        fetch33(bits, n0 + Z, k.b0, k.b1);
+        k.ey = (k.a0 ^ k.b0) & mz;
+    }
+    if (hasX) {
+        fetch33(bits, n0 + p.YZ, k.c0, k.c1);
+        k.ex = (k.a0 ^ k.c0) & mz;
+    }
+    if (hasX && hasY) {
+        fetch33(bits, n0 + p.YZ + Z, k.d0, k.d1);
+        u32 any = k.a0 | k.a1 | k.b0 | k.b1 | k.c0 | k.c1 | k.d0 | k.d1;
+        u32 all = k.a0 & k.a1 & k.b0 & k.b1 & k.c0 & k.c1 & k.d0 & k.d1;
+        k.cellact = any & ~all & mz1;
+    }
+    return k.cellact | k.ez | k.ey | k.ex;
+}
+
 __global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
                                                  u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
                                                  u32 *__restrict__ counters) {
@@ -150,40 +194,18 @@ __global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, D
     if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_A], 1u);
     __syncthreads();
     const u32 tile = s_tile;
-    const u32 q = tile * 256u + threadIdx.x;
-    const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z;
-    u32 m = 0, a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, ez = 0, ey = 0, ex = 0, cellact = 0;
-    u32 r = 0, c = 0, z0 = 0;
-    if (q < p.NQ) {
-        r = q / p.CPR;
-        c = q - r * p.CPR;
-        const u32 x = r / Y, y = r - x * Y;
-        z0 = c * 32u;
-        const i64 n0 = (i64) r * Z + z0;
-        const u32 nvalid = min(32u, Z - z0);              // points of this chunk inside the row
-        const u32 nv1 = min(32u, Z - z0 - 1u);            // ... that also have a z+1 neighbour
-        const u32 mz = nvalid == 32u ? 0xffffffffu : ((1u << nvalid) - 1u);
-        const u32 mz1 = nv1 == 32u ? 0xffffffffu : ((1u << nv1) - 1u);
-        const bool hasY = y + 1u < Y, hasX = x + 1u < X;
-        fetch33(bits, n0, a0, a1);
-        ez = (a0 ^ a1) & mz1;
-        if (hasY) {
-            fetch33(bits, n0 + Z, b0, b1);
-            ey = (a0 ^ b0) & mz;
+    const u32 q0 = tile * CP_TILE + threadIdx.x * CP_ITEMS;
+    const u32 Z = (u32) p.g.Z;
+    // pass 1: count (the masks are recomputed in pass 2; the words stay in L1)
+    u32 cnt = 0;
+#pragma unroll
+    for (int j = 0; j < CP_ITEMS; j++) {
+        const u32 q = q0 + j;
+        if (q < p.NQ) {
+            ChunkBits k;
+            cnt += __popc(chunk_classify(bits, p, q, k));
         }
-        if (hasX) {
-            fetch33(bits, n0 + p.YZ, c0, c1);
-            ex = (a0 ^ c0) & mz;
-        }
-        if (hasX && hasY) {
-            fetch33(bits, n0 + p.YZ + Z, d0, d1);
-            u32 any = a0 | a1 | b0 | b1 | c0 | c1 | d0 | d1;
-            u32 all = a0 & a1 & b0 & b1 & c0 & c1 & d0 & d1;
-            cellact = any & ~all & mz1;
-        }
-        m = cellact | ez | ey | ex;
     }
-    const u32 cnt = __popc(m);
     u32 total;
     const u32 excl = block_exclusive_scan(cnt, &total, sw);
     if (threadIdx.x < 32) {
@@ -192,24 +214,198 @@ __global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, D
     }
     __syncthreads();
     u32 off = s_prefix + excl;
-    if (q < p.NQ) {
-        if (c == 0) row_start[r] = off;
-        if (q == p.NQ - 1) {
-            row_start[p.R] = off + cnt;
-            counters[C_S] = off + cnt;
-        }
-        const bool cellrow = (r / Y + 1u < X) && (r % Y + 1u < Y);
+#pragma unroll 1
+    for (int j = 0; j < CP_ITEMS; j++) {
+        const u32 q = q0 + j;
+        if (q >= p.NQ) break;
+        ChunkBits k;
+        u32 m = chunk_classify(bits, p, q, k);
+        if (k.z0 == 0) row_start[k.r] = off;
         while (m) {
-            const u32 k = __ffs(m) - 1;
+            const u32 b = __ffs(m) - 1;
             m &= m - 1;
             if (off < cap) {
-                u32 cs = ((a0 >> k) & 1u) | (((a1 >> k) & 1u) << 1) | (((b0 >> k) & 1u) << 2) | (((b1 >> k) & 1u) << 3) |
-                         (((c0 >> k) & 1u) << 4) | (((c1 >> k) & 1u) << 5) | (((d0 >> k) & 1u) << 6) | (((d1 >> k) & 1u) << 7);
-                u32 own = ((ez >> k) & 1u) | (((ey >> k) & 1u) << 1) | (((ex >> k) & 1u) << 2);
-                u32 cv = (cellrow && (z0 + k + 1u < Z)) ? 1u : 0u;
-                entries[off] = make_uint2(r, (z0 + k) | (cs << 16) | (own << 24) | (cv << 27));
+                u32 cs = ((k.a0 >> b) & 1u) | (((k.a1 >> b) & 1u) << 1) | (((k.b0 >> b) & 1u) << 2) | (((k.b1 >> b) & 1u) << 3) |
+                         (((k.c0 >> b) & 1u) << 4) | (((k.c1 >> b) & 1u) << 5) | (((k.d0 >> b) & 1u) << 6) | (((k.d1 >> b) & 1u) << 7);
+                u32 own = ((k.ez >> b) & 1u) | (((k.ey >> b) & 1u) << 1) | (((k.ex >> b) & 1u) << 2);
+                u32 cv = (k.cellrow && (k.z0 + b + 1u < Z)) ? 1u : 0u;
+                entries[off] = make_uint2(k.r, (k.z0 + b) | (cs << 16) | (own << 24) | (cv << 27));
             }
             off++;
+        }
+        if (q == p.NQ - 1) {
+            row_start[p.R] = off;
+            counters[C_S] = off;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 fast path (Z % 128 == 0): one thread per 128-point span of a row.  The four rows of the
+// span's cells arrive as four aligned uint4 loads (+1 word for the z+1 neighbour of the last point);
+// a span whose 4x(128+1) sign bits are all equal -- >98% of a typical volume -- is rejected
+// with a few LOP3s, so the kernel costs ~0.4 instructions per voxel instead of ~8.
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_ITEMS = 4;                 // consecutive spans per thread
+constexpr int SP_TILE = 256 * SP_ITEMS;     // spans per block
+
+struct SpanBits {
+    u32 a[5], b[5], c[5], d[5];   // words 0..3 of the span + the following word (only bit 0 used)
+    u32 r, z0;
+    bool hasX, hasY, last;        // last: this span ends the row (no z+1 neighbour for its last point)
+};
+
+__device__ __forceinline__ void span_load(const u32 *__restrict__ bits, const DenseParams &p, u32 r, u32 x, u32 y, u32 c4,
+                                          u32 spr, SpanBits &k) {
+    const u32 Z = (u32) p.g.Z;
+    k.r = r;
+    k.z0 = c4 * 128u;
+    k.hasY = y + 1u < (u32) p.g.Y;
+    k.hasX = x + 1u < (u32) p.g.X;
+    k.last = c4 + 1u == spr;
+    const i64 w = ((i64) r * Z + k.z0) >> 5;   // multiple of 4: aligned uint4
+    const i64 wy = w + (Z >> 5), wx = w + (p.YZ >> 5);
+    const uint4 A = __ldg(reinterpret_cast<const uint4 *>(bits + w));
+    k.a[0] = A.x; k.a[1] = A.y; k.a[2] = A.z; k.a[3] = A.w;
+    k.a[4] = k.last ? 0u : __ldg(bits + w + 4);
+    if (k.hasY) {
+        const uint4 B = __ldg(reinterpret_cast<const uint4 *>(bits + wy));
+        k.b[0] = B.x; k.b[1] = B.y; k.b[2] = B.z; k.b[3] = B.w;
+        k.b[4] = k.last ? 0u : __ldg(bits + wy + 4);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 5; j++) k.b[j] = k.a[j];
+    }
+    if (k.hasX) {
+        const uint4 Cc = __ldg(reinterpret_cast<const uint4 *>(bits + wx));
+        k.c[0] = Cc.x; k.c[1] = Cc.y; k.c[2] = Cc.z; k.c[3] = Cc.w;
+        k.c[4] = k.last ? 0u : __ldg(bits + wx + 4);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 5; j++) k.c[j] = k.a[j];
+    }
+    if (k.hasX && k.hasY) {
+        const uint4 D = __ldg(reinterpret_cast<const uint4 *>(bits + wx + (Z >> 5)));
+        k.d[0] = D.x; k.d[1] = D.y; k.d[2] = D.z; k.d[3] = D.w;
+        k.d[4] = k.last ? 0u : __ldg(bits + wx + (Z >> 5) + 4);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 5; j++) k.d[j] = k.hasX ? k.c[j] : (k.hasY ? k.b[j] : k.a[j]);
+    }
+}
+
+// true if some pair of the span's 4x129 sign bits differs (=> the span may own an entry)
+__device__ __forceinline__ bool span_mixed(const SpanBits &k) {
+    u32 any = 0, all = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        any |= k.a[j] | k.b[j] | k.c[j] | k.d[j];
+        all &= k.a[j] & k.b[j] & k.c[j] & k.d[j];
+    }
+    if (!k.last) {
+        // the following word's bit 0 (z+1 neighbour of the span's last point) counts as one more sample
+        const u32 n_any = (k.a[4] | k.b[4] | k.c[4] | k.d[4]) & 1u, n_all = k.a[4] & k.b[4] & k.c[4] & k.d[4] & 1u;
+        return !((any == 0u && n_any == 0u) || (all == 0xffffffffu && n_all == 1u));
+    }
+    return !(any == 0u || all == 0xffffffffu);
+}
+
+// masks of word j of the span: m = entries, plus per-bit pieces
+__device__ __forceinline__ u32 span_word_masks(const SpanBits &k, int j, u32 &a0, u32 &a1, u32 &b0, u32 &b1, u32 &c0, u32 &c1,
+                                               u32 &d0, u32 &d1, u32 &ez, u32 &ey, u32 &ex, u32 &cellact) {
+    a0 = k.a[j]; a1 = (k.a[j] >> 1) | (k.a[j + 1] << 31);
+    b0 = k.b[j]; b1 = (k.b[j] >> 1) | (k.b[j + 1] << 31);
+    c0 = k.c[j]; c1 = (k.c[j] >> 1) | (k.c[j + 1] << 31);
+    d0 = k.d[j]; d1 = (k.d[j] >> 1) | (k.d[j + 1] << 31);
+    const u32 mz1 = (k.last && j == 3) ? 0x7fffffffu : 0xffffffffu;   // points with a z+1 neighbour
+    ez = (a0 ^ a1) & mz1;
+    ey = k.hasY ? (a0 ^ b0) : 0u;
+    ex = k.hasX ? (a0 ^ c0) : 0u;
+    cellact = 0;
+    if (k.hasX && k.hasY) {
+        u32 any = a0 | a1 | b0 | b1 | c0 | c1 | d0 | d1;
+        u32 all = a0 & a1 & b0 & b1 & c0 & c1 & d0 & d1;
+        cellact = any & ~all & mz1;
+    }
+    return cellact | ez | ey | ex;
+}
+
+__global__ void __launch_bounds__(256) k_compact128(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
+                                                    u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
+                                                    u32 *__restrict__ counters) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_A], 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 spr = Z >> 7;                 // spans per row
+    const u32 nspans = p.R * spr;
+    const u32 u0 = tile * SP_TILE + threadIdx.x * SP_ITEMS;
+    u32 r0 = u0 / spr, c0 = u0 - r0 * spr, x0 = r0 / Y, y0 = r0 - x0 * Y;
+
+    u32 cnt = 0, mixed = 0;
+    {
+        u32 r = r0, c4 = c0, x = x0, y = y0;
+#pragma unroll
+        for (int i = 0; i < SP_ITEMS; i++) {
+            if (u0 + i < nspans) {
+                SpanBits k;
+                span_load(bits, p, r, x, y, c4, spr, k);
+                if (span_mixed(k)) {
+                    u32 a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca, n = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) n += __popc(span_word_masks(k, j, a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca));
+                    if (n) mixed |= 1u << i;
+                    cnt += n;
+                }
+            }
+            if (++c4 == spr) { c4 = 0; r++; if (++y == Y) { y = 0; x++; } }
+        }
+    }
+    u32 total;
+    const u32 excl = block_exclusive_scan(cnt, &total, sw);
+    if (threadIdx.x < 32) {
+        u32 pre = lookback_exclusive(desc, 1, tile, total, 1u);
+        if (threadIdx.x == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    u32 off = s_prefix + excl;
+    {
+        u32 r = r0, c4 = c0, x = x0, y = y0;
+#pragma unroll 1
+        for (int i = 0; i < SP_ITEMS; i++) {
+            if (u0 + i >= nspans) break;
+            if (c4 == 0) row_start[r] = off;
+            if ((mixed >> i) & 1u) {
+                SpanBits k;
+                span_load(bits, p, r, x, y, c4, spr, k);
+                const bool cellrow = k.hasX && k.hasY;
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    u32 a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca;
+                    u32 m = span_word_masks(k, j, a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca);
+                    const u32 zb = k.z0 + 32u * j;
+                    while (m) {
+                        const u32 b = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (off < cap) {
+                            u32 cs = ((a0 >> b) & 1u) | (((a1 >> b) & 1u) << 1) | (((b0 >> b) & 1u) << 2) | (((b1 >> b) & 1u) << 3) |
+                                     (((cc0 >> b) & 1u) << 4) | (((c1 >> b) & 1u) << 5) | (((d0 >> b) & 1u) << 6) | (((d1 >> b) & 1u) << 7);
+                            if (!cellrow) cs &= 0x03u;   // rows y+1 / x+1 do not exist: their bits are copies
+                            u32 own = ((ez >> b) & 1u) | (((ey >> b) & 1u) << 1) | (((ex >> b) & 1u) << 2);
+                            u32 cv = (cellrow && (zb + b + 1u < Z)) ? 1u : 0u;
+                            entries[off] = make_uint2(r, (zb + b) | (cs << 16) | (own << 24) | (cv << 27));
+                        }
+                        off++;
+                    }
+                }
+            }
+            if (u0 + i == nspans - 1) {
+                row_start[p.R] = off;
+                counters[C_S] = off;
+            }
+            if (++c4 == spr) { c4 = 0; r++; if (++y == Y) { y = 0; x++; } }
         }
     }
 }

@@ -45,7 +45,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.counters = c.take<u32>(C_COUNT);
     b.bits = c.take<u32>(signbits_words(p.P));
     b.row_start = c.take<u32>((size_t) p.R + 2);
-    b.descA = c.take<u64>((size_t) (p.NQ + 255) / 256 + 1);
+    b.descA = c.take<u64>((size_t) p.NQ / CP_TILE + 2);
     b.entries = c.take<uint2>(cap + 1);
     b.nb = c.take<u32>(3 * cap);
     b.ntri = c.take<unsigned char>(cap);
@@ -405,7 +405,7 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
     const u32 cap = (u32) cap_entries;
 
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
-    ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) (p.NQ + 255) / 256 + 1) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) p.NQ / CP_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descT, 0, ((size_t) (cap + 255) / 256 + 1) * sizeof(u64) , stream));
     ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) (cap + 255) / 256 + 1) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.used, 0, 3 * ((size_t) cap + 2), stream));
@@ -417,7 +417,12 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
         int blocks = (int) (want < 1 ? 1 : (want > (i64) sms * 8 ? (i64) sms * 8 : want));
         k_signbits<<<blocks, 256, 0, stream>>>(values, b.bits, p.P, level);
     }
-    k_compact<<<(p.NQ + 255) / 256, 256, 0, stream>>>(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+    if ((p.g.Z & 127) == 0) {
+        const u32 nspans = p.R * (u32) (p.g.Z >> 7);
+        k_compact128<<<(nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream>>>(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+    } else {
+        k_compact<<<(p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream>>>(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+    }
     k_cell_tris<<<sms * 8, 128, 0, stream>>>(values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                                              b.trimask, b.used);
     k_scan_entries<<<sms * 4, 256, 0, stream>>>(cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU);

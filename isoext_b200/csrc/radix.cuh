@@ -59,12 +59,25 @@ __global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict__ kx, 
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-__global__ void __launch_bounds__(256) k_radix_prefix(u32 *__restrict__ hist) {
-    __shared__ u32 sw[33];
-    for (int p = 0; p < RADIX_PASSES; p++) {
-        u32 v = hist[p * 256 + threadIdx.x], total;
-        u32 ex = block_exclusive_scan(v, &total, sw);
-        hist[p * 256 + threadIdx.x] = ex;
+// one warp per digit place: exclusive scan of its 256-bin histogram (8 bins per lane)
+__global__ void __launch_bounds__(32 * RADIX_PASSES) k_radix_prefix(u32 *__restrict__ hist) {
+    const u32 lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+    u32 v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = hist[p * 256 + lane * 8 + k];
+        sum += v[k];
+    }
+    u32 incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32) o) incl += t;
+    }
+    u32 run = incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        hist[p * 256 + lane * 8 + k] = run;
+        run += v[k];
     }
 }
 
@@ -77,16 +90,26 @@ __device__ __forceinline__ u32 lookback_bin(u64 *desc, u32 tile, u32 bin, u32 ag
     }
     st_relaxed_u64(mine, desc_pack(1, epoch, aggregate));
     u32 excl = 0;
-    for (int t = (int) tile - 1; t >= 0; --t) {
-        const u64 *p = desc + (size_t) t * 256 + bin;
-        u64 d;
-        u32 state;
-        do {
-            d = ld_relaxed_u64(p);
-            state = (((u32) (d >> 32)) & 0x3fffffffu) == (epoch & 0x3fffffffu) ? (u32) (d >> 62) : 0u;
-        } while (state == 0);
-        excl += (u32) d;
-        if (state == 2) break;
+    // Walk back with 4 independent loads in flight (the walk is latency-bound, not bandwidth-bound).
+    for (int t = (int) tile - 1; t >= 0; t -= 4) {
+        u64 d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            d[k] = (t - k >= 0) ? ld_relaxed_u64(desc + (size_t) (t - k) * 256 + bin) : desc_pack(2, epoch, 0);
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (done) break;
+            u64 dk = d[k];
+            u32 state = (((u32) (dk >> 32)) & 0x3fffffffu) == (epoch & 0x3fffffffu) ? (u32) (dk >> 62) : 0u;
+            while (state == 0) {
+                dk = ld_relaxed_u64(desc + (size_t) (t - k) * 256 + bin);
+                state = (((u32) (dk >> 32)) & 0x3fffffffu) == (epoch & 0x3fffffffu) ? (u32) (dk >> 62) : 0u;
+            }
+            excl += (u32) dk;
+            if (state == 2) done = true;
+        }
+        if (done) break;
     }
     st_relaxed_u64(mine, desc_pack(2, epoch, excl + aggregate));
     return excl;
@@ -182,7 +205,7 @@ static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *
     u32 hist_blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (hist_blocks > 148 * 4) hist_blocks = 148 * 4;
     k_radix_hist<<<hist_blocks, 256, 0, stream>>>(kx, ky, kz, n, b.hist);
-    k_radix_prefix<<<1, 256, 0, stream>>>(b.hist);
+    k_radix_prefix<<<1, 32 * RADIX_PASSES, 0, stream>>>(b.hist);
     const u32 *src[3] = {kz, ky, kx};
     for (int p = 0; p < RADIX_PASSES; p++) {
         const int in = p & 1, out = in ^ 1;

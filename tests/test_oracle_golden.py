@@ -1,0 +1,105 @@
+"""CPU: pin the oracle (oracle/oracle_c.c) against every known-answer value the reference records.
+
+Sources (executed notebooks of the reference): doc/marching_cubes.ipynb:60-61,113-114,
+144-146; doc/grids.ipynb:172; doc/occupancy_grids.ipynb:88; doc/quickstart.ipynb:21;
+doc/dual_contouring.ipynb:51-52,104,145-146 -- plus the committed fixtures under tests/golden/, which are
+outputs of the reference's own CUDA build (tools/make_golden.py)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import fields
+import oracle
+from isoext_b200 import sdf as S
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def sphere07():
+    return fields.eval_field(S.SphereSDF(0.7), (64, 64, 64))
+
+
+@pytest.mark.parametrize("method", ["nagae", "lorensen"])
+def test_sphere_64_counts(sphere07, method):
+    v, f, n_active = oracle.mc_dense(sphere07.numpy(), 0.0, method)
+    assert (len(v), len(f), n_active) == (9168, 18332, 9170)
+
+
+@pytest.mark.parametrize("level,nv", [(-0.2, 4728), (0.2, 15072)])
+def test_sphere_64_levels(sphere07, level, nv):
+    v, f, _ = oracle.mc_dense(sphere07.numpy(), level, "nagae")
+    assert len(v) == nv
+
+
+def test_gyroid_64():
+    v, f, _ = oracle.mc_dense(fields.eval_field(fields.gyroid(6.0), (64, 64, 64)).numpy())
+    assert (len(v), len(f)) == (38760, 75484)
+
+
+def test_occupancy_64(sphere07):
+    occ = (sphere07 < 0).float()
+    v, f, _ = oracle.mc_dense(occ.numpy(), 0.5)
+    assert (len(v), len(f)) == (9168, 18332)
+
+
+def test_c1_sphere_64():
+    """BASELINE.json configs[0]."""
+    vals = fields.eval_field(S.SphereSDF(0.5), (64, 64, 64)).numpy()
+    for method in ("nagae", "lorensen"):
+        v, f, n = oracle.mc_dense(vals, 0.0, method)
+        assert (len(v), len(f), n) == (4728, 9452, 4730)
+
+
+def test_cuboid_65_exact_level_hits():
+    vals = fields.eval_field(S.CuboidSDF([1, 1, 1]), (65, 65, 65)).numpy()
+    v, f, n = oracle.mc_dense(vals)
+    assert (len(v), len(f), n) == (5766, 11528, 5768)
+
+
+def test_quickstart_256():
+    v, f, n = oracle.mc_dense(fields.eval_field(fields.quickstart(), (256, 256, 256)).numpy())
+    assert (len(v), len(f), n) == (196176, 392348, 196130)
+
+
+def test_torus_256():
+    v, f, n = oracle.mc_dense(fields.eval_field(fields.torus(), (256, 256, 256)).numpy())
+    assert (len(v), len(f), n) == (91850, 183700, 91872)
+
+
+def test_dc_cuboid_64_combinatorics():
+    """doc/dual_contouring.ipynb: 24,576 intersections; 6,146 V / 12,288 F."""
+    vals = fields.eval_field(S.CuboidSDF([1, 1, 1]), (64, 64, 64)).numpy()
+    its = oracle.get_intersection(vals, compute_normals=True)
+    assert len(its.points) == 24576
+    dc = oracle.dual_contouring(its, (64, 64, 64))
+    assert len(dc["quads"]) == 6144 and len(dc["f"]) == 12288 and len(dc["v"]) == 6146
+
+
+def test_points_formula():
+    p = oracle.points_dense((5, 3, 4), (-1, 0, 2), (1, 3, 4))
+    assert p.shape == (5, 3, 4, 3)
+    assert np.allclose(p[0, 0, 0], [-1, 0, 2]) and np.allclose(p[-1, -1, -1], [1, 3, 4])
+    q = np.float32(1) / np.float32(4)
+    assert p[1, 0, 0, 0] == np.float32(np.float64(q) * 2.0 - 1.0)
+
+
+def test_sparse_equals_dense_when_all_active_cells_present():
+    vals = fields.eval_field(S.SphereSDF(0.5), (20, 20, 20)).numpy()
+    X = Y = Z = 20
+    idx = np.arange((X - 1) * (Y - 1) * (Z - 1))
+    x, y, z = idx // ((Y - 1) * (Z - 1)), (idx // (Z - 1)) % (Y - 1), idx % (Z - 1)
+    v8 = np.stack([vals[x + (i >> 2 & 1), y + (i >> 1 & 1), z + (i & 1)] for i in range(8)], axis=1)
+    dv, df, _ = oracle.mc_dense(vals)
+    sv, sf, _ = oracle.mc_sparse(v8, idx, (X, Y, Z))
+    assert np.array_equal(dv, sv) and np.array_equal(df, sf)
+
+
+@pytest.mark.parametrize("path", sorted(GOLDEN.glob("mc_*.npz")), ids=lambda p: p.stem)
+def test_oracle_matches_reference_cuda_fixtures(path):
+    """Fixtures are outputs of the reference's own CUDA build (tools/make_golden.py on a B200)."""
+    g = np.load(path)
+    v, f, _ = oracle.mc_dense(g["values"], float(g["level"]), str(g["method"]), g["aabb_min"], g["aabb_max"])
+    assert np.array_equal(v.view(np.uint32), g["v"].view(np.uint32))
+    assert np.array_equal(f, g["f"])

@@ -53,6 +53,9 @@ allok &= cmp("boundary-crossing sphere 1.2", fields.eval_field(S.SphereSDF(1.2),
 allok &= cmp("aabb [0,3]x[-2,1]x[5,6]", fields.eval_field(S.SphereSDF(0.5), (40, 40, 40)), aabb=((0, -2, 5), (3, 1, 6)))
 allok &= cmp("2x2x2", torch.tensor([[[-1., 1], [1, 1]], [[1, 1], [1, -1]]]))
 allok &= cmp("3x2x200 noise", fields.noise((3, 2, 200), 2))
+allok &= cmp("noise 20x24x128", fields.noise((20, 24, 128), 3))
+allok &= cmp("noise 7x5x256 lorensen", fields.noise((7, 5, 256), 4), method="lorensen")
+allok &= cmp("sphere 33x40x128", fields.eval_field(S.SphereSDF(0.8), (33, 40, 128)))
 allok &= cmp("256 torus", fields.eval_field(fields.torus(), (256, 256, 256)))
 allok &= cmp("256 csg", fields.eval_field(fields.csg_box_minus_sphere(), (256, 256, 256)))
 allok &= cmp("256 quickstart", fields.eval_field(fields.quickstart(), (256, 256, 256)))
