@@ -72,8 +72,8 @@ def _borrow(ptr, shape, dtype):
 
 class _GridBase:
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().ref_grid_delete(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_grid_delete(self.h)
             self.h = None
 
     def get_num_cells(self):
@@ -158,8 +158,8 @@ class Intersection:
         self.h = h
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().ref_its_delete(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_its_delete(self.h)
             self.h = None
 
     def num_points(self):
