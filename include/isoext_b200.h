@@ -45,6 +45,13 @@ const char *isoext_last_error(void);
 const char *isoext_build_info(void);
 int isoext_abi_version(void);
 
+/* ---- measurement hooks (no reference counterpart; used by bench.py only) ---------------------
+ * begin(): reset the launch counter and start recording a CUDA-event pair around every launch of the
+ * volume-streaming kernel (the roofline's dominant kernel) on the stream it is launched on.
+ * end(): total / count of those durations and the number of kernel launches since begin(). */
+int isoext_profile_begin(void);
+int isoext_profile_end(double *stream_ms_total, int64_t *stream_launches, int64_t *kernel_launches);
+
 /* ---- UniformGrid.get_points  (src/grid/uniform.cu:22-30, include/utils.cuh:62-80) ----------
  * out: (X,Y,Z,3) f32.  Positions use the global index: pos_x = fma((x+x_offset)/(X_global-1), ...). */
 int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,

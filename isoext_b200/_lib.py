@@ -23,6 +23,8 @@ SIGNATURES = {
     "isoext_last_error": (C.c_char_p, []),
     "isoext_build_info": (C.c_char_p, []),
     "isoext_abi_version": (_int, []),
+    "isoext_profile_begin": (_int, []),
+    "isoext_profile_end": (_int, [C.POINTER(C.c_double), _pi64, _pi64]),
     "isoext_grid_points_dense": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp]),
     "isoext_mc_dense_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "isoext_mc_dense_scratch_bytes": (_sz, [_i64]),

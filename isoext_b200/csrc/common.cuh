@@ -34,6 +34,24 @@ int fail(int code, const std::string &msg);
             return isx::fail(isx::E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));  \
     } while (0)
 
+// Kernel-launch accounting and optional per-launch timing of the dominant (volume-streaming) kernel.
+// bench.py reads these through isoext_profile_begin/end (api.cu); the product path never depends on them.
+extern long long g_kernel_launches;
+struct StreamTimer {
+    bool enabled = false;
+    static constexpr int kMaxPairs = 4096;
+    cudaEvent_t ev[2 * kMaxPairs];
+    int used = 0, created = 0;
+};
+extern StreamTimer g_stream_timer;
+void stream_timer_mark(cudaStream_t s);   // record the next event of a (begin,end) pair if enabled
+
+#define ISX_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                              \
+        ++isx::g_kernel_launches;                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+    } while (0)
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Carves typed sub-buffers out of one caller-provided device blob (256-byte aligned pieces).

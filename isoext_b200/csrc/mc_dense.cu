@@ -415,17 +415,19 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
         i64 groups = p.P >> 7;
         i64 want = (groups + 8 * SB_UNROLL - 1) / (8 * SB_UNROLL);   // 8 warps per block
         int blocks = (int) (want < 1 ? 1 : (want > (i64) sms * 8 ? (i64) sms * 8 : want));
-        k_signbits<<<blocks, 256, 0, stream>>>(values, b.bits, p.P, level);
+        stream_timer_mark(stream);
+        ISX_LAUNCH(k_signbits, blocks, 256, 0, stream, values, b.bits, p.P, level);
+        stream_timer_mark(stream);
     }
     if ((p.g.Z & 127) == 0) {
         const u32 nspans = p.R * (u32) (p.g.Z >> 7);
-        k_compact128<<<(nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream>>>(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+        ISX_LAUNCH(k_compact128, (nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
     } else {
-        k_compact<<<(p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream>>>(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+        ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
     }
-    k_cell_tris<<<sms * 8, 128, 0, stream>>>(values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+    ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                                              b.trimask, b.used);
-    k_scan_entries<<<sms * 4, 256, 0, stream>>>(cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU);
+    ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
     ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -465,7 +467,7 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     const int sms = num_sms();
 
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) (nc + 255) / 256 + 1) * sizeof(u64), stream));
-    k_cand_pos<<<sms * 8, 256, 0, stream>>>(values, p, b.entries, b.counters, b.cand_info, s.kx, s.ky, s.kz);
+    ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
     // thresholds as keys: x < thr  <=>  key(x) < key(thr) for non-NaN values
     u32 klo, khi;
@@ -479,8 +481,8 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
         klo = hkey(x_lo_threshold);
         khi = hkey(x_hi_threshold);
     }
-    k_unique<<<sms * 4, 256, 0, stream>>>(nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV, klo, khi);
-    k_emit_faces<<<sms * 8, 128, 0, stream>>>(p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
+    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV, klo, khi);
+    ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
                                               s.cand_rank, F);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
@@ -503,7 +505,7 @@ int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, 
     if (P <= 0) return OK;
     i64 want = (P + 255) / 256;
     int blocks = (int) (want > (i64) num_sms() * 16 ? (i64) num_sms() * 16 : want);
-    k_grid_points<<<blocks, 256, 0, stream>>>(g, out);
+    ISX_LAUNCH(k_grid_points, blocks, 256, 0, stream, g, out);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }
@@ -525,7 +527,7 @@ int isoext_relabel_faces(int32_t *F, int64_t n_ids, int64_t n_lo, int64_t n_hi, 
     if (n_ids <= 0) return OK;
     i64 want = (n_ids + 255) / 256;
     int blocks = (int) (want > 148 * 16 ? 148 * 16 : want);
-    k_relabel_faces<<<blocks, 256, 0, stream>>>(F, n_ids, n_lo, n_hi, base_mine, base_next);
+    ISX_LAUNCH(k_relabel_faces, blocks, 256, 0, stream, F, n_ids, n_lo, n_hi, base_mine, base_next);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }

@@ -204,21 +204,21 @@ static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *
     if (e != cudaSuccess) return e;
     u32 hist_blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (hist_blocks > 148 * 4) hist_blocks = 148 * 4;
-    k_radix_hist<<<hist_blocks, 256, 0, stream>>>(kx, ky, kz, n, b.hist);
-    k_radix_prefix<<<1, 32 * RADIX_PASSES, 0, stream>>>(b.hist);
+    ISX_LAUNCH(k_radix_hist, hist_blocks, 256, 0, stream, kx, ky, kz, n, b.hist);
+    ISX_LAUNCH(k_radix_prefix, 1, 32 * RADIX_PASSES, 0, stream, b.hist);
     const u32 *src[3] = {kz, ky, kx};
     for (int p = 0; p < RADIX_PASSES; p++) {
         const int in = p & 1, out = in ^ 1;
         const u32 shift = 8 * (p & 3);
         const u32 *coord = src[p >> 2];
         if (p == 0)
-            k_radix_pass<true, true><<<ntiles, RADIX_THREADS, 0, stream>>>(
+            ISX_LAUNCH((k_radix_pass<true, true>), ntiles, RADIX_THREADS, 0, stream, 
                 b.key[in], b.perm[in], b.key[out], b.perm[out], coord, shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n);
         else if ((p & 3) == 0)
-            k_radix_pass<true, false><<<ntiles, RADIX_THREADS, 0, stream>>>(
+            ISX_LAUNCH((k_radix_pass<true, false>), ntiles, RADIX_THREADS, 0, stream, 
                 b.key[in], b.perm[in], b.key[out], b.perm[out], coord, shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n);
         else
-            k_radix_pass<false, false><<<ntiles, RADIX_THREADS, 0, stream>>>(
+            ISX_LAUNCH((k_radix_pass<false, false>), ntiles, RADIX_THREADS, 0, stream, 
                 b.key[in], b.perm[in], b.key[out], b.perm[out], coord, shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n);
     }
     return cudaGetLastError();
