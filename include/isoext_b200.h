@@ -45,6 +45,10 @@ const char *isoext_last_error(void);
 const char *isoext_build_info(void);
 int isoext_abi_version(void);
 
+/* Position of grid plane i along one axis: fma(i / (res-1), amax - amin, amin) in float32, i.e. the
+ * per-axis term of get_vtx_pos_op (include/utils.cuh:71-79).  Host-side; no GPU needed. */
+float isoext_axis_position(int64_t i, int64_t res, float amin, float amax);
+
 /* ---- measurement hooks (no reference counterpart; used by bench.py only) ---------------------
  * begin(): reset the launch counter and start recording a CUDA-event pair around every launch of the
  * volume-streaming kernel (the roofline's dominant kernel) on the stream it is launched on.

@@ -1,6 +1,8 @@
 // api.cu -- error plumbing and library identification of the C-ABI (include/isoext_b200.h).
 #include "common.cuh"
 
+#include <cmath>
+
 namespace isx {
 std::string &last_error() {
     static thread_local std::string e;
@@ -51,6 +53,12 @@ int isoext_profile_end(double *stream_ms_total, int64_t *stream_launches, int64_
 }
 
 const char *isoext_last_error(void) { return isx::last_error().c_str(); }
+// Grid-plane position along one axis, computed on the host with the same operations as the device
+// (float division, one fused multiply-add): used for the slab ownership thresholds.
+float isoext_axis_position(int64_t i, int64_t res, float amin, float amax) {
+    float q = (float) (uint32_t) i / (float) (uint32_t) (res - 1);
+    return fmaf(q, amax - amin, amin);
+}
 const char *isoext_build_info(void) { return "isoext_b200 sm_100a " __DATE__; }
 int isoext_abi_version(void) { return 1; }
 }

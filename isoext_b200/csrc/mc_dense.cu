@@ -26,6 +26,11 @@ __device__ __forceinline__ u64 tri_word(int method, u32 cs) {
     return method == 0 ? kTriWords_nagae[cs] : kTriWords_lorensen[cs];
 }
 
+constexpr int SE_ITEMS = 8;   // consecutive entries per thread in k_scan_entries
+constexpr int SE_TILE = 256 * SE_ITEMS;
+constexpr int UQ_ITEMS = 8;   // consecutive sorted candidates per thread in k_unique
+constexpr int UQ_TILE = 256 * UQ_ITEMS;
+
 struct McBuffers {
     // phase 1 (sized by the grid and the entry capacity)
     u32 *bits;
@@ -53,8 +58,8 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.used = c.take<unsigned char>(3 * (cap + 2));
     b.tri_off = c.take<u32>(cap);
     b.cand_info = c.take<u32>(cap + 1);
-    b.descT = c.take<u64>((cap + 255) / 256 + 1);
-    b.descU = c.take<u64>((cap + 255) / 256 + 1);
+    b.descT = c.take<u64>(cap / SE_TILE + 2);
+    b.descU = c.take<u64>(cap / SE_TILE + 2);
     if (out) *out = b;
     return c.bytes();
 }
@@ -72,7 +77,7 @@ static size_t carve_mc_scratch(Carver &c, size_t nc, McScratch *out) {
     s.ky = c.take<u32>(nc);
     s.kz = c.take<u32>(nc);
     s.cand_rank = c.take<u32>(nc);
-    s.descV = c.take<u64>((nc + 255) / 256 + 1);
+    s.descV = c.take<u64>(nc / UQ_TILE + 2);
     RadixBuffers::carve(c, nc, &s.radix);
     if (out) *out = s;
     return c.bytes();
@@ -150,23 +155,30 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
     __shared__ u32 s_tile, s_preT, s_preU;
     const u32 S = counters[C_S];
     if (S > cap) return;
-    const u32 ntiles = (S + 255) / 256;
+    const u32 ntiles = (S + SE_TILE - 1) / SE_TILE;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_B], 1u);
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
-        const u32 s = tile * 256 + threadIdx.x;
-        u32 nt = 0, um = 0;
-        if (s < S) {
-            nt = ntri[s];
-            um = (used[3 * s] ? 1u : 0u) | (used[3 * s + 1] ? 2u : 0u) | (used[3 * s + 2] ? 4u : 0u);
+        const u32 s0 = tile * SE_TILE + threadIdx.x * SE_ITEMS;
+        u32 nt[SE_ITEMS], um[SE_ITEMS], sumT = 0, sumU = 0;
+#pragma unroll
+        for (int j = 0; j < SE_ITEMS; j++) {
+            const u32 s = s0 + j;
+            nt[j] = 0;
+            um[j] = 0;
+            if (s < S) {
+                nt[j] = ntri[s];
+                um[j] = (used[3 * s] ? 1u : 0u) | (used[3 * s + 1] ? 2u : 0u) | (used[3 * s + 2] ? 4u : 0u);
+            }
+            sumT += nt[j];
+            sumU += __popc(um[j]);
         }
-        const u32 nu = __popc(um);
         u32 totT, totU;
-        const u32 exT = block_exclusive_scan(nt, &totT, sw);
-        const u32 exU = block_exclusive_scan(nu, &totU, sw);
+        u32 exT = block_exclusive_scan(sumT, &totT, sw);
+        u32 exU = block_exclusive_scan(sumU, &totU, sw);
         const u32 warp = threadIdx.x >> 5;
         if (warp == 0) {
             u32 pre = lookback_exclusive(descT, 1, tile, totT, 1u);
@@ -176,12 +188,20 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
             if ((threadIdx.x & 31) == 0) s_preU = pre;
         }
         __syncthreads();
-        if (s < S) {
-            tri_off[s] = s_preT + exT;
-            cand_info[s] = (s_preU + exU) | (um << 29);
-            if (s == S - 1) {
-                counters[C_T] = s_preT + exT + nt;
-                counters[C_VC] = s_preU + exU + nu;
+        exT += s_preT;
+        exU += s_preU;
+#pragma unroll
+        for (int j = 0; j < SE_ITEMS; j++) {
+            const u32 s = s0 + j;
+            if (s < S) {
+                tri_off[s] = exT;
+                cand_info[s] = exU | (um[j] << 29);
+                exT += nt[j];
+                exU += __popc(um[j]);
+                if (s == S - 1) {
+                    counters[C_T] = exT;
+                    counters[C_VC] = exU;
+                }
             }
         }
     }
@@ -246,47 +266,66 @@ __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restrict__ p
                                                 u64 *__restrict__ desc, u32 key_lo, u32 key_hi) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
-    const u32 ntiles = (n + 255) / 256;
+    const u32 ntiles = (n + UQ_TILE - 1) / UQ_TILE;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_C], 1u);
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
-        const u32 i = tile * 256 + threadIdx.x;
-        u32 isnew = 0, c = 0, x = 0, y = 0, z = 0;
-        if (i < n) {
-            c = perm[i];
-            x = kx[c]; y = ky[c]; z = kz[c];
-            if (i == 0) isnew = 1;
-            else {
-                const u32 pc = perm[i - 1];
-                isnew = (kx[pc] != x || ky[pc] != y || kz[pc] != z) ? 1u : 0u;
+        const u32 i0 = tile * UQ_TILE + threadIdx.x * UQ_ITEMS;
+        u32 c[UQ_ITEMS], x[UQ_ITEMS], y[UQ_ITEMS], z[UQ_ITEMS], isnew = 0, cnt = 0, nlo = 0, nhi = 0;
+        // predecessor of the thread's first item
+        u32 px = 0, py = 0, pz = 0;
+        if (i0 > 0 && i0 < n) {
+            const u32 pc = perm[i0 - 1];
+            px = kx[pc]; py = ky[pc]; pz = kz[pc];
+        }
+#pragma unroll
+        for (int j = 0; j < UQ_ITEMS; j++) {
+            const u32 i = i0 + j;
+            if (i < n) {
+                c[j] = perm[i];
+                x[j] = kx[c[j]]; y[j] = ky[c[j]]; z[j] = kz[c[j]];
+                const bool nw = (i == 0) || x[j] != px || y[j] != py || z[j] != pz;
+                px = x[j]; py = y[j]; pz = z[j];
+                if (nw) {
+                    isnew |= 1u << j;
+                    cnt++;
+                    nlo += x[j] < key_lo;
+                    nhi += x[j] < key_hi;
+                }
             }
         }
         u32 tot;
-        const u32 ex = block_exclusive_scan(isnew, &tot, sw);
+        const u32 ex = block_exclusive_scan(cnt, &tot, sw);
         if (threadIdx.x < 32) {
             u32 pre = lookback_exclusive(desc, 1, tile, tot, 1u);
             if (threadIdx.x == 0) s_pre = pre;
         }
-        // per-warp counts of new vertices under the thresholds
-        const u32 blo = __ballot_sync(0xffffffffu, isnew && x < key_lo);
-        const u32 bhi = __ballot_sync(0xffffffffu, isnew && x < key_hi);
+        for (int o = 16; o > 0; o >>= 1) {
+            nlo += __shfl_xor_sync(0xffffffffu, nlo, o);
+            nhi += __shfl_xor_sync(0xffffffffu, nhi, o);
+        }
         if ((threadIdx.x & 31) == 0) {
-            if (blo) atomicAdd(&counters[C_NLO], (u32) __popc(blo));
-            if (bhi) atomicAdd(&counters[C_NHI], (u32) __popc(bhi));
+            if (nlo) atomicAdd(&counters[C_NLO], nlo);
+            if (nhi) atomicAdd(&counters[C_NHI], nhi);
         }
         __syncthreads();
-        if (i < n) {
-            const u32 rank = s_pre + ex + isnew - 1;
-            cand_rank[c] = rank;
-            if (isnew) {
-                V[3 * (size_t) rank + 0] = key_float(x);
-                V[3 * (size_t) rank + 1] = key_float(y);
-                V[3 * (size_t) rank + 2] = key_float(z);
+        u32 rank = s_pre + ex;   // rank of the next new vertex
+#pragma unroll
+        for (int j = 0; j < UQ_ITEMS; j++) {
+            const u32 i = i0 + j;
+            if (i < n) {
+                if ((isnew >> j) & 1u) {
+                    V[3 * (size_t) rank + 0] = key_float(x[j]);
+                    V[3 * (size_t) rank + 1] = key_float(y[j]);
+                    V[3 * (size_t) rank + 2] = key_float(z[j]);
+                    rank++;
+                }
+                cand_rank[c[j]] = rank - 1;
+                if (i == n - 1) counters[C_V] = rank;
             }
-            if (i == n - 1) counters[C_V] = rank + 1;
         }
     }
 }
@@ -406,8 +445,8 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
 
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
     ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) p.NQ / CP_TILE + 2) * sizeof(u64), stream));
-    ISX_CUDA(cudaMemsetAsync(b.descT, 0, ((size_t) (cap + 255) / 256 + 1) * sizeof(u64) , stream));
-    ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) (cap + 255) / 256 + 1) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(b.descT, 0, ((size_t) cap / SE_TILE + 2) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) cap / SE_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.used, 0, 3 * ((size_t) cap + 2), stream));
 
     const int sms = num_sms();
@@ -466,7 +505,7 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     const u32 nc = (u32) n_candidates;
     const int sms = num_sms();
 
-    ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) (nc + 255) / 256 + 1) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
     // thresholds as keys: x < thr  <=>  key(x) < key(thr) for non-NaN values

@@ -1,0 +1,202 @@
+"""Slab-sharded multi-GPU extraction (new capability: the reference is single-GPU).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink; gloo works for the host logic on CPU).
+The global (X, Y, Z) grid is cut along dim 0 (the slowest axis, so slabs are contiguous):
+
+  * rank r owns cell layers ``[c_r, c_{r+1})`` and stores point planes ``[c_r, c_{r+1})`` (+ the last
+    plane on the last rank);
+  * for extraction it works on the EXTENDED slab of point planes ``[c_r - 1, c_{r+1} + 1]``: one halo
+    plane below, two above (P2P send/recv of (Y, Z) planes).  The ghost cell layers on either side are
+    evaluated (they decide which vertices on the shared planes exist) but emit no faces;
+  * the welded, position-sorted vertex list of the extended slab is split by the *position* thresholds
+    ``px[c_r]`` and ``px[c_{r+1}]``: a vertex with ``px[c_r] <= x < px[c_{r+1}]`` is owned by rank r.
+    Because both neighbours evaluate the same two cell layers around a shared plane with bit-identical
+    arithmetic, they agree on every vertex near it, so a face that references a vertex owned by a
+    neighbour can compute that vertex's global id locally from the all-gathered counts;
+  * per-rank vertex and face lists concatenate (in rank order) to exactly the single-GPU result: V is
+    sorted by x first and F is in ascending (x-major) cell order.
+Only counts cross ranks in the extraction step: one ``all_gather`` of two int64 per rank.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+# ---- pure host logic (no CUDA): unit-tested on CPU with gloo ---------------------------------------
+
+
+def partition_cells(X: int, world: int) -> list[int]:
+    """Cell-layer boundaries c_0..c_world along dim 0 (X points -> X-1 cell layers), as even as possible."""
+    layers = X - 1
+    if layers < 2 * world:
+        raise RuntimeError(f"cannot cut {layers} cell layers into {world} slabs of at least 2 layers")
+    return [(layers * r) // world for r in range(world + 1)]
+
+
+def slab_plan(X: int, rank: int, world: int) -> dict:
+    """Everything rank `rank` needs to know about its slab (all plane indices are GLOBAL)."""
+    c = partition_cells(X, world)
+    c_lo, c_hi = c[rank], c[rank + 1]
+    own_lo, own_hi = c_lo, (c_hi if rank < world - 1 else X)        # owned point planes [own_lo, own_hi)
+    ext_lo, ext_hi = max(0, c_lo - 1), min(X - 1, c_hi + 1)           # extended slab planes [ext_lo, ext_hi]
+    return dict(c_lo=c_lo, c_hi=c_hi, own_lo=own_lo, own_hi=own_hi, ext_lo=ext_lo, ext_hi=ext_hi,
+                n_ext=ext_hi - ext_lo + 1, emit_lo=c_lo - ext_lo, emit_hi=c_hi - ext_lo,
+                halo_below=(c_lo - 1 if rank > 0 else None),                       # 1 plane from rank-1
+                halo_above=([p for p in (c_hi, c_hi + 1) if p <= X - 1] if rank < world - 1 else []))
+
+
+def exchange_halos(ext: torch.Tensor, plan: dict, rank: int, world: int, group=None) -> None:
+    """Fill the halo planes of the extended slab `ext` ((n_ext, Y, Z), owned planes already in place).
+
+    Sends my first two owned planes down to rank-1 and my last owned plane up to rank+1."""
+    if world == 1:
+        return
+    ops, keep = [], []
+    base = plan["ext_lo"]
+
+    def plane(g):
+        return ext[g - base]
+
+    def peer(r):
+        return dist.get_global_rank(group, r) if group is not None else r
+
+    if rank > 0:
+        for g in (plan["own_lo"], plan["own_lo"] + 1):                 # they are rank-1's halo_above
+            t = plane(g).contiguous(); keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, peer(rank - 1), group))
+        ops.append(dist.P2POp(dist.irecv, plane(plan["halo_below"]), peer(rank - 1), group))
+    if rank < world - 1:
+        t = plane(plan["c_hi"] - 1).contiguous(); keep.append(t)      # rank+1's halo_below
+        ops.append(dist.P2POp(dist.isend, t, peer(rank + 1), group))
+        for g in plan["halo_above"]:
+            ops.append(dist.P2POp(dist.irecv, plane(g), peer(rank + 1), group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+def global_bases(n_own: int, n_tri: int, device, group=None):
+    """All-gather (owned vertices, triangles) and return (vertex base, face base, totals, all counts)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    mine = torch.tensor([n_own, n_tri], dtype=torch.int64, device=device)
+    if world == 1:
+        return 0, 0, (n_own, n_tri), mine[None]
+    flat = torch.empty(world * 2, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(flat, mine, group=group)
+    rank = dist.get_rank(group)
+    allc_h = flat.view(world, 2).cpu()
+    vb = int(allc_h[:rank, 0].sum())
+    fb = int(allc_h[:rank, 1].sum())
+    return vb, fb, (int(allc_h[:, 0].sum()), int(allc_h[:, 1].sum())), allc_h
+
+
+def relabel_ids_torch(F: torch.Tensor, n_lo: int, n_hi: int, base_mine: int, base_next: int) -> torch.Tensor:
+    """Reference implementation (pure torch) of the id map the CUDA kernel isoext_relabel_faces applies."""
+    ids = F.long()
+    out = torch.where(ids < n_lo, base_mine - (n_lo - ids),
+                      torch.where(ids < n_hi, base_mine + (ids - n_lo), base_next + (ids - n_hi)))
+    return out.to(F.dtype)
+
+
+# ---- GPU layer -------------------------------------------------------------------------------------
+class SlabGrid:
+    """This rank's slab of a global UniformGrid (same constructor arguments as ``UniformGrid``)."""
+
+    def __init__(self, shape, aabb_min=(-1.0, -1.0, -1.0), aabb_max=(1.0, 1.0, 1.0), default_value=3.4028234663852886e38,
+                 group=None, device=None, rank=None, world=None):
+        from . import _lib
+        from .grid import _Workspace
+        self.shape = tuple(int(s) for s in shape)
+        self.aabb_min = tuple(float(v) for v in aabb_min)
+        self.aabb_max = tuple(float(v) for v in aabb_max)
+        self.group = group
+        # rank/world may be given explicitly to simulate a slab without a process group (tests)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.plan = slab_plan(self.shape[0], self.rank, self.world)
+        _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        X, Y, Z = self.shape
+        self._ext = torch.full((self.plan["n_ext"], Y, Z), float(default_value), dtype=torch.float32, device=self.device)
+        self._ws = _Workspace()
+        self._cap_hint = 0
+        lib = _lib.lib()
+        px = lambda i: float(lib.isoext_axis_position(i, X, self.aabb_min[0], self.aabb_max[0]))
+        self.thresholds = (px(self.plan["c_lo"]) if self.rank > 0 else -math.inf,
+                           px(self.plan["c_hi"]) if self.rank < self.world - 1 else math.inf)
+
+    def owned_point_range(self):
+        return self.plan["own_lo"], self.plan["own_hi"]
+
+    def local_points(self) -> int:
+        return int(self._ext.numel())
+
+    def owned_values(self) -> torch.Tensor:
+        p = self.plan
+        return self._ext[p["own_lo"] - p["ext_lo"]:p["own_hi"] - p["ext_lo"]]
+
+    def set_owned_values(self, values: torch.Tensor) -> None:
+        own = self.owned_values()
+        if tuple(values.shape) != tuple(own.shape):
+            raise RuntimeError("Cannot set values with different shapes")
+        own.copy_(values)
+
+    def exchange_halos(self) -> None:
+        exchange_halos(self._ext, self.plan, self.rank, self.world, self.group)
+
+
+def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae"):
+    """The rank-local part of the distributed extraction (no communication): returns
+    ``(v_own, f_local, n_lo, n_hi)`` where ``f_local`` still holds extended-slab vertex ids."""
+    from .mc import _method_id, mc_dense_raw
+    mid = _method_id(method)
+    p = sg.plan
+    X, Y, Z = sg.shape
+    with torch.cuda.device(sg.device):
+        v_ext, f, n_lo, n_hi, cap = mc_dense_raw(sg._ext, (p["n_ext"], Y, Z), sg.aabb_min, sg.aabb_max, level, mid, sg._ws,
+                                                 cap_hint=sg._cap_hint, x_offset=p["ext_lo"], x_global=X,
+                                                 emit_range=(p["emit_lo"], p["emit_hi"]), x_thresholds=sg.thresholds)
+    sg._cap_hint = cap
+    if v_ext is None:
+        return (torch.empty((0, 3), dtype=torch.float32, device=sg.device),
+                torch.empty((0, 3), dtype=torch.int32, device=sg.device), 0, 0)
+    return v_ext[n_lo:n_hi], f, n_lo, n_hi
+
+
+def relabel_faces_(f: torch.Tensor, n_lo: int, n_hi: int, base_mine: int, base_next: int) -> None:
+    """In-place local -> global vertex ids (CUDA kernel isoext_relabel_faces)."""
+    from . import _lib
+    from .grid import _stream_ptr
+    if f.numel():
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().isoext_relabel_faces(f.data_ptr(), f.numel(), n_lo, n_hi, base_mine, base_next, _stream_ptr()))
+
+
+def marching_cubes(sg: SlabGrid, level: float = 0.0, method: str = "nagae", exchange: bool = True):
+    """Distributed ``marching_cubes``: returns this rank's part ``(v_own, f_own)`` of the global mesh.
+
+    Concatenating the parts of ranks 0..R-1 gives exactly the single-GPU ``(v, f)`` (global vertex ids).
+    Either element may be an empty tensor on a rank whose slab misses the surface."""
+    if exchange:
+        sg.exchange_halos()
+    v_own, f, n_lo, n_hi = marching_cubes_local(sg, level, method)
+    vb, fb, totals, _ = global_bases(n_hi - n_lo, int(f.shape[0]), sg.device, sg.group)
+    relabel_faces_(f, n_lo, n_hi, vb, vb + (n_hi - n_lo))
+    return v_own, f
+
+
+def gather_mesh(v_own: torch.Tensor, f_own: torch.Tensor, group=None):
+    """Concatenate the per-rank parts on every rank (surface-sized all_gather)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return v_own, f_own
+    sizes = torch.tensor([v_own.shape[0], f_own.shape[0]], dtype=torch.int64, device=v_own.device)
+    flat = torch.empty(world * 2, dtype=torch.int64, device=v_own.device)
+    dist.all_gather_into_tensor(flat, sizes, group=group)
+    alls = flat.view(world, 2).cpu()
+    vs = [torch.empty((int(alls[r, 0]), 3), dtype=v_own.dtype, device=v_own.device) for r in range(world)]
+    fs = [torch.empty((int(alls[r, 1]), 3), dtype=f_own.dtype, device=f_own.device) for r in range(world)]
+    dist.all_gather(vs, v_own.contiguous(), group=group)
+    dist.all_gather(fs, f_own.contiguous(), group=group)
+    return torch.cat(vs), torch.cat(fs)

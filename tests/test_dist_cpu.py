@@ -1,0 +1,113 @@
+"""CPU tests of the multi-GPU slab logic (isoext_b200/dist.py): partitioning, the gloo halo exchange at
+world_size 2 and 3, and -- using the CPU oracle in place of the CUDA kernels -- the vertex-ownership /
+global-id scheme itself: per-rank parts must concatenate to exactly the single-device mesh."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import fields
+import oracle
+from isoext_b200 import _lib
+from isoext_b200 import dist as idist
+from isoext_b200 import sdf as S
+
+
+def test_partition_covers_all_layers():
+    for X, world in [(64, 1), (64, 2), (65, 3), (2048, 8), (17, 8)]:
+        c = idist.partition_cells(X, world)
+        assert c[0] == 0 and c[-1] == X - 1 and all(b - a >= 2 for a, b in zip(c, c[1:]))
+    with pytest.raises(RuntimeError):
+        idist.partition_cells(8, 8)
+
+
+def test_slab_plan_halo_geometry():
+    X, world = 64, 4
+    plans = [idist.slab_plan(X, r, world) for r in range(world)]
+    assert plans[0]["halo_below"] is None and plans[-1]["halo_above"] == []
+    for r in range(world - 1):
+        assert plans[r]["halo_above"] == [plans[r + 1]["own_lo"], plans[r + 1]["own_lo"] + 1]
+        assert plans[r + 1]["halo_below"] == plans[r]["own_hi"] - 1
+    assert sum(p["own_hi"] - p["own_lo"] for p in plans) == X
+    assert [p["emit_hi"] - p["emit_lo"] for p in plans] == [p["c_hi"] - p["c_lo"] for p in plans]
+
+
+def _halo_worker(rank, world, port, shape):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = fields.noise(shape, 11)
+        plan = idist.slab_plan(shape[0], rank, world)
+        ext = torch.full((plan["n_ext"], shape[1], shape[2]), float("nan"))
+        ext[plan["own_lo"] - plan["ext_lo"]:plan["own_hi"] - plan["ext_lo"]] = full[plan["own_lo"]:plan["own_hi"]]
+        idist.exchange_halos(ext, plan, rank, world)
+        assert torch.equal(ext, full[plan["ext_lo"]:plan["ext_hi"] + 1]), f"rank {rank}: halo mismatch"
+        vb, fb, totals, allc = idist.global_bases(10 + rank, 100 + rank, torch.device("cpu"))
+        assert vb == sum(10 + r for r in range(rank)) and fb == sum(100 + r for r in range(rank))
+        assert totals == (sum(10 + r for r in range(world)), sum(100 + r for r in range(world)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_and_count_allgather_gloo(world):
+    mp.spawn(_halo_worker, args=(world, 29500 + world, (13, 5, 6)), nprocs=world, join=True)
+
+
+def px(i, X, lo=-1.0, hi=1.0):
+    return float(_lib.lib().isoext_axis_position(i, X, lo, hi))
+
+
+def simulate_rank(vals, rank, world, method):
+    """What one rank computes, with the oracle standing in for the CUDA pipeline."""
+    X = vals.shape[0]
+    p = idist.slab_plan(X, rank, world)
+    v_ext, f_ext, _ = oracle.mc_dense(vals, 0.0, method, x_range=(p["ext_lo"], p["ext_hi"]))
+    n_below = len(oracle.mc_dense(vals, 0.0, method, x_range=(p["ext_lo"], p["c_lo"]))[1])
+    n_own = len(oracle.mc_dense(vals, 0.0, method, x_range=(p["c_lo"], p["c_hi"]))[1])
+    f_own = f_ext[n_below:n_below + n_own]
+    b_lo = px(p["c_lo"], X) if rank > 0 else -np.inf
+    b_hi = px(p["c_hi"], X) if rank < world - 1 else np.inf
+    n_lo = int((v_ext[:, 0] < np.float32(b_lo)).sum()) if len(v_ext) else 0
+    n_hi = int((v_ext[:, 0] < np.float32(b_hi)).sum()) if len(v_ext) else 0
+    return v_ext[n_lo:n_hi], f_own, n_lo, n_hi
+
+
+FIELDS = {
+    "cuboid33_faces_on_slab_planes": lambda: fields.eval_field(S.CuboidSDF([1, 1, 1]), (33, 33, 33)),
+    "sphere40": lambda: fields.eval_field(S.SphereSDF(0.6), (40, 24, 28)),
+    "noise24": lambda: fields.noise((24, 10, 12), 3),
+    "csg36": lambda: fields.eval_field(fields.csg_box_minus_sphere(), (36, 36, 36)),
+    "planes_exactly_at_level": lambda: _plane_field(),
+}
+
+
+def _plane_field():
+    # f = x - px[k] for several k: whole grid planes sit exactly on the level set, including slab boundaries
+    X = 25
+    ax = fields.axis(X)
+    f = (ax[:, None, None] - ax[12]).expand(X, 9, 11).clone()
+    f[:, 4:, :] = (ax[:, None, None] - ax[8]).expand(X, 5, 11)
+    return f
+
+
+@pytest.mark.parametrize("method", ["nagae", "lorensen"])
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("name", sorted(FIELDS))
+def test_per_rank_parts_concatenate_to_the_single_device_mesh(name, world, method):
+    vals = FIELDS[name]().numpy()
+    gv, gf, _ = oracle.mc_dense(vals, 0.0, method)
+    parts = [simulate_rank(vals, r, world, method) for r in range(world)]
+    owned = [len(p[0]) for p in parts]
+    bases = np.concatenate([[0], np.cumsum(owned)])
+    vs, fs = [], []
+    for r, (v_own, f_own, n_lo, n_hi) in enumerate(parts):
+        f = idist.relabel_ids_torch(torch.from_numpy(f_own), n_lo, n_hi, int(bases[r]), int(bases[r + 1])).numpy()
+        vs.append(v_own); fs.append(f)
+    v = np.concatenate(vs) if vs else np.zeros((0, 3), np.float32)
+    f = np.concatenate(fs)
+    assert v.shape == gv.shape and np.array_equal(v.view(np.uint32), gv.view(np.uint32))
+    assert np.array_equal(f, gf)
