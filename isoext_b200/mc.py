@@ -54,8 +54,8 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         _lib.check(rc)
         break
     S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
-    if T == 0:
-        return None, None, 0, 0, cap
+    if Vc == 0:   # no vertex at all (T == 0 alone is not enough: a slab may own vertices that only
+        return None, None, 0, 0, cap   # its neighbour's faces reference)
     sbytes = lib.isoext_mc_dense_scratch_bytes(Vc)
     scratch = ws.get("mc_scratch", sbytes, dev)
     V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
@@ -82,6 +82,8 @@ def marching_cubes(grid, level: float = 0.0, method: str = "nagae"):
             v, f, _, _, cap = mc_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, mid, grid._ws,
                                            cap_hint=grid._cap_hint)
         grid._cap_hint = cap
+        if f is None or f.shape[0] == 0:
+            return None, None   # src/isoext_ext.cu:47-49: empty arrays become None
         return v, f
     from .sparse import SparseGrid, mc_sparse
     if isinstance(grid, SparseGrid):
