@@ -89,6 +89,53 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
                          float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
                          int64_t *counts_out);
 
+/* ---- get_intersection on a UniformGrid  (src/its.cu:93-159, src/isoext_ext.cu:329-343) -------
+ * The Intersection the host layer builds keeps caller-owned arrays instead of the reference's
+ * (cell, edge) -> uint2 edge list: `entries` (the ordered active-point list, 8 B each), `row_start`
+ * (X*Y+2 u32), `cellslot` / `its_off` (per entry: rank among active cells, CSR offset), `isout` (per
+ * entry: v_lo <= v_hi of its 3 owned edges, src/its.cu:78).  points / normals are the (I,3) arrays of
+ * include/its.cuh:6-26 in the same order (active cells ascending, edges 0..11).
+ * Phase 1: counts_out[0..2] = entries S, active cells, intersections I. */
+size_t isoext_its_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t cap_entries);
+int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                           const float *aabb_min, const float *aabb_max, float level, void *workspace,
+                           size_t workspace_bytes, int64_t cap_entries, void *entries, uint32_t *row_start,
+                           uint32_t *cellslot, uint32_t *its_off, void *stream, int64_t *counts_out);
+/* Phase 2: points (I x 3), normals (I x 3; written only if compute_normals), isout (S bytes),
+ * cell_offsets (n_cells+1 u32) and cell_indices (n_cells i64) as in include/its.cuh:9-12. */
+int isoext_its_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                          const float *aabb_min, const float *aabb_max, float level, int compute_normals,
+                          const void *entries, int64_t n_entries, const uint32_t *cellslot, const uint32_t *its_off,
+                          int64_t n_cells, int64_t n_its, float *points, float *normals, unsigned char *isout,
+                          uint32_t *cell_offsets, int64_t *cell_indices, void *stream);
+/* compute_intersection_normals (src/its.cu:270-284): trilinear central differences of each cell,
+ * in the reference's float32 rounding pattern. */
+int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                             const float *aabb_min, const float *aabb_max, const void *entries, int64_t n_entries,
+                             const uint32_t *cellslot, const uint32_t *its_off, const float *points, float *normals,
+                             void *stream);
+
+/* ---- dual_contouring on a UniformGrid  (src/dc.cu:161-218, src/isoext_ext.cu:345-378) --------
+ * Phase 1: QEF (src/dc.cu:14-80) + pseudo-inverse solve (replaces src/batched_la.cu:104-179) + clip
+ * (src/dc.cu:82-99) -> dual_v (n_cells x 3); quads from the owned sign-change edges (replaces
+ * Grid::get_dual_quads, src/grid/uniform.cu:60-83).  counts_out[0..1] = quads Q, used dual vertices Vc.
+ * Phase 2: V (capacity Vc x 3, position-sorted + welded like src/dc.cu:204-211), F (2Q x 3 int32:
+ * shorter-diagonal split, src/dc.cu:139-155), optional quads_out (Q x 4 active-cell slots, oriented).
+ * counts_out[0] = welded vertices. */
+size_t isoext_dc_dense_workspace_bytes(int64_t n_entries, int64_t n_cells);
+size_t isoext_dc_dense_scratch_bytes(int64_t n_candidates);
+int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
+                          const float *aabb_max, const void *entries, int64_t n_entries, const uint32_t *row_start,
+                          const uint32_t *cellslot, const uint32_t *its_off, int64_t n_cells, const float *points,
+                          const float *normals, float reg, float svd_tol, float *dual_v, void *workspace,
+                          size_t workspace_bytes, void *stream, int64_t *counts_out);
+int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
+                         const float *aabb_max, const void *entries, int64_t n_entries, const uint32_t *row_start,
+                         const uint32_t *cellslot, const unsigned char *isout, int64_t n_cells, const float *dual_v,
+                         void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
+                         int64_t n_candidates, float *V, int32_t *F, int32_t *quads_out, void *stream,
+                         int64_t *counts_out);
+
 /* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
  * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->
  * base_mine + (id - n_lo); id >= n_hi -> base_next + (id - n_hi). */

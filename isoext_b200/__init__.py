@@ -10,12 +10,16 @@ if importlib.util.find_spec("torch") is None:  # same guard as the reference (sr
     raise ImportError("PyTorch is required but not installed. Please install PyTorch with CUDA support.\n")
 
 from . import sdf, utils  # noqa: E402,F401
+from .dc import Intersection, dual_contouring, get_intersection  # noqa: E402,F401
 from .grid import Grid, UniformGrid  # noqa: E402,F401
 from .mc import marching_cubes  # noqa: E402,F401
 from .utils import gaussian_smooth, make_grid, write_obj  # noqa: E402,F401
 
 __all__ = [
+    "Intersection",
     "UniformGrid",
+    "dual_contouring",
+    "get_intersection",
     "gaussian_smooth",
     "marching_cubes",
     "make_grid",

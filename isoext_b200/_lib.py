@@ -33,6 +33,18 @@ SIGNATURES = {
                                      _vp, _sz, _i64, _vp, _pi64]),
     "isoext_mc_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
                                     _vp, _sz, _i64, _vp, _sz, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
+    "isoext_its_dense_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "isoext_its_dense_count": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _vp, _sz, _i64, _vp, _vp, _vp, _vp,
+                                      _vp, _pi64]),
+    "isoext_its_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _vp, _i64, _vp, _vp, _i64, _i64,
+                                     _vp, _vp, _vp, _vp, _vp, _vp]),
+    "isoext_its_dense_normals": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "isoext_dc_dense_workspace_bytes": (_sz, [_i64, _i64]),
+    "isoext_dc_dense_scratch_bytes": (_sz, [_i64]),
+    "isoext_dc_dense_count": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _f32,
+                                     _f32, _vp, _vp, _sz, _vp, _pi64]),
+    "isoext_dc_dense_emit": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp,
+                                    _sz, _i64, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
 }
 

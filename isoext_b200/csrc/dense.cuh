@@ -92,7 +92,7 @@ __device__ __forceinline__ u32 gather_word(u32 nib, u32 lane) {
     return w;
 }
 
-__global__ void __launch_bounds__(256) k_signbits(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level) {
+static __global__ void __launch_bounds__(256) k_signbits(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level) {
     const u32 lane = threadIdx.x & 31;
     const i64 ngroups = P >> 7;   // full groups of 128 points
     const i64 nwarps = ((i64) gridDim.x * blockDim.x) >> 5;
@@ -186,7 +186,7 @@ __device__ __forceinline__ u32 chunk_classify(const u32 *__restrict__ bits, cons
     return k.cellact | k.ez | k.ey | k.ex;
 }
 
-__global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
+static __global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
                                                  u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
                                                  u32 *__restrict__ counters) {
     __shared__ u32 sw[33];
@@ -330,7 +330,7 @@ __device__ __forceinline__ u32 span_word_masks(const SpanBits &k, int j, u32 &a0
     return cellact | ez | ey | ex;
 }
 
-__global__ void __launch_bounds__(256) k_compact128(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
+static __global__ void __launch_bounds__(256) k_compact128(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
                                                     u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
                                                     u32 *__restrict__ counters) {
     __shared__ u32 sw[33];
@@ -477,7 +477,7 @@ __device__ __forceinline__ void cell_edge_slots(const uint2 *__restrict__ entrie
 }
 
 // grid point positions, (X,Y,Z,3) f32 -- replaces get_vtx_pos_op (include/utils.cuh:62-80)
-__global__ void __launch_bounds__(256) k_grid_points(Geom g, float *__restrict__ out) {
+static __global__ void __launch_bounds__(256) k_grid_points(Geom g, float *__restrict__ out) {
     const i64 P = g.X * g.Y * g.Z;
     const u32 Y = (u32) g.Y, Z = (u32) g.Z;
     for (i64 n = (i64) blockIdx.x * blockDim.x + threadIdx.x; n < P; n += (i64) gridDim.x * blockDim.x) {

@@ -14,6 +14,7 @@
 // Every arithmetic step that decides a bit of the output uses explicit _rn intrinsics.
 #include "dense.cuh"
 #include "radix.cuh"
+#include "weld.cuh"
 
 #include <cstring>
 
@@ -28,8 +29,6 @@ __device__ __forceinline__ u64 tri_word(int method, u32 cs) {
 
 constexpr int SE_ITEMS = 8;   // consecutive entries per thread in k_scan_entries
 constexpr int SE_TILE = 256 * SE_ITEMS;
-constexpr int UQ_ITEMS = 8;   // consecutive sorted candidates per thread in k_unique
-constexpr int UQ_TILE = 256 * UQ_ITEMS;
 
 struct McBuffers {
     // phase 1 (sized by the grid and the entry capacity)
@@ -257,80 +256,6 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6: weld = unique over the sorted candidates (look-back scan of "differs from predecessor").
-// Also counts how many welded vertices lie below the slab thresholds (multi-GPU ownership).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restrict__ perm, const u32 *__restrict__ kx,
-                                                const u32 *__restrict__ ky, const u32 *__restrict__ kz,
-                                                u32 *__restrict__ cand_rank, float *__restrict__ V, u32 *__restrict__ counters,
-                                                u64 *__restrict__ desc, u32 key_lo, u32 key_hi) {
-    __shared__ u32 sw[33];
-    __shared__ u32 s_tile, s_pre;
-    const u32 ntiles = (n + UQ_TILE - 1) / UQ_TILE;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_C], 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= ntiles) break;
-        const u32 i0 = tile * UQ_TILE + threadIdx.x * UQ_ITEMS;
-        u32 c[UQ_ITEMS], x[UQ_ITEMS], y[UQ_ITEMS], z[UQ_ITEMS], isnew = 0, cnt = 0, nlo = 0, nhi = 0;
-        // predecessor of the thread's first item
-        u32 px = 0, py = 0, pz = 0;
-        if (i0 > 0 && i0 < n) {
-            const u32 pc = perm[i0 - 1];
-            px = kx[pc]; py = ky[pc]; pz = kz[pc];
-        }
-#pragma unroll
-        for (int j = 0; j < UQ_ITEMS; j++) {
-            const u32 i = i0 + j;
-            if (i < n) {
-                c[j] = perm[i];
-                x[j] = kx[c[j]]; y[j] = ky[c[j]]; z[j] = kz[c[j]];
-                const bool nw = (i == 0) || x[j] != px || y[j] != py || z[j] != pz;
-                px = x[j]; py = y[j]; pz = z[j];
-                if (nw) {
-                    isnew |= 1u << j;
-                    cnt++;
-                    nlo += x[j] < key_lo;
-                    nhi += x[j] < key_hi;
-                }
-            }
-        }
-        u32 tot;
-        const u32 ex = block_exclusive_scan(cnt, &tot, sw);
-        if (threadIdx.x < 32) {
-            u32 pre = lookback_exclusive(desc, 1, tile, tot, 1u);
-            if (threadIdx.x == 0) s_pre = pre;
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            nlo += __shfl_xor_sync(0xffffffffu, nlo, o);
-            nhi += __shfl_xor_sync(0xffffffffu, nhi, o);
-        }
-        if ((threadIdx.x & 31) == 0) {
-            if (nlo) atomicAdd(&counters[C_NLO], nlo);
-            if (nhi) atomicAdd(&counters[C_NHI], nhi);
-        }
-        __syncthreads();
-        u32 rank = s_pre + ex;   // rank of the next new vertex
-#pragma unroll
-        for (int j = 0; j < UQ_ITEMS; j++) {
-            const u32 i = i0 + j;
-            if (i < n) {
-                if ((isnew >> j) & 1u) {
-                    V[3 * (size_t) rank + 0] = key_float(x[j]);
-                    V[3 * (size_t) rank + 1] = key_float(y[j]);
-                    V[3 * (size_t) rank + 2] = key_float(z[j]);
-                    rank++;
-                }
-                cand_rank[c[j]] = rank - 1;
-                if (i == n - 1) counters[C_V] = rank;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // K7: faces.  One thread per emitting cell; triangle k of the LUT row goes to tri_off[s] + (#kept before k).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, const uint2 *__restrict__ entries,
@@ -368,7 +293,7 @@ __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, c
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int make_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin, const float *amax, float level,
+int make_dense_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin, const float *amax, float level,
                        i64 emit_lo, i64 emit_hi, DenseParams *out) {
     if (X < 1 || Y < 1 || Z < 1) return fail(E_INVALID, "grid shape must be positive");
     if (Z > 65535) return fail(E_INVALID, "Z (points along the last axis) must be <= 65535");
@@ -395,7 +320,7 @@ static int make_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin
     return OK;
 }
 
-static int num_sms() {
+int device_sms() {
     static int n = 0;
     if (!n) {
         int dev = 0;
@@ -415,7 +340,7 @@ extern "C" {
 size_t isoext_mc_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t cap_entries) {
     DenseParams p;
     float z3[3] = {0, 0, 0}, o3[3] = {1, 1, 1};
-    if (make_params(X, Y, Z, 0, X, z3, o3, 0.f, 0, X - 1, &p) != OK) return 0;
+    if (make_dense_params(X, Y, Z, 0, X, z3, o3, 0.f, 0, X - 1, &p) != OK) return 0;
     Carver c(nullptr);
     return carve_mc(c, p, (size_t) cap_entries, nullptr);
 }
@@ -434,7 +359,7 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
-    int rc = make_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
     if ((reinterpret_cast<uintptr_t>(values) & 15u) != 0) return fail(E_INVALID, "values must be 16-byte aligned");
     if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
@@ -449,7 +374,7 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
     ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) cap / SE_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.used, 0, 3 * ((size_t) cap + 2), stream));
 
-    const int sms = num_sms();
+    const int sms = device_sms();
     {
         i64 groups = p.P >> 7;
         i64 want = (groups + 8 * SB_UNROLL - 1) / (8 * SB_UNROLL);   // 8 warps per block
@@ -491,7 +416,7 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
-    int rc = make_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
     Carver c(workspace);
     McBuffers b;
@@ -503,23 +428,12 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     McScratch s;
     if (carve_mc_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
     const u32 nc = (u32) n_candidates;
-    const int sms = num_sms();
+    const int sms = device_sms();
 
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    // thresholds as keys: x < thr  <=>  key(x) < key(thr) for non-NaN values
-    u32 klo, khi;
-    {
-        auto hkey = [](float f) {
-            u32 bts;
-            memcpy(&bts, &f, 4);
-            if ((bts << 1) == 0u) bts = 0u;
-            return (bts & 0x80000000u) ? ~bts : (bts | 0x80000000u);
-        };
-        klo = hkey(x_lo_threshold);
-        khi = hkey(x_hi_threshold);
-    }
+    const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV, klo, khi);
     ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
                                               s.cand_rank, F);
@@ -543,7 +457,7 @@ int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, 
     i64 P = X * Y * Z;
     if (P <= 0) return OK;
     i64 want = (P + 255) / 256;
-    int blocks = (int) (want > (i64) num_sms() * 16 ? (i64) num_sms() * 16 : want);
+    int blocks = (int) (want > (i64) device_sms() * 16 ? (i64) device_sms() * 16 : want);
     ISX_LAUNCH(k_grid_points, blocks, 256, 0, stream, g, out);
     ISX_CUDA(cudaGetLastError());
     return OK;

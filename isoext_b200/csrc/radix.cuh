@@ -42,7 +42,7 @@ struct RadixBuffers {
     }
 };
 
-__global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
+static __global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                     const u32 *__restrict__ kz, u32 n, u32 *__restrict__ hist) {
     __shared__ u32 sh[RADIX_PASSES * 256];
     for (int i = threadIdx.x; i < RADIX_PASSES * 256; i += blockDim.x) sh[i] = 0;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict__ kx, 
 }
 
 // one warp per digit place: exclusive scan of its 256-bin histogram (8 bins per lane)
-__global__ void __launch_bounds__(32 * RADIX_PASSES) k_radix_prefix(u32 *__restrict__ hist) {
+static __global__ void __launch_bounds__(32 * RADIX_PASSES) k_radix_prefix(u32 *__restrict__ hist) {
     const u32 lane = threadIdx.x & 31, p = threadIdx.x >> 5;
     u32 v[8], sum = 0;
 #pragma unroll
@@ -118,7 +118,7 @@ __device__ __forceinline__ u32 lookback_bin(u64 *desc, u32 tile, u32 bin, u32 ag
 // One digit pass.  GATHER: the key of item i is src_keys[perm] (start of a new coordinate);
 // IDENTITY: perm_in is the identity (very first pass).
 template <bool GATHER, bool IDENTITY>
-__global__ void __launch_bounds__(RADIX_THREADS)
+static __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_pass(const u32 *__restrict__ key_in, const u32 *__restrict__ perm_in, u32 *__restrict__ key_out,
              u32 *__restrict__ perm_out, const u32 *__restrict__ src_keys, u32 shift,
              const u32 *__restrict__ gprefix, u64 *__restrict__ desc, u32 *__restrict__ ticket, u32 epoch, u32 n) {

@@ -1,0 +1,97 @@
+// weld.cuh -- positional welding of sorted vertex candidates (shared by MC and DC).
+//
+// Replaces thrust::unique + lower_bound of the reference's vertex_welding (src/utils.cu:49-55):
+// after radix_sort96 the candidates are in lexicographic (x,y,z) order; equal neighbours collapse
+// into one output vertex and every candidate learns its final rank.
+#pragma once
+#include "dense.cuh"
+
+#include <cstring>
+
+namespace isx {
+
+constexpr int UQ_ITEMS = 8;   // consecutive sorted candidates per thread
+constexpr int UQ_TILE = 256 * UQ_ITEMS;
+
+// unique over the sorted candidates (look-back scan of "differs from predecessor"); also counts how
+// many welded vertices lie below the slab thresholds (multi-GPU ownership).
+static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restrict__ perm, const u32 *__restrict__ kx,
+                                                const u32 *__restrict__ ky, const u32 *__restrict__ kz,
+                                                u32 *__restrict__ cand_rank, float *__restrict__ V, u32 *__restrict__ counters,
+                                                u64 *__restrict__ desc, u32 key_lo, u32 key_hi) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_tile, s_pre;
+    const u32 ntiles = (n + UQ_TILE - 1) / UQ_TILE;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_C], 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u32 i0 = tile * UQ_TILE + threadIdx.x * UQ_ITEMS;
+        u32 c[UQ_ITEMS], x[UQ_ITEMS], y[UQ_ITEMS], z[UQ_ITEMS], isnew = 0, cnt = 0, nlo = 0, nhi = 0;
+        // predecessor of the thread's first item
+        u32 px = 0, py = 0, pz = 0;
+        if (i0 > 0 && i0 < n) {
+            const u32 pc = perm[i0 - 1];
+            px = kx[pc]; py = ky[pc]; pz = kz[pc];
+        }
+#pragma unroll
+        for (int j = 0; j < UQ_ITEMS; j++) {
+            const u32 i = i0 + j;
+            if (i < n) {
+                c[j] = perm[i];
+                x[j] = kx[c[j]]; y[j] = ky[c[j]]; z[j] = kz[c[j]];
+                const bool nw = (i == 0) || x[j] != px || y[j] != py || z[j] != pz;
+                px = x[j]; py = y[j]; pz = z[j];
+                if (nw) {
+                    isnew |= 1u << j;
+                    cnt++;
+                    nlo += x[j] < key_lo;
+                    nhi += x[j] < key_hi;
+                }
+            }
+        }
+        u32 tot;
+        const u32 ex = block_exclusive_scan(cnt, &tot, sw);
+        if (threadIdx.x < 32) {
+            u32 pre = lookback_exclusive(desc, 1, tile, tot, 1u);
+            if (threadIdx.x == 0) s_pre = pre;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            nlo += __shfl_xor_sync(0xffffffffu, nlo, o);
+            nhi += __shfl_xor_sync(0xffffffffu, nhi, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (nlo) atomicAdd(&counters[C_NLO], nlo);
+            if (nhi) atomicAdd(&counters[C_NHI], nhi);
+        }
+        __syncthreads();
+        u32 rank = s_pre + ex;   // rank of the next new vertex
+#pragma unroll
+        for (int j = 0; j < UQ_ITEMS; j++) {
+            const u32 i = i0 + j;
+            if (i < n) {
+                if ((isnew >> j) & 1u) {
+                    V[3 * (size_t) rank + 0] = key_float(x[j]);
+                    V[3 * (size_t) rank + 1] = key_float(y[j]);
+                    V[3 * (size_t) rank + 2] = key_float(z[j]);
+                    rank++;
+                }
+                cand_rank[c[j]] = rank - 1;
+                if (i == n - 1) counters[C_V] = rank;
+            }
+        }
+    }
+}
+
+
+// x < thr  <=>  key(x) < key(thr) for non-NaN values (host-side twin of float_key)
+static inline u32 host_float_key(float f) {
+    u32 b;
+    memcpy(&b, &f, 4);
+    if ((b << 1) == 0u) b = 0u;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+}   // namespace isx

@@ -1,0 +1,178 @@
+"""``Intersection``, ``get_intersection`` and ``dual_contouring`` -- host-side mirror of the reference
+bindings (src/isoext_ext.cu:305-378) over the sm_100a kernels in csrc/dc_dense.cu."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .grid import UniformGrid, _expect_cuda, _stream_ptr
+from .mc import _initial_cap
+
+
+class Intersection:
+    """Edge/surface crossings of a grid (include/its.cuh:6-26).  Not constructible from Python, like the
+    reference's; created by :func:`get_intersection`.
+
+    ``get_points()`` / ``get_normals()`` are (I, 3) float32 with one row per (active cell, crossing edge)
+    pair -- active cells ascending, edges 0..11 -- so an interior crossing appears once per incident
+    cell (64^3 cube: 24,576 = 4 x 6,144).  Returned tensors are views of torch-owned storage (the
+    reference hands ownership to the returned tensor and keeps a dangling view; not replicated).
+    """
+
+    def __init__(self, _token=None):
+        if _token is not Intersection._TOKEN:
+            raise TypeError("Intersection cannot be constructed directly; use get_intersection()")
+
+    _TOKEN = object()
+
+    @classmethod
+    def _make(cls, **kw):
+        self = cls(cls._TOKEN)
+        self.__dict__.update(kw)
+        return self
+
+    def get_points(self) -> torch.Tensor:
+        return self.points
+
+    def get_normals(self) -> torch.Tensor:
+        """Before normals exist the reference returns uninitialised memory (include/its.cuh:15-17);
+        here the buffer is zero-filled."""
+        return self.normals
+
+    def has_normals(self) -> bool:
+        return self._has_normals
+
+    def set_normals(self, new_normals: torch.Tensor) -> None:
+        _expect_cuda(new_normals, torch.float32, ndim=2, last=3, what="new_normals")
+        if new_normals.shape[0] != self.points.shape[0]:
+            raise RuntimeError("Cannot set values with different shapes")   # include/ndarray.cuh:79-84
+        self.normals = new_normals.detach().clone()
+        self._has_normals = True
+
+    def _copy(self):
+        """By-value copy, as the binding takes std::optional<Intersection> (src/isoext_ext.cu:347-351)."""
+        d = dict(self.__dict__)
+        d["normals"] = self.normals.clone()
+        return Intersection._make(**d)
+
+
+def _its_dense(grid: UniformGrid, level: float, compute_normals: bool) -> Intersection:
+    lib = _lib.lib()
+    X, Y, Z = grid.shape
+    dev = grid.device
+    amin, amax = _lib.f3(grid.aabb_min), _lib.f3(grid.aabb_max)
+    stream = _stream_ptr()
+    counts = (C.c_int64 * 4)()
+    cap = max(int(grid._cap_hint), _initial_cap(grid.shape))
+    row_start = torch.empty(X * Y + 2, dtype=torch.int32, device=dev)
+    while True:
+        nbytes = lib.isoext_its_dense_workspace_bytes(X, Y, Z, cap)
+        if nbytes == 0:
+            raise RuntimeError(_lib.last_error())
+        ws = grid._ws.get("its_ws", nbytes, dev)
+        entries = torch.empty((cap + 1, 2), dtype=torch.int32, device=dev)
+        cellslot = torch.empty(cap, dtype=torch.int32, device=dev)
+        its_off = torch.empty(cap, dtype=torch.int32, device=dev)
+        rc = lib.isoext_its_dense_count(grid._values.data_ptr(), X, Y, Z, 0, X, amin, amax, float(level), ws.data_ptr(),
+                                        ws.numel(), cap, entries.data_ptr(), row_start.data_ptr(), cellslot.data_ptr(),
+                                        its_off.data_ptr(), stream, counts)
+        if rc == _lib.E_CAPACITY:
+            cap = int(counts[0]) + 1024
+            continue
+        _lib.check(rc)
+        break
+    S, n_cells, n_its = int(counts[0]), int(counts[1]), int(counts[2])
+    grid._cap_hint = max(cap, S)
+    entries, cellslot, its_off = entries[:S + 1], cellslot[:max(S, 1)], its_off[:max(S, 1)]
+    points = torch.empty((n_its, 3), dtype=torch.float32, device=dev)
+    normals = torch.zeros((n_its, 3), dtype=torch.float32, device=dev)
+    isout = torch.empty(max(S, 1), dtype=torch.uint8, device=dev)
+    cell_offsets = torch.zeros(n_cells + 1, dtype=torch.int32, device=dev)
+    cell_indices = torch.empty(n_cells, dtype=torch.int64, device=dev)
+    _lib.check(lib.isoext_its_dense_emit(grid._values.data_ptr(), X, Y, Z, 0, X, amin, amax, float(level),
+                                         int(bool(compute_normals)), entries.data_ptr(), S, cellslot.data_ptr(),
+                                         its_off.data_ptr(), n_cells, n_its, points.data_ptr(), normals.data_ptr(),
+                                         isout.data_ptr(), cell_offsets.data_ptr(), cell_indices.data_ptr(), stream))
+    return Intersection._make(kind="dense", shape=grid.shape, aabb_min=grid.aabb_min, aabb_max=grid.aabb_max, level=float(level),
+                              entries=entries, row_start=row_start, cellslot=cellslot, its_off=its_off, isout=isout,
+                              n_entries=S, n_cells=n_cells, points=points, normals=normals, cell_offsets=cell_offsets,
+                              cell_indices=cell_indices, _has_normals=bool(compute_normals))
+
+
+def get_intersection(grid, level: float = 0.0, compute_normals: bool = False) -> Intersection:
+    """Edge/iso-surface crossings of every active cell (src/isoext_ext.cu:329-343, src/its.cu:93-159)."""
+    if isinstance(grid, UniformGrid):
+        with torch.cuda.device(grid.device):
+            return _its_dense(grid, level, compute_normals)
+    from .sparse import SparseGrid, its_sparse
+    if isinstance(grid, SparseGrid):
+        return its_sparse(grid, level, compute_normals)
+    raise TypeError("get_intersection: grid must be a UniformGrid or SparseGrid")
+
+
+def _normals_dense(grid: UniformGrid, its: Intersection) -> None:
+    X, Y, Z = grid.shape
+    _lib.check(_lib.lib().isoext_its_dense_normals(grid._values.data_ptr(), X, Y, Z, 0, X, _lib.f3(grid.aabb_min),
+                                                   _lib.f3(grid.aabb_max), its.entries.data_ptr(), its.n_entries,
+                                                   its.cellslot.data_ptr(), its.its_off.data_ptr(), its.points.data_ptr(),
+                                                   its.normals.data_ptr(), _stream_ptr()))
+    its._has_normals = True
+
+
+def dc_dense_raw(grid: UniformGrid, its: Intersection, reg: float, svd_tol: float, want_quads: bool = False):
+    """Returns (v, f, dual_v, quads): welded mesh + per-active-cell dual vertices (+ oriented quads)."""
+    lib = _lib.lib()
+    X, Y, Z = grid.shape
+    dev = grid.device
+    amin, amax = _lib.f3(grid.aabb_min), _lib.f3(grid.aabb_max)
+    stream = _stream_ptr()
+    S, n_cells = its.n_entries, its.n_cells
+    dual_v = torch.empty((n_cells, 3), dtype=torch.float32, device=dev)
+    if S == 0 or n_cells == 0:
+        return None, None, dual_v, None
+    ws = grid._ws.get("dc_ws", lib.isoext_dc_dense_workspace_bytes(S, n_cells), dev)
+    counts = (C.c_int64 * 4)()
+    _lib.check(lib.isoext_dc_dense_count(X, Y, Z, 0, X, amin, amax, its.entries.data_ptr(), S, its.row_start.data_ptr(),
+                                         its.cellslot.data_ptr(), its.its_off.data_ptr(), n_cells, its.points.data_ptr(),
+                                         its.normals.data_ptr(), float(reg), float(svd_tol), dual_v.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), stream, counts))
+    Q, Vc = int(counts[0]), int(counts[1])
+    if Q == 0:
+        return None, None, dual_v, None
+    scratch = grid._ws.get("dc_scratch", lib.isoext_dc_dense_scratch_bytes(Vc), dev)
+    V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
+    F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)
+    quads = torch.empty((Q, 4), dtype=torch.int32, device=dev) if want_quads else None
+    out = (C.c_int64 * 4)()
+    _lib.check(lib.isoext_dc_dense_emit(X, Y, Z, 0, X, amin, amax, its.entries.data_ptr(), S, its.row_start.data_ptr(),
+                                        its.cellslot.data_ptr(), its.isout.data_ptr(), n_cells, dual_v.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), scratch.data_ptr(), scratch.numel(), Vc, V.data_ptr(), F.data_ptr(),
+                                        quads.data_ptr() if want_quads else None, stream, out))
+    return V[:int(out[0])], F, dual_v, quads
+
+
+def dual_contouring(grid, level: float = 0.0, intersection: Intersection | None = None, reg: float = 1e-2,
+                    svd_tol: float = 1e-6):
+    """Dual contouring (src/isoext_ext.cu:345-378, src/dc.cu:161-218): one vertex per active cell from a
+    regularised QEF, one quad (two triangles, split along the shorter diagonal) per sign-change edge.
+
+    Returns ``(v, f)``: (V, 3) float32 in lexicographic position order and (2Q, 3) int32, or
+    ``(None, None)`` if there is no quad.  A passed ``intersection`` is not modified; if it carries no
+    normals they are computed from the grid values (trilinear central differences).
+    Deviation: quads with a neighbour cell outside the grid are skipped on the upper faces as well
+    (the reference only checks the lower faces, include/utils.cuh:128-135, and reads out of bounds)."""
+    if isinstance(grid, UniformGrid):
+        with torch.cuda.device(grid.device):
+            its = intersection._copy() if intersection is not None else _its_dense(grid, level, True)
+            if its.kind != "dense" or tuple(its.shape) != tuple(grid.shape):
+                raise RuntimeError("intersection does not belong to this grid")
+            if not its.has_normals():
+                _normals_dense(grid, its)
+            v, f, _, _ = dc_dense_raw(grid, its, reg, svd_tol)
+        return v, f
+    from .sparse import SparseGrid, dc_sparse
+    if isinstance(grid, SparseGrid):
+        return dc_sparse(grid, level, intersection, reg, svd_tol)
+    raise TypeError("dual_contouring: grid must be a UniformGrid or SparseGrid")

@@ -285,36 +285,45 @@ void orc_its_free(orc_its *t) {
     memset(t, 0, sizeof(*t));
 }
 
-/* src/its.cu:172-185 */
-static float trilinear(float tx, float ty, float tz, const float *cv) {
-    float c00 = cv[0] * (1 - tz) + cv[1] * tz;
-    float c01 = cv[2] * (1 - tz) + cv[3] * tz;
-    float c10 = cv[4] * (1 - tz) + cv[5] * tz;
-    float c11 = cv[6] * (1 - tz) + cv[7] * tz;
-    float c0 = c00 * (1 - ty) + c01 * ty;
-    float c1 = c10 * (1 - ty) + c11 * ty;
-    return c0 * (1 - tx) + c1 * tx;
-}
+/* src/its.cu:172-268 for one intersection point p of a cell.
+ * Float32, in the operation order AND fused-multiply-add contraction pattern that nvcc 12.9 (default
+ * -fmad=true) emits for the reference's compute_normals_op (read off its SASS):
+ *   a*(1-t) + b*t  ->  fmaf(a, 1-t, b*t)          (first product fused)
+ * except the z-stage at t.z that the compiler shares between the x+- and y+- samples, where
+ *   c00, c01       ->  fmaf(b, t, a*(1-t))        (second product fused);
+ *   |g| = sqrtf(fmaf(gz,gz, fmaf(gx,gx, gy*gy)));  all divisions and the sqrt are IEEE-rounded. */
+static inline float mix_a(float a, float b, float t, float omt) { return fmaf(a, omt, b * t); }
+static inline float mix_b(float a, float b, float t, float omt) { return fmaf(b, t, a * omt); }
+static inline float clamp01(float t) { return fmaxf(0.01f, fminf(0.99f, t)); }
 
-/* src/its.cu:203-267 for one intersection point p of a cell (float32, uncontracted: the reference's
- * own contraction pattern is compiler-chosen, so normals are compared with a tolerance) */
-static f3 cell_normal(f3 p, const f3 *cp, const float *cv) {
+static f3 cell_normal(f3 p, const f3 *cp, const float *v) {
     f3 cmin = cp[0];
-    f3 csz = {cp[7].x - cp[0].x, cp[7].y - cp[0].y, cp[7].z - cp[0].z};
-    float tx = (p.x - cmin.x) / csz.x, ty = (p.y - cmin.y) / csz.y, tz = (p.z - cmin.z) / csz.z;
-    tx = fmaxf(0.01f, fminf(0.99f, tx));
-    ty = fmaxf(0.01f, fminf(0.99f, ty));
-    tz = fmaxf(0.01f, fminf(0.99f, tz));
+    float sx = cp[7].x - cp[0].x, sy = cp[7].y - cp[0].y, sz = cp[7].z - cp[0].z;
+    float tx = clamp01((p.x - cmin.x) / sx), ty = clamp01((p.y - cmin.y) / sy), tz = clamp01((p.z - cmin.z) / sz);
     const float eps = 0.02f;
     float xp = fminf(tx + eps, 0.99f), xm = fmaxf(tx - eps, 0.01f);
     float yp = fminf(ty + eps, 0.99f), ym = fmaxf(ty - eps, 0.01f);
     float zp = fminf(tz + eps, 0.99f), zm = fmaxf(tz - eps, 0.01f);
-    float dfdx = (trilinear(xp, ty, tz, cv) - trilinear(xm, ty, tz, cv)) / ((xp - xm) * csz.x);
-    float dfdy = (trilinear(tx, yp, tz, cv) - trilinear(tx, ym, tz, cv)) / ((yp - ym) * csz.y);
-    float dfdz = (trilinear(tx, ty, zp, cv) - trilinear(tx, ty, zm, cv)) / ((zp - zm) * csz.z);
-    float len = sqrtf(dfdx * dfdx + dfdy * dfdy + dfdz * dfdz);
+    float otx = 1 - tx, oty = 1 - ty, otz = 1 - tz;
+    float c00 = mix_b(v[0], v[1], tz, otz), c01 = mix_b(v[2], v[3], tz, otz);
+    float c10 = mix_a(v[4], v[5], tz, otz), c11 = mix_a(v[6], v[7], tz, otz);
+    float c0 = mix_a(c00, c01, ty, oty), c1 = mix_a(c10, c11, ty, oty);
+    float fxp = mix_a(c0, c1, xp, 1 - xp), fxm = mix_a(c0, c1, xm, 1 - xm);
+    float gx = (fxp - fxm) / (sx * (xp - xm));
+    float oyp = 1 - yp, oym = 1 - ym;
+    float fyp = mix_a(mix_a(c00, c01, yp, oyp), mix_a(c10, c11, yp, oyp), tx, otx);
+    float fym = mix_a(mix_a(c00, c01, ym, oym), mix_a(c10, c11, ym, oym), tx, otx);
+    float gy = (fyp - fym) / (sy * (yp - ym));
+    float ozp = 1 - zp, ozm = 1 - zm;
+    float p0 = mix_a(mix_a(v[0], v[1], zp, ozp), mix_a(v[2], v[3], zp, ozp), ty, oty);
+    float p1 = mix_a(mix_a(v[4], v[5], zp, ozp), mix_a(v[6], v[7], zp, ozp), ty, oty);
+    float m0 = mix_a(mix_a(v[0], v[1], zm, ozm), mix_a(v[2], v[3], zm, ozm), ty, oty);
+    float m1 = mix_a(mix_a(v[4], v[5], zm, ozm), mix_a(v[6], v[7], zm, ozm), ty, oty);
+    float fzp = mix_a(p0, p1, tx, otx), fzm = mix_a(m0, m1, tx, otx);
+    float gz = (fzp - fzm) / (sz * (zp - zm));
+    float len = sqrtf(fmaf(gz, gz, fmaf(gx, gx, gy * gy)));
     f3 n;
-    if (len > 1e-8f) { n.x = dfdx / len; n.y = dfdy / len; n.z = dfdz / len; }
+    if (len > 1e-8f) { n.x = gx / len; n.y = gy / len; n.z = gz / len; }
     else { n.x = 0; n.y = 0; n.z = 1; }
     return n;
 }
@@ -442,7 +451,7 @@ static int cell_cmp(const void *a, const void *b) {
     return x < y ? -1 : x > y;
 }
 
-/* src/dc.cu:161-218 with the solve of src/batched_la.cu:151-179 done in float64.
+/* src/dc.cu:161-218: QEF in the reference's float32 arithmetic, solve of src/batched_la.cu:151-179 in float64.
  * `its` must carry normals.  Quads with a neighbour cell outside the cell grid (either side) or
  * absent from the active list are skipped (the reference only checks the lower side,
  * include/utils.cuh:128-135, and is undefined otherwise). */
@@ -453,24 +462,29 @@ int orc_dual_contouring(const orc_its *its, int64_t X, int64_t Y, int64_t Z, con
     out->dual_v = (double *) malloc((size_t) (S > 0 ? S : 1) * 3 * sizeof(double));
     f3 *dvf = (f3 *) malloc((size_t) (S > 0 ? S : 1) * sizeof(f3));
     for (int64_t s = 0; s < S; s++) {
-        /* src/dc.cu:27-64 (accumulated in double from the float32 points/normals) */
-        double A[3][3] = {{0}}, b[3] = {0}, pavg[3] = {0};
+        /* src/dc.cu:27-64 in float32 with the reference's contraction pattern (SASS of get_qef_op):
+         *   d = fmaf(n.z,p.z, fmaf(n.x,p.x, n.y*p.y));  ATA_ij = fmaf(n_i,n_j,ATA_ij);  ATb_i = fmaf(n_i,d,ATb_i)
+         *   p_avg = sum(p)/float(k);  ATA_ii += reg;  ATb_i = fmaf(p_avg_i, reg, ATb_i) */
+        float Af[3][3] = {{0}}, bf[3] = {0}, sum[3] = {0};
         int64_t i0 = its->cell_offsets[s], i1 = its->cell_offsets[s + 1];
         for (int64_t i = i0; i < i1; i++) {
-            double n[3] = {its->normals[3 * i], its->normals[3 * i + 1], its->normals[3 * i + 2]};
-            double p[3] = {its->points[3 * i], its->points[3 * i + 1], its->points[3 * i + 2]};
-            double np = n[0] * p[0] + n[1] * p[1] + n[2] * p[2];
+            float n[3] = {its->normals[3 * i], its->normals[3 * i + 1], its->normals[3 * i + 2]};
+            float p[3] = {its->points[3 * i], its->points[3 * i + 1], its->points[3 * i + 2]};
+            for (int r = 0; r < 3; r++) sum[r] = sum[r] + p[r];
+            float d = fmaf(n[2], p[2], fmaf(n[0], p[0], n[1] * p[1]));
             for (int r = 0; r < 3; r++) {
-                for (int c = 0; c < 3; c++) A[r][c] += n[r] * n[c];
-                b[r] += n[r] * np;
-                pavg[r] += p[r];
+                for (int c = 0; c < 3; c++) Af[r][c] = fmaf(n[r], n[c], Af[r][c]);
+                bf[r] = fmaf(n[r], d, bf[r]);
             }
         }
+        float kf = (float) (uint32_t) (i1 - i0);
+        double A[3][3], b[3];
         for (int r = 0; r < 3; r++) {
-            pavg[r] /= (double) (i1 - i0);
-            A[r][r] += (double) reg;
-            b[r] += (double) reg * pavg[r];
+            float pavg = sum[r] / kf;
+            Af[r][r] = Af[r][r] + reg;
+            bf[r] = fmaf(pavg, reg, bf[r]);
         }
+        for (int r = 0; r < 3; r++) { b[r] = bf[r]; for (int c = 0; c < 3; c++) A[r][c] = Af[r][c]; }
         /* pinv via eigen-decomposition (A symmetric PSD => singular values = eigenvalues) */
         double V[3][3], w[3];
         jacobi3(A, V, w);

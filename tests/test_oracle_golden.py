@@ -113,10 +113,11 @@ def nearest_dist(a, b):
 
 @pytest.mark.parametrize("path", sorted(GOLDEN.glob("dc_*.npz")), ids=lambda p: p.stem)
 def test_oracle_dc_matches_reference_cuda_fixtures(path):
-    """Intersections: integer/index data and interpolated points bit-exact; normals within 1e-5
-    (the reference's FMA contraction pattern is compiler-chosen).  Dual vertices: the reference solves
-    in float32 through cuSOLVER, the oracle in float64, so positions agree to a tolerance only
-    (SURVEY.md 7.4 item 5): same vertex / face counts, every vertex within 2e-3 of a cell size."""
+    """Intersections: integer/index data, interpolated points AND normals bit-exact (the oracle mirrors
+    the FMA contraction pattern of the reference's SASS).  Dual vertices: the reference solves the 3x3
+    system in float32 through cuSOLVER's Jacobi SVD, the oracle in float64, so positions agree only to the
+    reference's own solver noise (measured 5e-4..1.1e-3 of a cell on these
+    fixtures): same face count, every reference vertex within 2e-3 of a cell size of an oracle vertex."""
     g = np.load(path)
     vals, level = g["values"], float(g["level"])
     its = oracle.get_intersection(vals, level=level, compute_normals=True)
@@ -125,7 +126,7 @@ def test_oracle_dc_matches_reference_cuda_fixtures(path):
     assert np.array_equal(its.is_out, g["its_is_out"])
     assert np.array_equal(its.cell_indices, g["its_cell_indices"].astype(np.int64))
     assert np.array_equal(its.cell_offsets, g["its_cell_offsets"].astype(np.int64))
-    assert np.abs(its.normals - g["its_normals"]).max() < 1e-5
+    assert np.array_equal(its.normals.view(np.uint32), g["its_normals"].view(np.uint32))
     dc = oracle.dual_contouring(its, vals.shape)
     assert len(dc["f"]) == len(g["f"])
     cell = 2.0 / (min(vals.shape) - 1)
