@@ -136,6 +136,47 @@ int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int6
                          int64_t n_candidates, float *V, int32_t *F, int32_t *quads_out, void *stream,
                          int64_t *counts_out);
 
+/* ---- SparseGrid  (src/grid/sparse.cu, src/isoext_ext.cu:170-303) ------------------------------
+ * A sparse grid is a sorted list of n cell indices (int64 here; the reference's int32 API caps the grid
+ * at INT_MAX points) plus (n,8) f32 corner values in the Morton corner order of include/utils.cuh:32-60.
+ * X,Y,Z = points per axis of the enclosing uniform grid. */
+/* get_points / get_points_by_cell_indices (src/grid/sparse.cu:21-43,144-148): out = (n,8,3) f32 */
+int isoext_sparse_points(int64_t X, int64_t Y, int64_t Z, const float *aabb_min, const float *aabb_max,
+                         const int64_t *cell_idx, int64_t n, float *d_out, void *stream);
+/* filter_cell_indices (src/grid/sparse.cu:150-179): keep[i] = 1 iff cell i's case is not 0/255 */
+int isoext_sparse_crossing(const float *values8, int64_t n, float level, unsigned char *keep, void *stream);
+/* marching_cubes on a SparseGrid: phase 1 counts_out[0..1] = T, Vc; phase 2 counts_out[0] = V */
+size_t isoext_mc_sparse_workspace_bytes(int64_t n);
+size_t isoext_sparse_scratch_bytes(int64_t n_candidates);
+int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
+                           const float *aabb_min, const float *aabb_max, float level, int method, void *workspace,
+                           size_t workspace_bytes, void *stream, int64_t *counts_out);
+int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
+                          const float *aabb_min, const float *aabb_max, float level, int method, void *workspace,
+                          size_t workspace_bytes, void *scratch, size_t scratch_bytes, int64_t n_candidates, float *V,
+                          int32_t *F, void *stream, int64_t *counts_out);
+/* get_intersection on a SparseGrid: cinfo / cellslot / its_off are caller-owned (n+1) u32 arrays kept by
+ * the Intersection.  Phase 1 counts_out[0..1] = active cells, intersections.  emit mode: 0 points,
+ * 1 points + normals, 2 normals only (compute_intersection_normals). */
+int isoext_its_sparse_count(const float *values8, int64_t n, float level, uint32_t *cinfo, uint32_t *cellslot,
+                            uint32_t *its_off, void *workspace, size_t workspace_bytes, void *stream, int64_t *counts_out);
+int isoext_its_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
+                           const float *aabb_min, const float *aabb_max, float level, int mode, const uint32_t *cinfo,
+                           const uint32_t *cellslot, const uint32_t *its_off, int64_t n_cells, int64_t n_its, float *points,
+                           float *normals, uint32_t *cell_offsets, int64_t *cell_indices, void *stream);
+/* dual_contouring on a SparseGrid: neighbour cells by binary search in cell_idx (replaces the dense
+ * X*Y*Z idx_map of src/grid/sparse.cu:223-243).  Phase 1 counts_out[0..1] = Q, Vc; phase 2 [0] = V. */
+size_t isoext_dc_sparse_workspace_bytes(int64_t n);
+int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
+                           const float *aabb_min, const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot,
+                           const uint32_t *its_off, const float *points, const float *normals, float reg, float svd_tol,
+                           float *dual_v, void *workspace, size_t workspace_bytes, void *stream, int64_t *counts_out);
+int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z, const float *aabb_min,
+                          const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot, const float *dual_v,
+                          void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
+                          int64_t n_candidates, float *V, int32_t *F, int32_t *quads_out, void *stream,
+                          int64_t *counts_out);
+
 /* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
  * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->
  * base_mine + (id - n_lo); id >= n_hi -> base_next + (id - n_hi). */

@@ -13,10 +13,12 @@ from . import sdf, utils  # noqa: E402,F401
 from .dc import Intersection, dual_contouring, get_intersection  # noqa: E402,F401
 from .grid import Grid, UniformGrid  # noqa: E402,F401
 from .mc import marching_cubes  # noqa: E402,F401
+from .sparse import SparseGrid  # noqa: E402,F401
 from .utils import gaussian_smooth, make_grid, write_obj  # noqa: E402,F401
 
 __all__ = [
     "Intersection",
+    "SparseGrid",
     "UniformGrid",
     "dual_contouring",
     "get_intersection",
