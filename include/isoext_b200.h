@@ -49,6 +49,10 @@ int isoext_abi_version(void);
  * per-axis term of get_vtx_pos_op (include/utils.cuh:71-79).  Host-side; no GPU needed. */
 float isoext_axis_position(int64_t i, int64_t res, float amin, float amax);
 
+/* Tuning knob of the volume-streaming kernel (development only): low byte = variant, next byte =
+ * launched blocks per SM; 0 = default. */
+int isoext_debug_set_signbits_variant(int v);
+
 /* ---- measurement hooks (no reference counterpart; used by bench.py only) ---------------------
  * begin(): reset the launch counter and start recording a CUDA-event pair around every launch of the
  * volume-streaming kernel (the roofline's dominant kernel) on the stream it is launched on.

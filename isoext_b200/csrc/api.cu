@@ -13,6 +13,7 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 long long g_kernel_launches = 0;
+int g_signbits_variant = 0;
 StreamTimer g_stream_timer;
 void stream_timer_mark(cudaStream_t s) {
     StreamTimer &t = g_stream_timer;
@@ -26,6 +27,8 @@ void stream_timer_mark(cudaStream_t s) {
 }   // namespace isx
 
 extern "C" {
+// tuning knob for the streaming kernel: low byte = variant, next byte = blocks per SM (0 = default)
+int isoext_debug_set_signbits_variant(int v) { isx::g_signbits_variant = v; return 0; }
 // ---- measurement hooks (bench.py): count kernel launches, time the volume-streaming kernel --------
 int isoext_profile_begin(void) {
     isx::g_stream_timer.enabled = true;

@@ -37,6 +37,7 @@ int fail(int code, const std::string &msg);
 // Kernel-launch accounting and optional per-launch timing of the dominant (volume-streaming) kernel.
 // bench.py reads these through isoext_profile_begin/end (api.cu); the product path never depends on them.
 extern long long g_kernel_launches;
+extern int g_signbits_variant;
 struct StreamTimer {
     bool enabled = false;
     static constexpr int kMaxPairs = 4096;

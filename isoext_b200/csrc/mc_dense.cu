@@ -375,14 +375,7 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
     ISX_CUDA(cudaMemsetAsync(b.used, 0, 3 * ((size_t) cap + 2), stream));
 
     const int sms = device_sms();
-    {
-        i64 groups = p.P >> 7;
-        i64 want = (groups + 8 * SB_UNROLL - 1) / (8 * SB_UNROLL);   // 8 warps per block
-        int blocks = (int) (want < 1 ? 1 : (want > (i64) sms * 8 ? (i64) sms * 8 : want));
-        stream_timer_mark(stream);
-        ISX_LAUNCH(k_signbits, blocks, 256, 0, stream, values, b.bits, p.P, level);
-        stream_timer_mark(stream);
-    }
+    launch_signbits(values, b.bits, p.P, level, stream);
     if ((p.g.Z & 127) == 0) {
         const u32 nspans = p.R * (u32) (p.g.Z >> 7);
         ISX_LAUNCH(k_compact128, (nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
