@@ -71,10 +71,11 @@ int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, 
 size_t isoext_mc_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t cap_entries);
 size_t isoext_mc_dense_scratch_bytes(int64_t n_candidates);
 
-/* Phase 1.  values: (X,Y,Z) f32, 16-byte aligned, read exactly once from HBM.
+/* Phase 1.  values: (X,Y,Z) f32, 32-byte aligned, read exactly once from HBM.
  * emit_x_lo/hi: local cell-x range [lo,hi) whose triangles are emitted (whole slab: 0, X-1);
  * cells outside it still decide which shared-plane vertices exist (slab halo layers).
- * counts_out[0..2] = active entries S, triangles T, vertex candidates Vc (>= welded vertex count). */
+ * counts_out[0..3] = active entries S, triangles T, vertex candidates Vc (>= welded vertex count),
+ * n_big = candidates in x-plane buckets too large for the shared-memory sort (pass it to emit). */
 int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                           const float *aabb_min, const float *aabb_max, float level, int method,
                           int64_t emit_x_lo, int64_t emit_x_hi, void *workspace, size_t workspace_bytes,
@@ -89,7 +90,7 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
 int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                          const float *aabb_min, const float *aabb_max, float level, int method,
                          int64_t emit_x_lo, int64_t emit_x_hi, void *workspace, size_t workspace_bytes,
-                         int64_t cap_entries, void *scratch, size_t scratch_bytes, int64_t n_candidates,
+                         int64_t cap_entries, void *scratch, size_t scratch_bytes, int64_t n_candidates, int64_t n_big,
                          float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
                          int64_t *counts_out);
 
@@ -180,6 +181,18 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
                           void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
                           int64_t n_candidates, float *V, int32_t *F, int32_t *quads_out, void *stream,
                           int64_t *counts_out);
+
+/* Single-call fast path of marching_cubes on a UniformGrid: both phases enqueued back to back, ONE
+ * stream synchronisation.  The caller supplies capacities (typically the sizes of the previous extraction
+ * of this grid): V holds cand_cap rows, F tri_cap rows, scratch = isoext_mc_dense_scratch_bytes(cand_cap).
+ * Returns 0 with counts_out[0..6] = {S, T, Vc, n_big, V, n_lo, n_hi}; returns 1 ("not completed",
+ * counts_out[0..3] valid, outputs undefined) if a capacity was exceeded or oversized x-buckets need the
+ * radix fallback -- the caller then uses isoext_mc_dense_count + isoext_mc_dense_emit. */
+int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                        const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
+                        int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
+                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, float x_lo_threshold,
+                        float x_hi_threshold, float *V, int32_t *F, void *stream, int64_t *counts_out);
 
 /* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
  * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->

@@ -33,7 +33,7 @@ SIGNATURES = {
     "isoext_mc_dense_count": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
                                      _vp, _sz, _i64, _vp, _pi64]),
     "isoext_mc_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
-                                    _vp, _sz, _i64, _vp, _sz, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
+                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
     "isoext_its_dense_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "isoext_its_dense_count": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _vp, _sz, _i64, _vp, _vp, _vp, _vp,
                                       _vp, _pi64]),
@@ -61,6 +61,8 @@ SIGNATURES = {
                                       _vp, _pi64]),
     "isoext_dc_sparse_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i64, _vp, _vp, _vp,
                                      _vp, _pi64]),
+    "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
+                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
 }
 

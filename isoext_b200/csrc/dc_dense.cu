@@ -437,7 +437,7 @@ int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z,
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, 0, X - 1, &p);
     if (rc != OK) return rc;
-    if ((reinterpret_cast<uintptr_t>(values) & 15u) != 0) return fail(E_INVALID, "values must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
     if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
     Carver c(workspace);
     ItsWs b;

@@ -32,6 +32,8 @@ enum Counter : int {
     C_Q = 10,         // quads (DC)
     C_TICKET_D = 11,
     C_TICKET_E = 12,
+    C_NBIG = 13,      // candidates in x-buckets larger than SEG_CAP (radix fallback needed if > 0)
+    C_MAXB = 14,      // largest x-bucket
     C_COUNT = 16
 };
 

@@ -15,6 +15,7 @@
 #include "dense.cuh"
 #include "radix.cuh"
 #include "weld.cuh"
+#include "segsort.cuh"
 
 #include <cstring>
 
@@ -41,24 +42,33 @@ struct McBuffers {
     unsigned char *ntri, *trimask;
     unsigned char *used;   // 3 per entry
     u32 *tri_off, *cand_info;
-    u64 *descT, *descU;
+    u64 *descT, *descU, *descV;
+    size_t zero_bytes;       // bytes from `counters` that one memset clears at the start of a call
+    unsigned char *bdelta;   // per entry: x-bucket offset (+1) of its 3 owned edge vertices, 2 bits each
+    SegHead seg;             // bucket histogram / offsets over the X+2 x-plane buckets
 };
 
 static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *out) {
     McBuffers b;
+    // --- everything that must be zero at the start of a call is contiguous: ONE memset per call ---
     b.counters = c.take<u32>(C_COUNT);
+    b.descA = c.take<u64>((size_t) p.NQ / CP_TILE + 2);
+    b.descT = c.take<u64>(cap / SE_TILE + 2);
+    b.descU = c.take<u64>(cap / SE_TILE + 2);
+    b.descV = c.take<u64>(3 * cap / UQ_TILE + 2);
+    SegHead::carve(c, (size_t) p.g.X + 2, &b.seg);
+    b.used = c.take<unsigned char>(3 * (cap + 2));
+    b.zero_bytes = (size_t) ((char *) (b.used + 3 * (cap + 2)) - (char *) b.counters);
+    // --- the rest is fully overwritten before it is read ---
     b.bits = c.take<u32>(signbits_words(p.P));
     b.row_start = c.take<u32>((size_t) p.R + 2);
-    b.descA = c.take<u64>((size_t) p.NQ / CP_TILE + 2);
     b.entries = c.take<uint2>(cap + 1);
     b.nb = c.take<u32>(3 * cap);
     b.ntri = c.take<unsigned char>(cap);
     b.trimask = c.take<unsigned char>(cap);
-    b.used = c.take<unsigned char>(3 * (cap + 2));
     b.tri_off = c.take<u32>(cap);
     b.cand_info = c.take<u32>(cap + 1);
-    b.descT = c.take<u64>(cap / SE_TILE + 2);
-    b.descU = c.take<u64>(cap / SE_TILE + 2);
+    b.bdelta = c.take<unsigned char>(cap + 1);
     if (out) *out = b;
     return c.bytes();
 }
@@ -66,8 +76,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
 struct McScratch {
     u32 *kx, *ky, *kz;
     u32 *cand_rank;
-    u64 *descV;
-    RadixBuffers radix;
+    SegScratch seg;
 };
 
 static size_t carve_mc_scratch(Carver &c, size_t nc, McScratch *out) {
@@ -76,10 +85,41 @@ static size_t carve_mc_scratch(Carver &c, size_t nc, McScratch *out) {
     s.ky = c.take<u32>(nc);
     s.kz = c.take<u32>(nc);
     s.cand_rank = c.take<u32>(nc);
-    s.descV = c.take<u64>(nc / UQ_TILE + 2);
-    RadixBuffers::carve(c, nc, &s.radix);
+    SegScratch::carve(c, nc, &s.seg);
     if (out) *out = s;
     return c.bytes();
+}
+
+// x-plane bucket of the vertices on the entry's owned edges, relative to the entry's own plane x:
+// code = delta + 1 in {0,1,2}, 2 bits per axis (bit 0-1: +z edge, 2-3: +y, 4-5: +x).  The bucket of a
+// position is b = #{i : px[i] <= x'} - 1, a monotone function of x' (segsort.cuh); for a vertex owned by
+// plane x it is x-1 (an in-plane vertex whose x rounded just below px[x]), x, or x+1 (an x-edge vertex
+// that landed exactly on the next plane).
+__device__ __forceinline__ u32 owned_bucket_deltas(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, u32 own) {
+    if (!own) return 0x15u;
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 x = r / Y;
+    const i64 n = (i64) r * Z + z;
+    const u32 xg = x + (u32) p.g.x_off;
+    const float v0 = __ldg(values + n);
+    const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+    u32 code = 0x15u;   // delta 0 everywhere
+    if (own & 1u) {
+        const float t = edge_t(v0, __ldg(values + n + 1), p.level);
+        if (lerp_ref(t, px0, px0) < px0) code = (code & ~0x03u) | 0x00u;
+    }
+    if (own & 2u) {
+        const float t = edge_t(v0, __ldg(values + n + Z), p.level);
+        if (lerp_ref(t, px0, px0) < px0) code = (code & ~0x0cu) | 0x00u;
+    }
+    if (own & 4u) {
+        const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
+        const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+        const float xv = lerp_ref(t, px0, px1);
+        if (xv >= px1) code = (code & ~0x30u) | 0x20u;
+        else if (xv < px0) code = (code & ~0x30u) | 0x00u;
+    }
+    return code;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -89,13 +129,14 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
                                                    const uint2 *__restrict__ entries, const u32 *__restrict__ row_start,
                                                    u32 cap, const u32 *__restrict__ counters, u32 *__restrict__ nb,
                                                    unsigned char *__restrict__ ntri, unsigned char *__restrict__ trimask,
-                                                   unsigned char *__restrict__ used) {
+                                                   unsigned char *__restrict__ used, unsigned char *__restrict__ bdelta) {
     const u32 S = counters[C_S];
     if (S > cap) return;
     const u32 Y = (u32) p.g.Y;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const uint2 e = entries[s];
         const u32 w = e.y;
+        bdelta[s] = (unsigned char) owned_bucket_deltas(values, p, e.x, ent_z(w), ent_own(w));
         if (!ent_cell(w) || ent_case(w) == 0u || ent_case(w) == 255u) {
             ntri[s] = 0;
             trimask[s] = 0;
@@ -149,18 +190,26 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__ counters, const unsigned char *__restrict__ ntri,
                                                       const unsigned char *__restrict__ used, u32 *__restrict__ tri_off,
-                                                      u32 *__restrict__ cand_info, u64 *__restrict__ descT, u64 *__restrict__ descU) {
+                                                      u32 *__restrict__ cand_info, u64 *__restrict__ descT, u64 *__restrict__ descU,
+                                                      const uint2 *__restrict__ entries, const unsigned char *__restrict__ bdelta,
+                                                      u32 Y, u32 *__restrict__ bucket_count) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_preT, s_preU;
+    // x-bucket histogram window: the entries of a tile are sorted by x, so almost all of its vertices fall
+    // into a handful of consecutive buckets; count those in shared memory, the rest directly in L2
+    constexpr u32 WIN = 32;
+    __shared__ u32 s_hist[WIN];
     const u32 S = counters[C_S];
     if (S > cap) return;
     const u32 ntiles = (S + SE_TILE - 1) / SE_TILE;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_B], 1u);
+        if (threadIdx.x < WIN) s_hist[threadIdx.x] = 0;
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
+        const u32 win0 = entries[tile * SE_TILE].x / Y;   // bucket of plane x-1 of the tile's first entry
         const u32 s0 = tile * SE_TILE + threadIdx.x * SE_ITEMS;
         u32 nt[SE_ITEMS], um[SE_ITEMS], sumT = 0, sumU = 0;
 #pragma unroll
@@ -171,6 +220,16 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
             if (s < S) {
                 nt[j] = ntri[s];
                 um[j] = (used[3 * s] ? 1u : 0u) | (used[3 * s + 1] ? 2u : 0u) | (used[3 * s + 2] ? 4u : 0u);
+                if (um[j]) {   // x-bucket histogram of the vertices this entry owns (segsort.cuh)
+                    const u32 x = entries[s].x / Y, bd = bdelta[s];
+#pragma unroll
+                    for (int a = 0; a < 3; a++)
+                        if ((um[j] >> a) & 1u) {
+                            const u32 bkt = x + ((bd >> (2 * a)) & 3u);
+                            if (bkt - win0 < WIN) atomicAdd(&s_hist[bkt - win0], 1u);
+                            else atomicAdd(&bucket_count[bkt], 1u);
+                        }
+                }
             }
             sumT += nt[j];
             sumU += __popc(um[j]);
@@ -187,6 +246,7 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
             if ((threadIdx.x & 31) == 0) s_preU = pre;
         }
         __syncthreads();
+        if (threadIdx.x < WIN && s_hist[threadIdx.x]) atomicAdd(&bucket_count[win0 + threadIdx.x], s_hist[threadIdx.x]);
         exT += s_preT;
         exU += s_preU;
 #pragma unroll
@@ -211,9 +271,11 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
-                                                  const u32 *__restrict__ cand_info, u32 *__restrict__ kx,
-                                                  u32 *__restrict__ ky, u32 *__restrict__ kz) {
+                                                  const u32 *__restrict__ cand_info, const unsigned char *__restrict__ bdelta,
+                                                  u32 *__restrict__ kx, u32 *__restrict__ ky, u32 *__restrict__ kz,
+                                                  u32 *__restrict__ cbucket, u32 cand_cap, u32 entry_cap) {
     const u32 S = counters[C_S];
+    if (S > entry_cap || counters[C_VC] > cand_cap) return;   // single-call fast path: the host re-runs with larger buffers
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const u32 ci = cand_info[s];
@@ -226,6 +288,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
         const i64 n = (i64) r * Z + z;
         const float v0 = __ldg(values + n);
         const u32 xg = x + (u32) p.g.x_off;
+        const u32 bd = bdelta[s];
         const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
         const float py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
         const float pz0 = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
@@ -235,6 +298,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             kx[id] = float_key(lerp_ref(t, px0, px0));
             ky[id] = float_key(lerp_ref(t, py0, py0));
             kz[id] = float_key(lerp_ref(t, pz0, pz1));
+            cbucket[id] = x + (bd & 3u);
             id++;
         }
         if (um & 2u) {   // +y edge
@@ -243,6 +307,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             kx[id] = float_key(lerp_ref(t, px0, px0));
             ky[id] = float_key(lerp_ref(t, py0, py1));
             kz[id] = float_key(lerp_ref(t, pz0, pz0));
+            cbucket[id] = x + ((bd >> 2) & 3u);
             id++;
         }
         if (um & 4u) {   // +x edge
@@ -251,6 +316,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             kx[id] = float_key(lerp_ref(t, px0, px1));
             ky[id] = float_key(lerp_ref(t, py0, py0));
             kz[id] = float_key(lerp_ref(t, pz0, pz0));
+            cbucket[id] = x + ((bd >> 4) & 3u);
         }
     }
 }
@@ -262,8 +328,9 @@ __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, c
                                                     const u32 *__restrict__ counters, const u32 *__restrict__ nb,
                                                     const unsigned char *__restrict__ trimask, const u32 *__restrict__ tri_off,
                                                     const u32 *__restrict__ cand_info, const u32 *__restrict__ cand_rank,
-                                                    int *__restrict__ F) {
+                                                    int *__restrict__ F, u32 cand_cap, u32 tri_cap, u32 entry_cap) {
     const u32 S = counters[C_S];
+    if (S > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap) return;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const u32 mask = trimask[s];
         if (!mask) continue;
@@ -350,8 +417,56 @@ size_t isoext_mc_dense_scratch_bytes(int64_t n_candidates) {
     return carve_mc_scratch(c, (size_t) (n_candidates > 0 ? n_candidates : 1), nullptr);
 }
 
+// ---- shared enqueue helpers ---------------------------------------------------------------------
+static int enqueue_phase1(const float *values, const DenseParams &p, int method, const McBuffers &b, u32 cap, cudaStream_t stream) {
+    ISX_CUDA(cudaMemsetAsync(b.counters, 0, b.zero_bytes, stream));
+    const int sms = device_sms();
+    const u32 nb = (u32) p.g.X + 2;   // x-plane buckets (local planes -1 .. X)
+    launch_signbits(values, b.bits, p.P, p.level, stream);
+    if ((p.g.Z & 127) == 0) {
+        const u32 nspans = p.R * (u32) (p.g.Z >> 7);
+        ISX_LAUNCH(k_compact128, (nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+    } else {
+        ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
+    }
+    ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+               b.trimask, b.used, b.bdelta);
+    ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
+               b.entries, b.bdelta, (u32) p.g.Y, b.seg.count);
+    ISX_LAUNCH(k_seg_scan, 1, 1024, 0, stream, nb, b.seg.count, b.seg.start, b.seg.cursor, b.seg.bigoff, b.counters + C_NBIG,
+               b.counters + C_MAXB);
+    ISX_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// host_nc: number of candidates if the host knows it (two-phase path), else 0 with device_counts = true:
+// the kernels then read the counts from the counter block and do nothing if a capacity is exceeded.
+static int enqueue_phase2(const float *values, const DenseParams &p, int method, const McBuffers &b, const McScratch &s,
+                          u32 entry_cap, u32 host_nc, u32 n_big, bool device_counts, u32 cand_cap, u32 tri_cap, float x_lo_threshold,
+                          float x_hi_threshold, float *V, int32_t *F, cudaStream_t stream) {
+    const int sms = device_sms();
+    const u32 *n_dev = device_counts ? b.counters + C_VC : nullptr;
+    const u32 grid_n = device_counts ? cand_cap : host_nc;
+    ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, s.kx, s.ky, s.kz,
+               s.seg.cbucket, cand_cap, entry_cap);
+    ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, (u32) p.g.X + 2, n_big, b.seg, s.seg, stream));
+    const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
+    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, b.descV, klo, khi,
+               n_dev, cand_cap);
+    ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
+               s.cand_rank, F, cand_cap, tri_cap, entry_cap);
+    ISX_CUDA(cudaGetLastError());
+    return OK;
+}
+
+static int read_counters(const McBuffers &b, u32 *h, cudaStream_t stream) {
+    ISX_CUDA(cudaMemcpyAsync(h, b.counters, C_COUNT * sizeof(u32), cudaMemcpyDeviceToHost, stream));
+    ISX_CUDA(cudaStreamSynchronize(stream));
+    return OK;
+}
+
 // Phase 1: classify + compact + per-cell triangle analysis + scans.
-// counts_out[0..2] = entries S, triangles T, vertex candidates Vc (upper bound of the vertex count).
+// counts_out[0..3] = entries S, triangles T, vertex candidates Vc (upper bound of the vertex count), n_big.
 int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                           const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                           int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries,
@@ -361,37 +476,21 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
-    if ((reinterpret_cast<uintptr_t>(values) & 15u) != 0) return fail(E_INVALID, "values must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
     if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
     Carver c(workspace);
     McBuffers b;
     if (carve_mc(c, p, (size_t) cap_entries, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
     const u32 cap = (u32) cap_entries;
-
-    ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
-    ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) p.NQ / CP_TILE + 2) * sizeof(u64), stream));
-    ISX_CUDA(cudaMemsetAsync(b.descT, 0, ((size_t) cap / SE_TILE + 2) * sizeof(u64), stream));
-    ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) cap / SE_TILE + 2) * sizeof(u64), stream));
-    ISX_CUDA(cudaMemsetAsync(b.used, 0, 3 * ((size_t) cap + 2), stream));
-
-    const int sms = device_sms();
-    launch_signbits(values, b.bits, p.P, level, stream);
-    if ((p.g.Z & 127) == 0) {
-        const u32 nspans = p.R * (u32) (p.g.Z >> 7);
-        ISX_LAUNCH(k_compact128, (nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
-    } else {
-        ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
-    }
-    ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
-                                             b.trimask, b.used);
-    ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU);
-    ISX_CUDA(cudaGetLastError());
+    rc = enqueue_phase1(values, p, method, b, cap, stream);
+    if (rc != OK) return rc;
     u32 h[C_COUNT];
-    ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    ISX_CUDA(cudaStreamSynchronize(stream));
+    rc = read_counters(b, h, stream);
+    if (rc != OK) return rc;
     counts_out[0] = h[C_S];
     counts_out[1] = h[C_T];
     counts_out[2] = h[C_VC];
+    counts_out[3] = h[C_NBIG];   // candidates living in x-buckets too large for the shared-memory sort
     if (h[C_S] > cap) return fail(E_CAPACITY, "entry capacity exceeded; retry with cap_entries >= counts_out[0]");
     return OK;
 }
@@ -404,7 +503,7 @@ int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, 
 int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                          const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                          int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
-                         size_t scratch_bytes, int64_t n_candidates, float x_lo_threshold, float x_hi_threshold,
+                         size_t scratch_bytes, int64_t n_candidates, int64_t n_big, float x_lo_threshold, float x_hi_threshold,
                          float *V, int32_t *F, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
@@ -420,23 +519,55 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     Carver cs(scratch);
     McScratch s;
     if (carve_mc_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
-    const u32 nc = (u32) n_candidates;
-    const int sms = device_sms();
-
-    ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
-    ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, s.kx, s.ky, s.kz);
-    ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
-    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV, klo, khi);
-    ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
-                                              s.cand_rank, F);
-    ISX_CUDA(cudaGetLastError());
+    rc = enqueue_phase2(values, p, method, b, s, (u32) cap_entries, (u32) n_candidates, (u32) n_big, false, 0xffffffffu, 0xffffffffu, x_lo_threshold,
+                        x_hi_threshold, V, F, stream);
+    if (rc != OK) return rc;
     u32 h[C_COUNT];
-    ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    ISX_CUDA(cudaStreamSynchronize(stream));
+    rc = read_counters(b, h, stream);
+    if (rc != OK) return rc;
     counts_out[0] = h[C_V];
     counts_out[1] = h[C_NLO];
     counts_out[2] = h[C_NHI];
+    return OK;
+}
+
+// Single-call fast path: both phases are enqueued back to back and the stream is synchronised ONCE.
+// The caller provides output / scratch capacities (typically the sizes of the previous extraction of the
+// same grid): V has room for cand_cap rows, F for tri_cap rows, scratch for cand_cap candidates.
+// Returns ISOEXT_OK with counts_out = {S, T, Vc, n_big, V, n_lo, n_hi} when everything fitted; returns
+// 1 ("not completed") with counts_out[0..3] filled when a capacity was exceeded or the radix fallback is
+// needed (n_big > 0) -- outputs are then undefined and the caller uses count + emit.
+int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                        const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
+                        int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
+                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, float x_lo_threshold, float x_hi_threshold,
+                        float *V, int32_t *F, void *stream_, int64_t *counts_out) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
+    DenseParams p;
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
+    if (rc != OK) return rc;
+    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
+    if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
+    if (cand_cap < 1 || cand_cap >= ((i64) 1 << 29) || tri_cap < 1) return fail(E_INVALID, "capacities out of range");
+    Carver c(workspace);
+    McBuffers b;
+    if (carve_mc(c, p, (size_t) cap_entries, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
+    Carver cs(scratch);
+    McScratch s;
+    if (carve_mc_scratch(cs, (size_t) cand_cap, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
+    const u32 cap = (u32) cap_entries;
+    rc = enqueue_phase1(values, p, method, b, cap, stream);
+    if (rc != OK) return rc;
+    rc = enqueue_phase2(values, p, method, b, s, cap, 0, 0, true, (u32) cand_cap, (u32) (tri_cap > 0xffffffffLL ? 0xffffffffLL : tri_cap),
+                        x_lo_threshold, x_hi_threshold, V, F, stream);
+    if (rc != OK) return rc;
+    u32 h[C_COUNT];
+    rc = read_counters(b, h, stream);
+    if (rc != OK) return rc;
+    counts_out[0] = h[C_S]; counts_out[1] = h[C_T]; counts_out[2] = h[C_VC]; counts_out[3] = h[C_NBIG];
+    counts_out[4] = h[C_V]; counts_out[5] = h[C_NLO]; counts_out[6] = h[C_NHI];
+    if (h[C_S] > cap || h[C_VC] > (u32) cand_cap || (i64) h[C_T] > tri_cap || h[C_NBIG] > 0) return 1;
     return OK;
 }
 

@@ -18,9 +18,12 @@ constexpr int UQ_TILE = 256 * UQ_ITEMS;
 static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restrict__ perm, const u32 *__restrict__ kx,
                                                 const u32 *__restrict__ ky, const u32 *__restrict__ kz,
                                                 u32 *__restrict__ cand_rank, float *__restrict__ V, u32 *__restrict__ counters,
-                                                u64 *__restrict__ desc, u32 key_lo, u32 key_hi) {
+                                                u64 *__restrict__ desc, u32 key_lo, u32 key_hi,
+                                                const u32 *__restrict__ n_dev = nullptr, u32 n_cap = 0xffffffffu) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
+    if (n_dev) n = *n_dev;       // single-call fast path: the count lives on the device
+    if (n > n_cap) return;
     const u32 ntiles = (n + UQ_TILE - 1) / UQ_TILE;
     while (true) {
         __syncthreads();

@@ -121,6 +121,7 @@ class SlabGrid:
         self._ext = torch.full((self.plan["n_ext"], Y, Z), float(default_value), dtype=torch.float32, device=self.device)
         self._ws = _Workspace()
         self._cap_hint = 0
+        self._hints = {}
         lib = _lib.lib()
         px = lambda i: float(lib.isoext_axis_position(i, X, self.aabb_min[0], self.aabb_max[0]))
         self.thresholds = (px(self.plan["c_lo"]) if self.rank > 0 else -math.inf,
@@ -156,7 +157,8 @@ def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae"
     with torch.cuda.device(sg.device):
         v_ext, f, n_lo, n_hi, cap = mc_dense_raw(sg._ext, (p["n_ext"], Y, Z), sg.aabb_min, sg.aabb_max, level, mid, sg._ws,
                                                  cap_hint=sg._cap_hint, x_offset=p["ext_lo"], x_global=X,
-                                                 emit_range=(p["emit_lo"], p["emit_hi"]), x_thresholds=sg.thresholds)
+                                                 emit_range=(p["emit_lo"], p["emit_hi"]), x_thresholds=sg.thresholds,
+                                                 hints=sg._hints)
     sg._cap_hint = cap
     if v_ext is None:
         return (torch.empty((0, 3), dtype=torch.float32, device=sg.device),

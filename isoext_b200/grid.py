@@ -85,6 +85,7 @@ class UniformGrid(Grid):
         self._values = torch.full(self.shape, self.default_value, dtype=torch.float32, device=self.device)
         self._ws = _Workspace()
         self._cap_hint = 0
+        self._hints = {}   # sizes of the previous extraction (single-call fast path of marching_cubes)
 
     # -- sizes ------------------------------------------------------------------------------
     def get_num_cells(self) -> int:

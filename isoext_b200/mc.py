@@ -25,12 +25,16 @@ def _initial_cap(shape) -> int:
 
 
 def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_id, ws, cap_hint=0, x_offset=0,
-                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf)):
+                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf), hints=None):
     """Run the dense pipeline on a (X,Y,Z) float32 CUDA tensor.
 
     Returns ``(V_ext, F, n_lo, n_hi, cap_used)``: ``V_ext`` (n,3) position-sorted welded vertices of
     the slab, ``F`` (T,3) int32 ids into ``V_ext``; ``n_lo``/``n_hi`` split ``V_ext`` by the x
     thresholds (slab ownership; 0 and n on a single GPU).  ``(None, None, 0, 0, cap)`` if empty.
+
+    ``hints``: a dict owned by the caller (one per grid) remembering the sizes of the previous extraction.
+    With hints the single-call fast path (``isoext_mc_dense_run``: one stream sync, no host round trip
+    between the phases) is tried first; any capacity miss falls back to count + emit.
     """
     lib = _lib.lib()
     X, Y, Z = shape
@@ -39,8 +43,32 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     amin, amax = _lib.f3(aabb_min), _lib.f3(aabb_max)
     dev = values.device
     stream = _stream_ptr()
-    counts = (C.c_int64 * 4)()
+    counts = (C.c_int64 * 8)()
     cap = max(int(cap_hint), _initial_cap(shape))
+    thr_lo, thr_hi = float(x_thresholds[0]), float(x_thresholds[1])
+
+    if hints is not None and hints.get("Vc", 0) > 0 and hints.get("T", 0) > 0 and not hints.get("big", False):
+        cand_cap = hints["Vc"] + (hints["Vc"] >> 6) + 16
+        tri_cap = hints["T"] + (hints["T"] >> 6) + 16
+        wsbuf = ws.get("mc_ws", lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap), dev)
+        scratch = ws.get("mc_scratch", lib.isoext_mc_dense_scratch_bytes(cand_cap), dev)
+        V = torch.empty((cand_cap, 3), dtype=torch.float32, device=dev)
+        F = torch.empty((tri_cap, 3), dtype=torch.int32, device=dev)
+        rc = lib.isoext_mc_dense_run(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
+                                     wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(), cand_cap, tri_cap,
+                                     thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), stream, counts)
+        if rc == 0:
+            S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
+            hints.update(Vc=Vc, T=T)
+            if Vc == 0:
+                return None, None, 0, 0, cap
+            return V[:int(counts[4])], F[:T], int(counts[5]), int(counts[6]), max(cap, S)
+        if rc != 1:
+            _lib.check(rc)
+        if int(counts[0]) > cap:
+            cap = int(counts[0]) + 1024
+        # fall through to the two-phase path
+
     while True:
         nbytes = lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap)
         if nbytes == 0:
@@ -53,7 +81,9 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
             continue
         _lib.check(rc)
         break
-    S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
+    S, T, Vc, n_big = int(counts[0]), int(counts[1]), int(counts[2]), int(counts[3])
+    if hints is not None:
+        hints.update(Vc=Vc, T=T, big=n_big > 0)
     if Vc == 0:   # no vertex at all (T == 0 alone is not enough: a slab may own vertices that only
         return None, None, 0, 0, cap   # its neighbour's faces reference)
     sbytes = lib.isoext_mc_dense_scratch_bytes(Vc)
@@ -63,7 +93,7 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     out = (C.c_int64 * 4)()
     _lib.check(lib.isoext_mc_dense_emit(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
                                         lo, hi, wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(),
-                                        Vc, float(x_thresholds[0]), float(x_thresholds[1]), V.data_ptr(), F.data_ptr(),
+                                        Vc, n_big, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(),
                                         stream, out))
     nV, n_lo, n_hi = int(out[0]), int(out[1]), int(out[2])
     return V[:nV], F, n_lo, n_hi, max(cap, S)
@@ -80,7 +110,7 @@ def marching_cubes(grid, level: float = 0.0, method: str = "nagae"):
     if isinstance(grid, UniformGrid):
         with torch.cuda.device(grid.device):
             v, f, _, _, cap = mc_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, mid, grid._ws,
-                                           cap_hint=grid._cap_hint)
+                                           cap_hint=grid._cap_hint, hints=grid._hints)
         grid._cap_hint = cap
         if f is None or f.shape[0] == 0:
             return None, None   # src/isoext_ext.cu:47-49: empty arrays become None
