@@ -53,6 +53,10 @@ float isoext_axis_position(int64_t i, int64_t res, float amin, float amax);
  * launched blocks per SM; 0 = default. */
 int isoext_debug_set_signbits_variant(int v);
 
+/* Development: per-kernel CUDA-event timing of every launch of this library. */
+int isoext_debug_detail_enable(int on);
+int isoext_debug_detail_report(char *buf, int buf_size);
+
 /* ---- measurement hooks (no reference counterpart; used by bench.py only) ---------------------
  * begin(): reset the launch counter and start recording a CUDA-event pair around every launch of the
  * volume-streaming kernel (the roofline's dominant kernel) on the stream it is launched on.

@@ -25,6 +25,8 @@ SIGNATURES = {
     "isoext_abi_version": (_int, []),
     "isoext_axis_position": (_f32, [_i64, _i64, _f32, _f32]),
     "isoext_debug_set_signbits_variant": (_int, [_int]),
+    "isoext_debug_detail_enable": (_int, [_int]),
+    "isoext_debug_detail_report": (_int, [C.c_char_p, _int]),
     "isoext_profile_begin": (_int, []),
     "isoext_profile_end": (_int, [C.POINTER(C.c_double), _pi64, _pi64]),
     "isoext_grid_points_dense": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp]),

@@ -2,6 +2,8 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <map>
+#include <vector>
 
 namespace isx {
 std::string &last_error() {
@@ -11,6 +13,20 @@ std::string &last_error() {
 int fail(int code, const std::string &msg) {
     last_error() = msg;
     return code;
+}
+bool g_detail_timing = false;
+struct DetailRec { const char *name; cudaEvent_t e0, e1; };
+static std::vector<DetailRec> g_detail;
+void detail_mark(const char *name, cudaStream_t s, bool begin) {
+    if (begin) {
+        DetailRec r{name, nullptr, nullptr};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, s);
+        g_detail.push_back(r);
+    } else if (!g_detail.empty()) {
+        cudaEventRecord(g_detail.back().e1, s);
+    }
 }
 long long g_kernel_launches = 0;
 int g_signbits_variant = 0;
@@ -29,6 +45,34 @@ void stream_timer_mark(cudaStream_t s) {
 extern "C" {
 // tuning knob for the streaming kernel: low byte = variant, next byte = blocks per SM (0 = default)
 int isoext_debug_set_signbits_variant(int v) { isx::g_signbits_variant = v; return 0; }
+// Development: per-kernel CUDA-event timing.  enable(1) starts collecting; report() synchronises, writes
+// "name total_us launches" lines into buf and clears the records.
+int isoext_debug_detail_enable(int on) { isx::g_detail_timing = on != 0; return 0; }
+int isoext_debug_detail_report(char *buf, int buf_size) {
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto &r : isx::g_detail) {
+        float ms = 0;
+        if (r.e1 && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            if (!acc.count(r.name)) order.push_back(r.name);
+            acc[r.name].first += ms * 1e3;
+            acc[r.name].second += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    isx::g_detail.clear();
+    std::string out;
+    for (auto &n : order) {
+        char line[256];
+        snprintf(line, sizeof(line), "%-28s %10.1f us total %6d launches %8.2f us each\n", n.c_str(), acc[n].first, acc[n].second,
+                 acc[n].first / acc[n].second);
+        out += line;
+    }
+    snprintf(buf, buf_size, "%s", out.c_str());
+    return 0;
+}
 // ---- measurement hooks (bench.py): count kernel launches, time the volume-streaming kernel --------
 int isoext_profile_begin(void) {
     isx::g_stream_timer.enabled = true;

@@ -47,10 +47,16 @@ struct StreamTimer {
 extern StreamTimer g_stream_timer;
 void stream_timer_mark(cudaStream_t s);   // record the next event of a (begin,end) pair if enabled
 
-#define ISX_LAUNCH(kernel, grid, block, smem, stream, ...)            \
-    do {                                                              \
-        ++isx::g_kernel_launches;                                     \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+// optional per-kernel timing (development): every launch is bracketed by CUDA events
+extern bool g_detail_timing;
+void detail_mark(const char *name, cudaStream_t s, bool begin);
+
+#define ISX_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
+    do {                                                                       \
+        ++isx::g_kernel_launches;                                              \
+        if (isx::g_detail_timing) isx::detail_mark(#kernel, (stream), true);   \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
+        if (isx::g_detail_timing) isx::detail_mark(#kernel, (stream), false);  \
     } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

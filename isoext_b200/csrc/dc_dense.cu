@@ -34,14 +34,16 @@ struct ItsWs {
     u32 *counters;
     u32 *bits;
     u64 *descA, *descC, *descI;
+    unsigned char *span_cnt;
 };
 static size_t carve_its_ws(Carver &c, const DenseParams &p, size_t cap, ItsWs *out) {
     ItsWs b;
     b.counters = c.take<u32>(C_COUNT);
     b.bits = c.take<u32>(signbits_words(p.P));
-    b.descA = c.take<u64>((size_t) p.NQ / CP_TILE + 2);
+    b.descA = c.take<u64>(compact_desc_count(p));
     b.descC = c.take<u64>(cap / IT_TILE + 2);
     b.descI = c.take<u64>(cap / IT_TILE + 2);
+    b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
     if (out) *out = b;
     return c.bytes();
 }
@@ -445,17 +447,14 @@ int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z,
     const u32 cap = (u32) cap_entries;
     uint2 *ent = static_cast<uint2 *>(entries);
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
-    ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) p.NQ / CP_TILE + 2) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(b.descA, 0, compact_desc_count(p) * sizeof(u64), stream));
+    ISX_CUDA(cudaMemsetAsync(row_start, 0, ((size_t) p.R + 2) * sizeof(u32), stream));
+    ISX_CUDA(cudaMemsetAsync(b.span_cnt, 0, compact_span_bytes(p), stream));
     ISX_CUDA(cudaMemsetAsync(b.descC, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descI, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     const int sms = device_sms();
     launch_signbits(values, b.bits, p.P, level, stream);
-    if ((p.g.Z & 127) == 0) {
-        const u32 nspans = p.R * (u32) (p.g.Z >> 7);
-        ISX_LAUNCH(k_compact128, (nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream, b.bits, p, ent, cap, row_start, b.descA, b.counters);
-    } else {
-        ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, b.bits, p, ent, cap, row_start, b.descA, b.counters);
-    }
+    launch_compact(b.bits, p, ent, cap, row_start, b.descA, b.counters, b.span_cnt, stream);
     ISX_LAUNCH(k_its_scan, sms * 4, 256, 0, stream, cap, b.counters, ent, cellslot, its_off, b.descC, b.descI);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];

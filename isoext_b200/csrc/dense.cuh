@@ -311,39 +311,40 @@ struct SpanBits {
     bool hasX, hasY, last;        // last: this span ends the row (no z+1 neighbour for its last point)
 };
 
-__device__ __forceinline__ void span_load(const u32 *__restrict__ bits, const DenseParams &p, u32 r, u32 x, u32 y, u32 c4,
-                                          u32 spr, SpanBits &k) {
-    const u32 Z = (u32) p.g.Z;
+// Loads the span's four rows from the shared-memory tile: plane 0 = rows [r0, r0+R], plane 1 = rows
+// [r0+Y, r0+Y+R] of the bit volume (spr uint4 per row), staged by k_compact128.
+__device__ __forceinline__ void span_load(const u32 *__restrict__ sm0, const u32 *__restrict__ sm1, const DenseParams &p, u32 r,
+                                          u32 rl, u32 x, u32 y, u32 c4, u32 spr, SpanBits &k) {
     k.r = r;
     k.z0 = c4 * 128u;
     k.hasY = y + 1u < (u32) p.g.Y;
     k.hasX = x + 1u < (u32) p.g.X;
     k.last = c4 + 1u == spr;
-    const i64 w = ((i64) r * Z + k.z0) >> 5;   // multiple of 4: aligned uint4
-    const i64 wy = w + (Z >> 5), wx = w + (p.YZ >> 5);
-    const uint4 A = __ldg(reinterpret_cast<const uint4 *>(bits + w));
+    const u32 wpr = spr * 4u;                 // words per row
+    const u32 o = rl * wpr + c4 * 4u;         // word offset of the span inside a plane of the tile
+    const uint4 A = *reinterpret_cast<const uint4 *>(sm0 + o);
     k.a[0] = A.x; k.a[1] = A.y; k.a[2] = A.z; k.a[3] = A.w;
-    k.a[4] = k.last ? 0u : __ldg(bits + w + 4);
+    k.a[4] = k.last ? 0u : sm0[o + 4];
     if (k.hasY) {
-        const uint4 B = __ldg(reinterpret_cast<const uint4 *>(bits + wy));
+        const uint4 B = *reinterpret_cast<const uint4 *>(sm0 + o + wpr);
         k.b[0] = B.x; k.b[1] = B.y; k.b[2] = B.z; k.b[3] = B.w;
-        k.b[4] = k.last ? 0u : __ldg(bits + wy + 4);
+        k.b[4] = k.last ? 0u : sm0[o + wpr + 4];
     } else {
 #pragma unroll
         for (int j = 0; j < 5; j++) k.b[j] = k.a[j];
     }
     if (k.hasX) {
-        const uint4 Cc = __ldg(reinterpret_cast<const uint4 *>(bits + wx));
+        const uint4 Cc = *reinterpret_cast<const uint4 *>(sm1 + o);
         k.c[0] = Cc.x; k.c[1] = Cc.y; k.c[2] = Cc.z; k.c[3] = Cc.w;
-        k.c[4] = k.last ? 0u : __ldg(bits + wx + 4);
+        k.c[4] = k.last ? 0u : sm1[o + 4];
     } else {
 #pragma unroll
         for (int j = 0; j < 5; j++) k.c[j] = k.a[j];
     }
     if (k.hasX && k.hasY) {
-        const uint4 D = __ldg(reinterpret_cast<const uint4 *>(bits + wx + (Z >> 5)));
+        const uint4 D = *reinterpret_cast<const uint4 *>(sm1 + o + wpr);
         k.d[0] = D.x; k.d[1] = D.y; k.d[2] = D.z; k.d[3] = D.w;
-        k.d[4] = k.last ? 0u : __ldg(bits + wx + (Z >> 5) + 4);
+        k.d[4] = k.last ? 0u : sm1[o + wpr + 4];
     } else {
 #pragma unroll
         for (int j = 0; j < 5; j++) k.d[j] = k.hasX ? k.c[j] : (k.hasY ? k.b[j] : k.a[j]);
@@ -386,85 +387,203 @@ __device__ __forceinline__ u32 span_word_masks(const SpanBits &k, int j, u32 &a0
     return cellact | ez | ey | ex;
 }
 
-static __global__ void __launch_bounds__(256) k_compact128(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
-                                                    u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
-                                                    u32 *__restrict__ counters) {
-    __shared__ u32 sw[33];
-    __shared__ u32 s_tile, s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_A], 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
-    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
-    const u32 spr = Z >> 7;                 // spans per row
-    const u32 nspans = p.R * spr;
-    const u32 u0 = tile * SP_TILE + threadIdx.x * SP_ITEMS;
-    u32 r0 = u0 / spr, c0 = u0 - r0 * spr, x0 = r0 / Y, y0 = r0 - x0 * Y;
+// ---- span fast path, three sync-free stages (Z % 128 == 0) -------------------------------------
+//   k_rowcount128  thread = 128-point span, straight from L2: branch-free uniformity test; only the ~1 %
+//                  mixed spans are classified in detail and add their entry count to row_count[r]
+//   k_scan_rows    decoupled look-back exclusive scan over the X*Y row counts (in place) -> row_start, S
+//   k_rowfill128   thread = row that owns entries: re-classifies its spans and writes the entries
+// (a single-pass chained-scan version of this stage spent its time at barriers waiting for the
+//  look-back warp and ran 3x slower at 1024^3; see profiles/)
+struct SpanRows {
+    const uint4 *a, *c;   // row (x,y) in plane x and in plane x+1 (aliases plane x when x+1 does not exist)
+    u32 dy;               // uint4 offset of row y+1 (0 when it does not exist)
+    bool hasX, hasY, last;
+};
 
-    u32 cnt = 0, mixed = 0;
-    {
-        u32 r = r0, c4 = c0, x = x0, y = y0;
+// global-memory variant of span_load (rows addressed through SpanRows)
+__device__ __forceinline__ void span_load_g(const SpanRows &q, u32 r, u32 c4, SpanBits &k) {
+    k.r = r;
+    k.z0 = c4 * 128u;
+    k.hasX = q.hasX; k.hasY = q.hasY; k.last = q.last;
+    const uint4 A = __ldg(q.a + c4), B = __ldg(q.a + q.dy + c4), Cc = __ldg(q.c + c4), D = __ldg(q.c + q.dy + c4);
+    k.a[0] = A.x; k.a[1] = A.y; k.a[2] = A.z; k.a[3] = A.w;
+    k.b[0] = B.x; k.b[1] = B.y; k.b[2] = B.z; k.b[3] = B.w;
+    k.c[0] = Cc.x; k.c[1] = Cc.y; k.c[2] = Cc.z; k.c[3] = Cc.w;
+    k.d[0] = D.x; k.d[1] = D.y; k.d[2] = D.z; k.d[3] = D.w;
+    if (q.last) {
+        k.a[4] = k.b[4] = k.c[4] = k.d[4] = 0u;
+    } else {
+        k.a[4] = __ldg(reinterpret_cast<const u32 *>(q.a + c4 + 1));
+        k.b[4] = __ldg(reinterpret_cast<const u32 *>(q.a + q.dy + c4 + 1));
+        k.c[4] = __ldg(reinterpret_cast<const u32 *>(q.c + c4 + 1));
+        k.d[4] = __ldg(reinterpret_cast<const u32 *>(q.c + q.dy + c4 + 1));
+    }
+}
+
+// number of entries of a span; if entries != nullptr also writes them starting at off
+static __device__ __noinline__ u32 span_detail(const SpanRows q, u32 r, u32 c4, u32 Z, uint2 *__restrict__ entries, u32 cap, u32 off) {
+    SpanBits k;
+    span_load_g(q, r, c4, k);
+    const bool cellrow = k.hasX && k.hasY;
+    u32 n = 0;
 #pragma unroll
-        for (int i = 0; i < SP_ITEMS; i++) {
-            if (u0 + i < nspans) {
-                SpanBits k;
-                span_load(bits, p, r, x, y, c4, spr, k);
-                if (span_mixed(k)) {
-                    u32 a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca, n = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) n += __popc(span_word_masks(k, j, a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca));
-                    if (n) mixed |= 1u << i;
-                    cnt += n;
+    for (int j = 0; j < 4; j++) {
+        u32 a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca;
+        u32 m = span_word_masks(k, j, a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca);
+        n += __popc(m);
+        if (entries) {
+            const u32 zb = k.z0 + 32u * j;
+            while (m) {
+                const u32 b = __ffs(m) - 1;
+                m &= m - 1;
+                if (off < cap) {
+                    u32 cs = ((a0 >> b) & 1u) | (((a1 >> b) & 1u) << 1) | (((b0 >> b) & 1u) << 2) | (((b1 >> b) & 1u) << 3) |
+                             (((cc0 >> b) & 1u) << 4) | (((c1 >> b) & 1u) << 5) | (((d0 >> b) & 1u) << 6) | (((d1 >> b) & 1u) << 7);
+                    if (!cellrow) cs &= 0x03u;   // rows y+1 / x+1 do not exist: their bits are copies
+                    u32 own = ((ez >> b) & 1u) | (((ey >> b) & 1u) << 1) | (((ex >> b) & 1u) << 2);
+                    u32 cv = (cellrow && (zb + b + 1u < Z)) ? 1u : 0u;
+                    entries[off] = make_uint2(r, (zb + b) | (cs << 16) | (own << 24) | (cv << 27));
                 }
+                off++;
             }
-            if (++c4 == spr) { c4 = 0; r++; if (++y == Y) { y = 0; x++; } }
         }
     }
-    u32 total;
-    const u32 excl = block_exclusive_scan(cnt, &total, sw);
-    if (threadIdx.x < 32) {
-        u32 pre = lookback_exclusive(desc, 1, tile, total, 1u);
-        if (threadIdx.x == 0) s_prefix = pre;
+    return n;
+}
+
+__device__ __forceinline__ SpanRows span_rows(const u32 *__restrict__ bits, const DenseParams &p, u32 x, u32 y, u32 spr) {
+    SpanRows q;
+    q.hasY = y + 1u < (u32) p.g.Y;
+    q.hasX = x + 1u < (u32) p.g.X;
+    q.last = false;
+    const u64 r = (u64) x * (u32) p.g.Y + y;
+    q.a = reinterpret_cast<const uint4 *>(bits) + r * spr;
+    q.c = q.a + (q.hasX ? (u64) (u32) p.g.Y * spr : 0ull);
+    q.dy = q.hasY ? spr : 0u;
+    return q;
+}
+
+// Threads cover (y, c4) of a plane; blockIdx.y selects a chunk of RC_XCHUNK consecutive x planes that the
+// thread marches through with a rolling two-plane window, so every row of the bit volume is fetched from
+// L2 about once (as row y of plane x+1, reused as plane x of the next step; row y+1 comes from L1).
+struct SpanQuad { uint4 v; u32 nx; };   // 128 sign bits + the following word (bit 0 = z+1 neighbour of the last point)
+
+__device__ __forceinline__ SpanQuad load_quad(const uint4 *row, u32 c4, bool last) {
+    SpanQuad q;
+    q.v = __ldg(row + c4);
+    q.nx = last ? 0u : __ldg(reinterpret_cast<const u32 *>(row + c4 + 1));
+    return q;
+}
+
+static __global__ void __launch_bounds__(256) k_rowcount128(const u32 *__restrict__ bits, DenseParams p, u32 *__restrict__ row_count,
+                                                            unsigned char *__restrict__ span_cnt, u32 xchunk) {
+    const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
+    const u32 idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= Y * spr) return;
+    const u32 y = idx / spr, c4 = idx - y * spr;
+    const bool hasY = y + 1u < Y, last = c4 + 1u == spr;
+    const u32 dy = hasY ? spr : 0u;
+    const u32 x_begin = blockIdx.y * xchunk;
+    const u32 x_end = min(x_begin + xchunk, X);
+    const size_t plane4 = (size_t) Y * spr;                       // uint4 per x plane
+    const uint4 *row = reinterpret_cast<const uint4 *>(bits) + (size_t) x_begin * plane4 + (size_t) y * spr;
+    SpanQuad A = load_quad(row, c4, last), B = load_quad(row + dy, c4, last);
+    for (u32 x = x_begin; x < x_end; x++) {
+        const bool hasX = x + 1u < X;
+        const uint4 *nrow = row + (hasX ? plane4 : 0);           // missing plane aliases the current one
+        const SpanQuad Cq = load_quad(nrow, c4, last), Dq = load_quad(nrow + dy, c4, last);
+        u32 any = (A.v.x | A.v.y | A.v.z | A.v.w) | (B.v.x | B.v.y | B.v.z | B.v.w) | (Cq.v.x | Cq.v.y | Cq.v.z | Cq.v.w) |
+                  (Dq.v.x | Dq.v.y | Dq.v.z | Dq.v.w);
+        u32 all = (A.v.x & A.v.y & A.v.z & A.v.w) & (B.v.x & B.v.y & B.v.z & B.v.w) & (Cq.v.x & Cq.v.y & Cq.v.z & Cq.v.w) &
+                  (Dq.v.x & Dq.v.y & Dq.v.z & Dq.v.w);
+        if (!last) {
+            any |= (A.nx | B.nx | Cq.nx | Dq.nx) & 1u;
+            if (!(A.nx & B.nx & Cq.nx & Dq.nx & 1u)) all &= ~1u;
+        }
+        if (!(any == 0u || all == 0xffffffffu)) {
+            SpanRows q = span_rows(bits, p, x, y, spr);
+            q.last = last;
+            const u32 n = span_detail(q, x * Y + y, c4, Z, nullptr, 0, 0);
+            if (n) {
+                atomicAdd(&row_count[x * Y + y], n);
+                span_cnt[(size_t) (x * Y + y) * spr + c4] = (unsigned char) n;   // <= 128; the array is zero-initialised
+            }
+        }
+        A = Cq; B = Dq;
+        row += plane4;
     }
-    __syncthreads();
-    u32 off = s_prefix + excl;
-    {
-        u32 r = r0, c4 = c0, x = x0, y = y0;
-#pragma unroll 1
-        for (int i = 0; i < SP_ITEMS; i++) {
-            if (u0 + i >= nspans) break;
-            if (c4 == 0) row_start[r] = off;
-            if ((mixed >> i) & 1u) {
-                SpanBits k;
-                span_load(bits, p, r, x, y, c4, spr, k);
-                const bool cellrow = k.hasX && k.hasY;
-#pragma unroll 1
-                for (int j = 0; j < 4; j++) {
-                    u32 a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca;
-                    u32 m = span_word_masks(k, j, a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca);
-                    const u32 zb = k.z0 + 32u * j;
-                    while (m) {
-                        const u32 b = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (off < cap) {
-                            u32 cs = ((a0 >> b) & 1u) | (((a1 >> b) & 1u) << 1) | (((b0 >> b) & 1u) << 2) | (((b1 >> b) & 1u) << 3) |
-                                     (((cc0 >> b) & 1u) << 4) | (((c1 >> b) & 1u) << 5) | (((d0 >> b) & 1u) << 6) | (((d1 >> b) & 1u) << 7);
-                            if (!cellrow) cs &= 0x03u;   // rows y+1 / x+1 do not exist: their bits are copies
-                            u32 own = ((ez >> b) & 1u) | (((ey >> b) & 1u) << 1) | (((ex >> b) & 1u) << 2);
-                            u32 cv = (cellrow && (zb + b + 1u < Z)) ? 1u : 0u;
-                            entries[off] = make_uint2(r, (zb + b) | (cs << 16) | (own << 24) | (cv << 27));
-                        }
-                        off++;
-                    }
+}
+
+// in-place exclusive scan of n u32 (8 per thread, look-back across blocks); total -> counters[total_idx], data[n]
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = 256 * RS_ITEMS;
+static __global__ void __launch_bounds__(256) k_scan_rows(u32 *__restrict__ data, u32 n, u64 *__restrict__ desc, u32 *__restrict__ counters,
+                                                          int ticket_idx, int total_idx) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_tile, s_pre;
+    const u32 ntiles = (n + RS_TILE - 1) / RS_TILE;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[ticket_idx], 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u32 i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
+        u32 v[RS_ITEMS], sum = 0;
+        if (i0 + RS_ITEMS <= n) {
+            const uint4 lo = *reinterpret_cast<const uint4 *>(data + i0), hi = *reinterpret_cast<const uint4 *>(data + i0 + 4);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < RS_ITEMS; j++) v[j] = i0 + j < n ? data[i0 + j] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) sum += v[j];
+        u32 tot;
+        u32 ex = block_exclusive_scan(sum, &tot, sw);
+        if (threadIdx.x < 32) {
+            u32 pre = lookback_exclusive(desc, 1, tile, tot, 1u);
+            if (threadIdx.x == 0) s_pre = pre;
+        }
+        __syncthreads();
+        ex += s_pre;
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            if (i0 + j < n) {
+                data[i0 + j] = ex;
+                ex += v[j];
+                if (i0 + j == n - 1) {
+                    data[n] = ex;
+                    counters[total_idx] = ex;
                 }
             }
-            if (u0 + i == nspans - 1) {
-                row_start[p.R] = off;
-                counters[C_S] = off;
-            }
-            if (++c4 == spr) { c4 = 0; r++; if (++y == Y) { y = 0; x++; } }
         }
     }
 }
+
+// one thread per row that owns entries; inside the row only the spans with a non-zero count byte are re-classified
+static __global__ void __launch_bounds__(128) k_rowfill128(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
+                                                           const unsigned char *__restrict__ span_cnt, uint2 *__restrict__ entries, u32 cap) {
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < p.R; r += gridDim.x * blockDim.x) {
+        u32 off = row_start[r];
+        const u32 end = row_start[r + 1];
+        if (off == end) continue;
+        const u32 x = r / Y, y = r - x * Y;
+        SpanRows q = span_rows(bits, p, x, y, spr);
+        const unsigned char *rc = span_cnt + (size_t) r * spr;
+        for (u32 c4 = 0; c4 < spr && off < end; c4++) {
+            const u32 n = rc[c4];
+            if (!n) continue;
+            q.last = c4 + 1u == spr;
+            span_detail(q, r, c4, Z, entries, cap, off);
+            off += n;
+        }
+    }
+}
+
+// host-side: the span path needs Z % 128 == 0
+static inline bool compact128_ok(const DenseParams &p) { return (p.g.Z & 127) == 0 && p.g.Z >= 128; }
 
 // first entry of row [lo,hi) whose z is >= z
 __device__ __forceinline__ u32 row_lower_bound(const uint2 *__restrict__ entries, u32 lo, u32 hi, u32 z) {
@@ -545,6 +664,32 @@ static __global__ void __launch_bounds__(256) k_grid_points(Geom g, float *__res
         o[1] = axis_pos(y, Y - 1, g.amin[1], g.asize[1]);
         o[2] = axis_pos(z, Z - 1, g.amin[2], g.asize[2]);
     }
+}
+
+// Enqueue the compaction stage: bits -> entries (ordered) + row_start + counters[C_S].
+// desc must hold compact_desc_count(p) zeroed descriptors; counters, row_start and span_cnt (one byte per
+// 128-point span, compact_span_bytes(p)) zeroed.
+static inline void launch_compact(const u32 *bits, const DenseParams &p, uint2 *entries, u32 cap, u32 *row_start, u64 *desc,
+                                  u32 *counters, unsigned char *span_cnt, cudaStream_t stream) {
+    if (compact128_ok(p)) {
+        const u32 spr = (u32) (p.g.Z >> 7);
+        // x planes marched per thread: keep >= ~1M threads in flight, at most 8 planes per thread
+        const u64 nsp = (u64) p.R * spr;
+        u32 xchunk = (u32) (nsp >> 20);
+        xchunk = xchunk < 1 ? 1 : (xchunk > 8 ? 8 : xchunk);
+        dim3 grid(((u32) p.g.Y * spr + 255) / 256, ((u32) p.g.X + xchunk - 1) / xchunk);
+        ISX_LAUNCH(k_rowcount128, grid, 256, 0, stream, bits, p, row_start, span_cnt, xchunk);
+        ISX_LAUNCH(k_scan_rows, 148 * 4, 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+        const u32 fblocks = (p.R + 127u) / 128u;
+        ISX_LAUNCH(k_rowfill128, fblocks > 148u * 16u ? 148u * 16u : fblocks, 128, 0, stream, bits, p, row_start, span_cnt, entries, cap);
+    } else {
+        ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, bits, p, entries, cap, row_start, desc, counters);
+    }
+}
+static inline size_t compact_span_bytes(const DenseParams &p) { return compact128_ok(p) ? (size_t) p.R * (size_t) (p.g.Z >> 7) + 16 : 16; }
+static inline size_t compact_desc_count(const DenseParams &p) {
+    size_t a = (size_t) p.NQ / CP_TILE + 2, b = (size_t) p.R / RS_TILE + 2;
+    return a > b ? a : b;
 }
 
 }   // namespace isx

@@ -43,6 +43,7 @@ struct McBuffers {
     unsigned char *used;   // 3 per entry
     u32 *tri_off, *cand_info;
     u64 *descT, *descU, *descV;
+    unsigned char *span_cnt;   // entries per 128-point span (span fast path)
     size_t zero_bytes;       // bytes from `counters` that one memset clears at the start of a call
     unsigned char *bdelta;   // per entry: x-bucket offset (+1) of its 3 owned edge vertices, 2 bits each
     SegHead seg;             // bucket histogram / offsets over the X+2 x-plane buckets
@@ -52,16 +53,17 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     McBuffers b;
     // --- everything that must be zero at the start of a call is contiguous: ONE memset per call ---
     b.counters = c.take<u32>(C_COUNT);
-    b.descA = c.take<u64>((size_t) p.NQ / CP_TILE + 2);
+    b.descA = c.take<u64>(compact_desc_count(p));
     b.descT = c.take<u64>(cap / SE_TILE + 2);
     b.descU = c.take<u64>(cap / SE_TILE + 2);
     b.descV = c.take<u64>(3 * cap / UQ_TILE + 2);
     SegHead::carve(c, (size_t) p.g.X + 2, &b.seg);
+    b.row_start = c.take<u32>((size_t) p.R + 2);   // accumulates the per-row entry counts before it is scanned
+    b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
     b.used = c.take<unsigned char>(3 * (cap + 2));
     b.zero_bytes = (size_t) ((char *) (b.used + 3 * (cap + 2)) - (char *) b.counters);
     // --- the rest is fully overwritten before it is read ---
     b.bits = c.take<u32>(signbits_words(p.P));
-    b.row_start = c.take<u32>((size_t) p.R + 2);
     b.entries = c.take<uint2>(cap + 1);
     b.nb = c.take<u32>(3 * cap);
     b.ntri = c.take<unsigned char>(cap);
@@ -423,12 +425,7 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
     const int sms = device_sms();
     const u32 nb = (u32) p.g.X + 2;   // x-plane buckets (local planes -1 .. X)
     launch_signbits(values, b.bits, p.P, p.level, stream);
-    if ((p.g.Z & 127) == 0) {
-        const u32 nspans = p.R * (u32) (p.g.Z >> 7);
-        ISX_LAUNCH(k_compact128, (nspans + SP_TILE - 1) / SP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
-    } else {
-        ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters);
-    }
+    launch_compact(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters, b.span_cnt, stream);
     ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                b.trimask, b.used, b.bdelta);
     ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,

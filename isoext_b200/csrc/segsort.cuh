@@ -135,105 +135,19 @@ __device__ __forceinline__ bool key_less(u32 ax, u32 ay, u32 az, u32 bx, u32 by,
     return ax < bx || (ax == bx && (ay < by || (ay == by && az < bz)));
 }
 
-struct SKey { u32 x, y, z, id; };
-// (x,y,z,id) as one 128-bit big-endian integer: a < b  <=>  the subtraction a - b borrows.
-// 5 instructions instead of a branchy lexicographic compare; ids are distinct, so the order is total.
-__device__ __forceinline__ u32 skey_less(const SKey &a, const SKey &b) {
-    u32 r;
-    asm("{\n\t.reg .u32 t;\n\t"
-        "sub.cc.u32 t, %1, %5;\n\t"
-        "subc.cc.u32 t, %2, %6;\n\t"
-        "subc.cc.u32 t, %3, %7;\n\t"
-        "subc.cc.u32 t, %4, %8;\n\t"
-        "subc.u32 %0, 0, 0;\n\t}"
-        : "=r"(r)
-        : "r"(a.id), "r"(a.z), "r"(a.y), "r"(a.x), "r"(b.id), "r"(b.z), "r"(b.y), "r"(b.x));
-    return r;   // 0xffffffff if a < b, else 0
-}
+// One block per bucket: LSD radix sort (8-bit digits) entirely in shared memory.
+//   keys stay in place (sk[3][SEG_CAP]); only 16-bit local indices move (ord ping-pong);
+//   ranking is stable: each warp owns a contiguous run of positions, ranks 32 of them at a time with
+//   match_any against its private digit counters, then a (digit, warp) exclusive scan gives the bases;
+//   digit places on which all keys of the bucket agree (typically the high bytes of x) are skipped.
+// Shared memory: 3*16 KB keys + 16 KB ids + 16 KB ord + 16 KB counters = 96 KB (dynamic).
+constexpr int SEG_WARPS = SEG_THREADS / 32;
+constexpr int SEG_CHUNKS = SEG_CAP / SEG_THREADS;          // 32-element chunks per warp at full capacity
+constexpr size_t SEG_SMEM = (size_t) SEG_CAP * 4 * 4       // sk[3] + ids
+                            + (size_t) SEG_CAP * 2 * 2     // ord[2] (u16)
+                            + (size_t) SEG_WARPS * 256 * 4 // cnt
+                            + (256 + 64) * 4;              // digit bases + vary + scan scratch
 
-// compare-exchange of `mine` with `other` (the element at index e ^ j): keep the smaller one if
-// keep_min, else the larger; equal elements (only the padding) keep their own copy.
-__device__ __forceinline__ void cmpx(SKey &mine, const SKey &other, bool keep_min) {
-    const u32 take = keep_min ? skey_less(other, mine) : skey_less(mine, other);
-    if (take) mine = other;
-}
-
-// Bitonic sort of m = SEG_THREADS * E elements, element e = tid * E + r held in registers.
-// Stages with j < E are thread-local, E <= j < 32 E use warp shuffles, wider ones go through smem.
-template <int E>
-__device__ __forceinline__ void bitonic_block(SKey (&v)[E], u32 m, u32 *sx, u32 *sy, u32 *sz, u32 *si) {
-    const u32 tid = threadIdx.x;
-    for (u32 k = 2; k <= m; k <<= 1) {
-        for (u32 j = k >> 1; j > 0; j >>= 1) {
-            if (j < (u32) E) {
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    const int q = r ^ (int) j;
-                    if (q > r) {
-                        const u32 e = tid * E + r;
-                        const bool up = (e & k) == 0;
-                        SKey a = v[r], b = v[q];
-                        cmpx(v[r], b, up);
-                        cmpx(v[q], a, !up);
-                    }
-                }
-            } else if (j < 32u * E) {
-                const u32 lj = j / E;   // lane distance
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    const u32 e = tid * E + r;
-                    SKey o;
-                    o.x = __shfl_xor_sync(0xffffffffu, v[r].x, lj);
-                    o.y = __shfl_xor_sync(0xffffffffu, v[r].y, lj);
-                    o.z = __shfl_xor_sync(0xffffffffu, v[r].z, lj);
-                    o.id = __shfl_xor_sync(0xffffffffu, v[r].id, lj);
-                    const bool lower = (e & j) == 0, up = (e & k) == 0;
-                    cmpx(v[r], o, lower == up);
-                }
-            } else {
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    const u32 e = tid * E + r;
-                    sx[e] = v[r].x; sy[e] = v[r].y; sz[e] = v[r].z; si[e] = v[r].id;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    const u32 e = tid * E + r, q = e ^ j;
-                    SKey o = {sx[q], sy[q], sz[q], si[q]};
-                    const bool lower = (e & j) == 0, up = (e & k) == 0;
-                    cmpx(v[r], o, lower == up);
-                }
-            }
-        }
-    }
-}
-
-template <int E>
-__device__ __forceinline__ void seg_sort_bucket(const u32 *__restrict__ kx, const u32 *__restrict__ ky, const u32 *__restrict__ kz,
-                                                const u32 *__restrict__ perm0, u32 *__restrict__ perm, u32 s0, u32 n, u32 *smem) {
-    u32 *sx = smem, *sy = smem + SEG_CAP, *sz = smem + 2 * SEG_CAP, *si = smem + 3 * SEG_CAP;
-    SKey v[E];
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-        const u32 e = threadIdx.x * E + r;
-        if (e < n) {
-            const u32 id = perm0[s0 + e];
-            v[r].x = kx[id]; v[r].y = ky[id]; v[r].z = kz[id]; v[r].id = id;
-        } else {
-            v[r].x = 0xffffffffu; v[r].y = 0xffffffffu; v[r].z = 0xffffffffu; v[r].id = 0xffffffffu;
-        }
-    }
-    bitonic_block<E>(v, SEG_THREADS * E, sx, sy, sz, si);
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-        const u32 e = threadIdx.x * E + r;
-        if (e < n) perm[s0 + e] = v[r].id;
-    }
-}
-
-// one block per bucket; dynamic smem = 4 arrays of SEG_CAP u32
 static __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                                  const u32 *__restrict__ kz, const u32 *__restrict__ count,
                                                                  const u32 *__restrict__ start, const u32 *__restrict__ perm0,
@@ -248,10 +162,104 @@ static __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort(const u32 *__re
         if (threadIdx.x == 0) perm[s0] = perm0[s0];
         return;
     }
-    if (n <= SEG_THREADS) seg_sort_bucket<1>(kx, ky, kz, perm0, perm, s0, n, smem);
-    else if (n <= 2 * SEG_THREADS) seg_sort_bucket<2>(kx, ky, kz, perm0, perm, s0, n, smem);
-    else if (n <= 4 * SEG_THREADS) seg_sort_bucket<4>(kx, ky, kz, perm0, perm, s0, n, smem);
-    else seg_sort_bucket<8>(kx, ky, kz, perm0, perm, s0, n, smem);
+    u32 *sk = smem;                                   // [3][SEG_CAP]: z, y, x keys (LSD order)
+    u32 *ids = smem + 3 * SEG_CAP;                    // [SEG_CAP]
+    unsigned short *ord = reinterpret_cast<unsigned short *>(smem + 4 * SEG_CAP);   // [2][SEG_CAP]
+    u32 *cnt = smem + 5 * SEG_CAP;                    // [SEG_WARPS][256]
+    u32 *dbase = cnt + SEG_WARPS * 256;               // [256]
+    u32 *vary = dbase + 256;                          // [3] OR of (key ^ key[0]) per coordinate
+    u32 *sw = vary + 4;                               // [33] scan scratch
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid < 3) vary[tid] = 0;
+    __syncthreads();
+    {
+        u32 vz = 0, vy = 0, vx = 0;
+        const u32 id0 = perm0[s0];
+        const u32 z0 = kz[id0], y0 = ky[id0], x0 = kx[id0];
+        for (u32 i = tid; i < n; i += SEG_THREADS) {
+            const u32 id = perm0[s0 + i];
+            const u32 z = kz[id], y = ky[id], x = kx[id];
+            sk[i] = z; sk[SEG_CAP + i] = y; sk[2 * SEG_CAP + i] = x;
+            ids[i] = id;
+            ord[i] = (unsigned short) i;
+            vz |= z ^ z0; vy |= y ^ y0; vx |= x ^ x0;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            vz |= __shfl_xor_sync(0xffffffffu, vz, o);
+            vy |= __shfl_xor_sync(0xffffffffu, vy, o);
+            vx |= __shfl_xor_sync(0xffffffffu, vx, o);
+        }
+        if (lane == 0) { atomicOr(&vary[0], vz); atomicOr(&vary[1], vy); atomicOr(&vary[2], vx); }
+    }
+    __syncthreads();
+    // contiguous run of positions per warp, a multiple of 32
+    const u32 run = ((n + SEG_WARPS - 1) / SEG_WARPS + 31) & ~31u;
+    const u32 nchunks = run >> 5;                     // <= SEG_CHUNKS
+    const u32 wbase = warp * run;
+    u32 cur = 0;
+    for (int pass = 0; pass < 12; pass++) {
+        const u32 c = pass >> 2, shift = 8 * (pass & 3);
+        if (((vary[c] >> shift) & 255u) == 0) continue;   // all keys agree on this digit
+        const u32 *key = sk + c * SEG_CAP;
+        const unsigned short *oin = ord + cur * SEG_CAP;
+        unsigned short *oout = ord + (cur ^ 1) * SEG_CAP;
+        for (u32 i = tid; i < SEG_WARPS * 256; i += SEG_THREADS) cnt[i] = 0;
+        __syncthreads();
+        u32 packed[SEG_CHUNKS];                       // li | digit << 16 | rank-in-warp << 24 .. (rank kept separately)
+        u32 rnk[SEG_CHUNKS];
+#pragma unroll
+        for (int j = 0; j < SEG_CHUNKS; j++) {
+            packed[j] = 0xffffffffu;
+            rnk[j] = 0;
+            if ((u32) j < nchunks) {
+                const u32 i = wbase + j * 32 + lane;
+                const bool valid = i < n;
+                const u32 active = __ballot_sync(0xffffffffu, valid);
+                if (valid) {
+                    const u32 li = oin[i];
+                    const u32 d = (key[li] >> shift) & 255u;
+                    const u32 peers = __match_any_sync(active, d);
+                    const u32 leader = __ffs(peers) - 1;
+                    u32 old = 0;
+                    if (lane == leader) {
+                        old = cnt[warp * 256 + d];
+                        cnt[warp * 256 + d] = old + __popc(peers);
+                    }
+                    old = __shfl_sync(peers, old, leader);
+                    rnk[j] = old + __popc(peers & ((1u << lane) - 1u));
+                    packed[j] = li | (d << 16);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // digit totals over the warps (exclusive per warp), then exclusive scan over the 256 digits
+        u32 tot = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < SEG_WARPS; w++) {
+                const u32 t = cnt[w * 256 + tid];
+                cnt[w * 256 + tid] = tot;
+                tot += t;
+            }
+        }
+        u32 total;
+        const u32 ex = block_exclusive_scan(tot, &total, sw);
+        if (tid < 256) dbase[tid] = ex;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SEG_CHUNKS; j++) {
+            if (packed[j] != 0xffffffffu) {
+                const u32 d = (packed[j] >> 16) & 255u;
+                oout[dbase[d] + cnt[warp * 256 + d] + rnk[j]] = (unsigned short) (packed[j] & 0xffffu);
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const unsigned short *ofin = ord + cur * SEG_CAP;
+    for (u32 i = tid; i < n; i += SEG_THREADS) perm[s0 + i] = ids[ofin[i]];
 }
 
 // ---- fallback for big buckets -------------------------------------------------------------------
@@ -289,12 +297,12 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
                                        u32 nb, u32 n_big, const SegHead &h, const SegScratch &b, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SEG_CAP * (int) sizeof(u32));
+        cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEG_SMEM);
         attr_set = true;
     }
     const int blocks = (int) ((grid_n + 255) / 256 > 148 * 8 ? 148 * 8 : (grid_n + 255) / 256);
     ISX_LAUNCH(k_seg_scatter, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap);
-    ISX_LAUNCH(k_seg_sort, nb, SEG_THREADS, 4 * SEG_CAP * sizeof(u32), stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm, n_dev,
+    ISX_LAUNCH(k_seg_sort, nb, SEG_THREADS, SEG_SMEM, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm, n_dev,
                n_cap);
     if (n_big > 0) {
         dim3 grid(32, nb < 1024 ? nb : 1024);
