@@ -194,13 +194,14 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
                                                       const unsigned char *__restrict__ used, u32 *__restrict__ tri_off,
                                                       u32 *__restrict__ cand_info, u64 *__restrict__ descT, u64 *__restrict__ descU,
                                                       const uint2 *__restrict__ entries, const unsigned char *__restrict__ bdelta,
-                                                      u32 Y, u32 *__restrict__ bucket_count) {
+                                                      u32 Y, u32 *__restrict__ bucket_count, u32 nb, SegHead seg) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_preT, s_preU;
     // x-bucket histogram window: the entries of a tile are sorted by x, so almost all of its vertices fall
     // into a handful of consecutive buckets; count those in shared memory, the rest directly in L2
     constexpr u32 WIN = 32;
     __shared__ u32 s_hist[WIN];
+    __shared__ u32 s_last, s4[4];
     const u32 S = counters[C_S];
     if (S > cap) return;
     const u32 ntiles = (S + SE_TILE - 1) / SE_TILE;
@@ -264,6 +265,15 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
                     counters[C_VC] = exU;
                 }
             }
+        }
+        // the block that finishes the last tile turns the bucket histogram into offsets (saves a launch)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&counters[C_TICKET_E], 1u) == ntiles - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            seg_scan_block(nb, seg.count, seg.start, seg.cursor, seg.bigoff, counters + C_NBIG, counters + C_MAXB, sw, s4);
         }
     }
 }
@@ -429,9 +439,7 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
     ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                b.trimask, b.used, b.bdelta);
     ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
-               b.entries, b.bdelta, (u32) p.g.Y, b.seg.count);
-    ISX_LAUNCH(k_seg_scan, 1, 1024, 0, stream, nb, b.seg.count, b.seg.start, b.seg.cursor, b.seg.bigoff, b.counters + C_NBIG,
-               b.counters + C_MAXB);
+               b.entries, b.bdelta, (u32) p.g.Y, b.seg.count, nb, b.seg);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }
@@ -448,8 +456,8 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
                s.seg.cbucket, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, (u32) p.g.X + 2, n_big, b.seg, s.seg, stream));
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
-    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, b.descV, klo, khi,
-               n_dev, cand_cap);
+    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
+               b.descV, klo, khi, n_dev, cand_cap, true);
     ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
                s.cand_rank, F, cand_cap, tri_cap, entry_cap);
     ISX_CUDA(cudaGetLastError());

@@ -45,6 +45,7 @@ struct SegScratch {
     u32 *cbucket;    // n   bucket id of every candidate
     u32 *perm0;      // n   ids grouped by bucket
     u32 *perm;       // n   ids in final sorted order
+    u32 *skx, *sky, *skz;         // n   keys in final sorted order (so that the weld pass reads sequentially)
     u32 *bkx, *bky, *bkz, *bid;   // fallback: compacted keys / ids of the big buckets
     RadixBuffers radix;
     static void carve(Carver &c, size_t n, SegScratch *out) {
@@ -52,6 +53,9 @@ struct SegScratch {
         b.cbucket = c.take<u32>(n);
         b.perm0 = c.take<u32>(n);
         b.perm = c.take<u32>(n);
+        b.skx = c.take<u32>(n);
+        b.sky = c.take<u32>(n);
+        b.skz = c.take<u32>(n);
         b.bkx = c.take<u32>(n);
         b.bky = c.take<u32>(n);
         b.bkz = c.take<u32>(n);
@@ -76,37 +80,44 @@ static __global__ void __launch_bounds__(256) k_seg_count(const u32 *__restrict_
     }
 }
 
-// one block: exclusive scan over nb buckets; big buckets (> SEG_CAP) get offsets in the compacted big list
-static __global__ void __launch_bounds__(1024) k_seg_scan(u32 nb, const u32 *__restrict__ count, u32 *__restrict__ start,
-                                                           u32 *__restrict__ cursor, u32 *__restrict__ bigoff, u32 *__restrict__ info_nbig,
-                                                           u32 *__restrict__ info_max) {
-    __shared__ u32 sw[33];
-    __shared__ u32 s_carry, s_carry_big, s_max, s_nbig;
-    if (threadIdx.x == 0) { s_carry = 0; s_carry_big = 0; s_max = 0; s_nbig = 0; }
+// Executed by ONE block (any blockDim that is a multiple of 32, <= 1024): exclusive scan over nb buckets;
+// big buckets (> SEG_CAP) also get offsets in the compacted big list.  `count` is read with L2 loads
+// (it was produced by atomics of other blocks).
+__device__ __forceinline__ void seg_scan_block(u32 nb, const u32 *__restrict__ count, u32 *__restrict__ start, u32 *__restrict__ cursor,
+                                               u32 *__restrict__ bigoff, u32 *__restrict__ info_nbig, u32 *__restrict__ info_max,
+                                               u32 *sw /* >= 33 */, u32 *s4 /* >= 4 */) {
+    if (threadIdx.x == 0) { s4[0] = 0; s4[1] = 0; s4[2] = 0; }
     __syncthreads();
-    for (u32 base = 0; base < nb; base += 1024) {
+    for (u32 base = 0; base < nb; base += blockDim.x) {
         const u32 b = base + threadIdx.x;
-        const u32 c = b < nb ? count[b] : 0u;
+        const u32 c = b < nb ? __ldcg(count + b) : 0u;
         const u32 cb = c > (u32) SEG_CAP ? c : 0u;
         u32 tot, totb;
         const u32 ex = block_exclusive_scan(c, &tot, sw);
         const u32 exb = block_exclusive_scan(cb, &totb, sw);
         if (b < nb) {
-            start[b] = s_carry + ex;
+            start[b] = s4[0] + ex;
             cursor[b] = 0;
-            bigoff[b] = s_carry_big + exb;
-            if (c) atomicMax(&s_max, c);
-            if (cb) atomicAdd(&s_nbig, 1u);
+            bigoff[b] = s4[1] + exb;
+            if (c) atomicMax(&s4[2], c);
         }
         __syncthreads();
-        if (threadIdx.x == 0) { s_carry += tot; s_carry_big += totb; }
+        if (threadIdx.x == 0) { s4[0] += tot; s4[1] += totb; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        start[nb] = s_carry;
-        *info_nbig = s_carry_big;   // number of candidates living in big buckets
-        *info_max = s_max;          // largest bucket
+        start[nb] = s4[0];
+        *info_nbig = s4[1];   // number of candidates living in big buckets
+        *info_max = s4[2];    // largest bucket
     }
+}
+
+static __global__ void __launch_bounds__(1024) k_seg_scan(u32 nb, const u32 *__restrict__ count, u32 *__restrict__ start,
+                                                           u32 *__restrict__ cursor, u32 *__restrict__ bigoff, u32 *__restrict__ info_nbig,
+                                                           u32 *__restrict__ info_max) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s4[4];
+    seg_scan_block(nb, count, start, cursor, bigoff, info_nbig, info_max, sw, s4);
 }
 
 static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restrict__ cbucket, u32 n, const u32 *__restrict__ start,
@@ -151,7 +162,8 @@ constexpr size_t SEG_SMEM = (size_t) SEG_CAP * 4 * 4       // sk[3] + ids
 static __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                                  const u32 *__restrict__ kz, const u32 *__restrict__ count,
                                                                  const u32 *__restrict__ start, const u32 *__restrict__ perm0,
-                                                                 u32 *__restrict__ perm, const u32 *__restrict__ n_dev, u32 n_cap) {
+                                                                 u32 *__restrict__ perm, u32 *__restrict__ skx, u32 *__restrict__ sky,
+                                                                 u32 *__restrict__ skz, const u32 *__restrict__ n_dev, u32 n_cap) {
     extern __shared__ u32 smem[];
     if (n_dev && *n_dev > n_cap) return;
     const u32 b = blockIdx.x;
@@ -159,7 +171,11 @@ static __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort(const u32 *__re
     if (n == 0 || n > (u32) SEG_CAP) return;
     const u32 s0 = start[b];
     if (n == 1) {
-        if (threadIdx.x == 0) perm[s0] = perm0[s0];
+        if (threadIdx.x == 0) {
+            const u32 id = perm0[s0];
+            perm[s0] = id;
+            skx[s0] = kx[id]; sky[s0] = ky[id]; skz[s0] = kz[id];
+        }
         return;
     }
     u32 *sk = smem;                                   // [3][SEG_CAP]: z, y, x keys (LSD order)
@@ -259,7 +275,11 @@ static __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort(const u32 *__re
         cur ^= 1;
     }
     const unsigned short *ofin = ord + cur * SEG_CAP;
-    for (u32 i = tid; i < n; i += SEG_THREADS) perm[s0 + i] = ids[ofin[i]];
+    for (u32 i = tid; i < n; i += SEG_THREADS) {
+        const u32 li = ofin[i];
+        perm[s0 + i] = ids[li];
+        skz[s0 + i] = sk[li]; sky[s0 + i] = sk[SEG_CAP + li]; skx[s0 + i] = sk[2 * SEG_CAP + li];
+    }
 }
 
 // ---- fallback for big buckets -------------------------------------------------------------------
@@ -281,11 +301,17 @@ static __global__ void __launch_bounds__(256) k_seg_big_gather(u32 nb, const u32
 // sorted rank r of the big list -> final position: the big list is ordered by bucket (x decides the bucket)
 static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const u32 *__restrict__ sorted, const u32 *__restrict__ bid,
                                                                 const u32 *__restrict__ cbucket, const u32 *__restrict__ start,
-                                                                const u32 *__restrict__ bigoff, u32 *__restrict__ perm) {
+                                                                const u32 *__restrict__ bigoff, u32 *__restrict__ perm,
+                                                                const u32 *__restrict__ bkx, const u32 *__restrict__ bky,
+                                                                const u32 *__restrict__ bkz, u32 *__restrict__ skx, u32 *__restrict__ sky,
+                                                                u32 *__restrict__ skz) {
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_big; r += gridDim.x * blockDim.x) {
-        const u32 id = bid[sorted[r]];
+        const u32 j = sorted[r];
+        const u32 id = bid[j];
         const u32 b = cbucket[id];
-        perm[start[b] + (r - bigoff[b])] = id;
+        const u32 pos = start[b] + (r - bigoff[b]);
+        perm[pos] = id;
+        skx[pos] = bkx[j]; sky[pos] = bky[j]; skz[pos] = bkz[j];
     }
 }
 
@@ -302,15 +328,16 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
     }
     const int blocks = (int) ((grid_n + 255) / 256 > 148 * 8 ? 148 * 8 : (grid_n + 255) / 256);
     ISX_LAUNCH(k_seg_scatter, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap);
-    ISX_LAUNCH(k_seg_sort, nb, SEG_THREADS, SEG_SMEM, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm, n_dev,
-               n_cap);
+    ISX_LAUNCH(k_seg_sort, nb, SEG_THREADS, SEG_SMEM, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm, b.skx, b.sky,
+               b.skz, n_dev, n_cap);
     if (n_big > 0) {
         dim3 grid(32, nb < 1024 ? nb : 1024);
         ISX_LAUNCH(k_seg_big_gather, grid, 256, 0, stream, nb, h.count, h.start, h.bigoff, b.perm0, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid);
         cudaError_t e = radix_sort96(b.bkx, b.bky, b.bkz, n_big, b.radix, stream);
         if (e != cudaSuccess) return e;
         const int bb = (int) ((n_big + 255) / 256 > 148 * 8 ? 148 * 8 : (n_big + 255) / 256);
-        ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, n_big, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm);
+        ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, n_big, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx, b.bky,
+                   b.bkz, b.skx, b.sky, b.skz);
     }
     return cudaGetLastError();
 }

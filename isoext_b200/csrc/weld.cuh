@@ -19,7 +19,8 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
                                                 const u32 *__restrict__ ky, const u32 *__restrict__ kz,
                                                 u32 *__restrict__ cand_rank, float *__restrict__ V, u32 *__restrict__ counters,
                                                 u64 *__restrict__ desc, u32 key_lo, u32 key_hi,
-                                                const u32 *__restrict__ n_dev = nullptr, u32 n_cap = 0xffffffffu) {
+                                                const u32 *__restrict__ n_dev = nullptr, u32 n_cap = 0xffffffffu,
+                                                bool keys_sorted = false) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
     if (n_dev) n = *n_dev;       // single-call fast path: the count lives on the device
@@ -35,8 +36,9 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
         u32 c[UQ_ITEMS], x[UQ_ITEMS], y[UQ_ITEMS], z[UQ_ITEMS], isnew = 0, cnt = 0, nlo = 0, nhi = 0;
         // predecessor of the thread's first item
         u32 px = 0, py = 0, pz = 0;
+        // keys_sorted: kx/ky/kz are already in sorted order (indexed by position, not by candidate id)
         if (i0 > 0 && i0 < n) {
-            const u32 pc = perm[i0 - 1];
+            const u32 pc = keys_sorted ? i0 - 1 : perm[i0 - 1];
             px = kx[pc]; py = ky[pc]; pz = kz[pc];
         }
 #pragma unroll
@@ -44,7 +46,8 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
             const u32 i = i0 + j;
             if (i < n) {
                 c[j] = perm[i];
-                x[j] = kx[c[j]]; y[j] = ky[c[j]]; z[j] = kz[c[j]];
+                const u32 kidx = keys_sorted ? i : c[j];
+                x[j] = kx[kidx]; y[j] = ky[kidx]; z[j] = kz[kidx];
                 const bool nw = (i == 0) || x[j] != px || y[j] != py || z[j] != pz;
                 px = x[j]; py = y[j]; pz = z[j];
                 if (nw) {
