@@ -35,6 +35,7 @@ struct ItsWs {
     u32 *bits;
     u64 *descA, *descC, *descI;
     unsigned char *span_cnt;
+    u32 *heavy_list;
 };
 static size_t carve_its_ws(Carver &c, const DenseParams &p, size_t cap, ItsWs *out) {
     ItsWs b;
@@ -44,6 +45,7 @@ static size_t carve_its_ws(Carver &c, const DenseParams &p, size_t cap, ItsWs *o
     b.descC = c.take<u64>(cap / IT_TILE + 2);
     b.descI = c.take<u64>(cap / IT_TILE + 2);
     b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
+    b.heavy_list = c.take<u32>(compact_heavy_cap((u32) cap));
     if (out) *out = b;
     return c.bytes();
 }
@@ -454,7 +456,7 @@ int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z,
     ISX_CUDA(cudaMemsetAsync(b.descI, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     const int sms = device_sms();
     launch_signbits(values, b.bits, p.P, level, stream);
-    launch_compact(b.bits, p, ent, cap, row_start, b.descA, b.counters, b.span_cnt, stream);
+    launch_compact(b.bits, p, ent, cap, row_start, b.descA, b.counters, b.span_cnt, b.heavy_list, stream);
     ISX_LAUNCH(k_its_scan, sms * 4, 256, 0, stream, cap, b.counters, ent, cellslot, its_off, b.descC, b.descI);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];

@@ -34,6 +34,7 @@ enum Counter : int {
     C_TICKET_E = 12,
     C_NBIG = 13,      // candidates in x-buckets larger than SEG_CAP (radix fallback needed if > 0)
     C_MAXB = 14,      // largest x-bucket
+    C_NHEAVY = 15,    // rows handed to k_rowfill_heavy
     C_COUNT = 16
 };
 
@@ -561,23 +562,98 @@ static __global__ void __launch_bounds__(256) k_scan_rows(u32 *__restrict__ data
     }
 }
 
-// one thread per row that owns entries; inside the row only the spans with a non-zero count byte are re-classified
+// Fill, ordinary rows: one thread per row (no grid-stride loop: a stride that is a multiple of Y would hand
+// every full-face row of a CSG box to the same threads); only the mixed spans (count byte != 0) are
+// re-classified.  HEAVY rows -- a row lying in an axis-aligned face owns up to Z entries -- are appended to a
+// list and filled by k_rowfill_heavy with one warp per row.
+constexpr u32 FILL_HEAVY = 160;   // entries per row above which the row goes to the heavy list
 static __global__ void __launch_bounds__(128) k_rowfill128(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
-                                                           const unsigned char *__restrict__ span_cnt, uint2 *__restrict__ entries, u32 cap) {
+                                                           const unsigned char *__restrict__ span_cnt, uint2 *__restrict__ entries, u32 cap,
+                                                           u32 *__restrict__ heavy_list, u32 heavy_cap, u32 *__restrict__ n_heavy) {
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < p.R; r += gridDim.x * blockDim.x) {
-        u32 off = row_start[r];
-        const u32 end = row_start[r + 1];
-        if (off == end) continue;
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R) return;
+    u32 off = row_start[r];
+    const u32 end = row_start[r + 1];
+    if (off == end) return;
+    if (end - off > FILL_HEAVY) {
+        const u32 slot = atomicAdd(n_heavy, 1u);
+        if (slot < heavy_cap) heavy_list[slot] = r;   // heavy_cap >= cap / FILL_HEAVY + 1 always suffices when S <= cap
+        return;
+    }
+    const u32 x = r / Y, y = r - x * Y;
+    SpanRows q = span_rows(bits, p, x, y, spr);
+    const unsigned char *rc = span_cnt + (size_t) r * spr;
+    for (u32 c4 = 0; c4 < spr && off < end; c4++) {
+        const u32 n = rc[c4];
+        if (!n) continue;
+        q.last = c4 + 1u == spr;
+        span_detail(q, r, c4, Z, entries, cap, off);
+        off += n;
+    }
+}
+
+// Fill, heavy rows: warp per row, lane per 32-point word; a shuffle scan of the per-word entry counts gives
+// the offsets, every lane emits at most 32 entries.
+static __global__ void __launch_bounds__(256) k_rowfill_heavy(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
+                                                              uint2 *__restrict__ entries, u32 cap, const u32 *__restrict__ heavy_list,
+                                                              u32 heavy_cap, const u32 *__restrict__ n_heavy) {
+    const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z, wpr = Z >> 5;   // words per row
+    const u32 lane = threadIdx.x & 31;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    u32 nh = *n_heavy;
+    if (nh > heavy_cap) nh = heavy_cap;
+    for (u32 h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nh; h += nwarps) {
+        const u32 r = heavy_list[h];
         const u32 x = r / Y, y = r - x * Y;
-        SpanRows q = span_rows(bits, p, x, y, spr);
-        const unsigned char *rc = span_cnt + (size_t) r * spr;
-        for (u32 c4 = 0; c4 < spr && off < end; c4++) {
-            const u32 n = rc[c4];
-            if (!n) continue;
-            q.last = c4 + 1u == spr;
-            span_detail(q, r, c4, Z, entries, cap, off);
-            off += n;
+        const bool hasX = x + 1u < X, hasY = y + 1u < Y, cellrow = hasX && hasY;
+        const u32 *ra = bits + (size_t) r * wpr;
+        const u32 *rb = ra + (hasY ? wpr : 0u);
+        const u32 *rcn = ra + (hasX ? (size_t) Y * wpr : 0);
+        const u32 *rd = rcn + (hasY ? wpr : 0u);
+        u32 off = row_start[r];
+        for (u32 wb = 0; wb < wpr; wb += 32) {
+            const u32 wi = wb + lane;
+            u32 m = 0, a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, ez = 0, ey = 0, ex = 0;
+            if (wi < wpr) {
+                const bool lastw = wi + 1u == wpr;
+                const u32 an = lastw ? 0u : __ldg(ra + wi + 1), bn = lastw ? 0u : __ldg(rb + wi + 1);
+                const u32 cn = lastw ? 0u : __ldg(rcn + wi + 1), dn = lastw ? 0u : __ldg(rd + wi + 1);
+                a0 = __ldg(ra + wi); b0 = __ldg(rb + wi); c0 = __ldg(rcn + wi); d0 = __ldg(rd + wi);
+                a1 = (a0 >> 1) | (an << 31); b1 = (b0 >> 1) | (bn << 31); c1 = (c0 >> 1) | (cn << 31); d1 = (d0 >> 1) | (dn << 31);
+                const u32 mz1 = lastw ? 0x7fffffffu : 0xffffffffu;
+                ez = (a0 ^ a1) & mz1;
+                ey = hasY ? (a0 ^ b0) : 0u;
+                ex = hasX ? (a0 ^ c0) : 0u;
+                u32 cellact = 0;
+                if (cellrow) {
+                    const u32 any = a0 | a1 | b0 | b1 | c0 | c1 | d0 | d1, all = a0 & a1 & b0 & b1 & c0 & c1 & d0 & d1;
+                    cellact = any & ~all & mz1;
+                }
+                m = cellact | ez | ey | ex;
+            }
+            const u32 n = __popc(m);
+            u32 incl = n;
+            for (u32 o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            u32 o = off + incl - n;
+            const u32 zb = wi * 32u;
+            while (m) {
+                const u32 b = __ffs(m) - 1;
+                m &= m - 1;
+                if (o < cap) {
+                    u32 cs = ((a0 >> b) & 1u) | (((a1 >> b) & 1u) << 1) | (((b0 >> b) & 1u) << 2) | (((b1 >> b) & 1u) << 3) |
+                             (((c0 >> b) & 1u) << 4) | (((c1 >> b) & 1u) << 5) | (((d0 >> b) & 1u) << 6) | (((d1 >> b) & 1u) << 7);
+                    if (!cellrow) cs &= 0x03u;
+                    const u32 own = ((ez >> b) & 1u) | (((ey >> b) & 1u) << 1) | (((ex >> b) & 1u) << 2);
+                    const u32 cv = (cellrow && (zb + b + 1u < Z)) ? 1u : 0u;
+                    entries[o] = make_uint2(r, (zb + b) | (cs << 16) | (own << 24) | (cv << 27));
+                }
+                o++;
+            }
+            off += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -666,11 +742,12 @@ static __global__ void __launch_bounds__(256) k_grid_points(Geom g, float *__res
     }
 }
 
+static inline u32 compact_heavy_cap(u32 cap) { return cap / FILL_HEAVY + 2; }
 // Enqueue the compaction stage: bits -> entries (ordered) + row_start + counters[C_S].
 // desc must hold compact_desc_count(p) zeroed descriptors; counters, row_start and span_cnt (one byte per
 // 128-point span, compact_span_bytes(p)) zeroed.
 static inline void launch_compact(const u32 *bits, const DenseParams &p, uint2 *entries, u32 cap, u32 *row_start, u64 *desc,
-                                  u32 *counters, unsigned char *span_cnt, cudaStream_t stream) {
+                                  u32 *counters, unsigned char *span_cnt, u32 *heavy_list, cudaStream_t stream) {
     if (compact128_ok(p)) {
         const u32 spr = (u32) (p.g.Z >> 7);
         // x planes marched per thread: keep >= ~1M threads in flight, at most 8 planes per thread
@@ -680,8 +757,10 @@ static inline void launch_compact(const u32 *bits, const DenseParams &p, uint2 *
         dim3 grid(((u32) p.g.Y * spr + 255) / 256, ((u32) p.g.X + xchunk - 1) / xchunk);
         ISX_LAUNCH(k_rowcount128, grid, 256, 0, stream, bits, p, row_start, span_cnt, xchunk);
         ISX_LAUNCH(k_scan_rows, 148 * 4, 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
-        const u32 fblocks = (p.R + 127u) / 128u;
-        ISX_LAUNCH(k_rowfill128, fblocks > 148u * 16u ? 148u * 16u : fblocks, 128, 0, stream, bits, p, row_start, span_cnt, entries, cap);
+        const u32 heavy_cap = compact_heavy_cap(cap);
+        ISX_LAUNCH(k_rowfill128, (p.R + 127u) / 128u, 128, 0, stream, bits, p, row_start, span_cnt, entries, cap, heavy_list, heavy_cap,
+                   counters + C_NHEAVY);
+        ISX_LAUNCH(k_rowfill_heavy, 148 * 4, 256, 0, stream, bits, p, row_start, entries, cap, heavy_list, heavy_cap, counters + C_NHEAVY);
     } else {
         ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, bits, p, entries, cap, row_start, desc, counters);
     }

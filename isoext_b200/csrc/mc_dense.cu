@@ -44,6 +44,7 @@ struct McBuffers {
     u32 *tri_off, *cand_info;
     u64 *descT, *descU, *descV;
     unsigned char *span_cnt;   // entries per 128-point span (span fast path)
+    u32 *heavy_list;           // rows filled cooperatively (k_rowfill_heavy)
     size_t zero_bytes;       // bytes from `counters` that one memset clears at the start of a call
     unsigned char *bdelta;   // per entry: x-bucket offset (+1) of its 3 owned edge vertices, 2 bits each
     SegHead seg;             // bucket histogram / offsets over the X+2 x-plane buckets
@@ -71,6 +72,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.tri_off = c.take<u32>(cap);
     b.cand_info = c.take<u32>(cap + 1);
     b.bdelta = c.take<unsigned char>(cap + 1);
+    b.heavy_list = c.take<u32>(compact_heavy_cap((u32) cap));
     if (out) *out = b;
     return c.bytes();
 }
@@ -435,7 +437,7 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
     const int sms = device_sms();
     const u32 nb = (u32) p.g.X + 2;   // x-plane buckets (local planes -1 .. X)
     launch_signbits(values, b.bits, p.P, p.level, stream);
-    launch_compact(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters, b.span_cnt, stream);
+    launch_compact(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters, b.span_cnt, b.heavy_list, stream);
     ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                b.trimask, b.used, b.bdelta);
     ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
