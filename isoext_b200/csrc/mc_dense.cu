@@ -449,14 +449,16 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
 // host_nc: number of candidates if the host knows it (two-phase path), else 0 with device_counts = true:
 // the kernels then read the counts from the counter block and do nothing if a capacity is exceeded.
 static int enqueue_phase2(const float *values, const DenseParams &p, int method, const McBuffers &b, const McScratch &s,
-                          u32 entry_cap, u32 host_nc, u32 n_big, bool device_counts, u32 cand_cap, u32 tri_cap, float x_lo_threshold,
+                          u32 entry_cap, u32 host_nc, u32 n_big, bool device_counts, u32 cand_cap, u32 tri_cap, u32 big_cap,
+                          float x_lo_threshold,
                           float x_hi_threshold, float *V, int32_t *F, cudaStream_t stream) {
     const int sms = device_sms();
     const u32 *n_dev = device_counts ? b.counters + C_VC : nullptr;
     const u32 grid_n = device_counts ? cand_cap : host_nc;
     ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, s.kx, s.ky, s.kz,
                s.seg.cbucket, cand_cap, entry_cap);
-    ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, (u32) p.g.X + 2, n_big, b.seg, s.seg, stream));
+    ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, (u32) p.g.X + 2, n_big,
+                          device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg, stream));
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
                b.descV, klo, khi, n_dev, cand_cap, true);
@@ -526,7 +528,8 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     Carver cs(scratch);
     McScratch s;
     if (carve_mc_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
-    rc = enqueue_phase2(values, p, method, b, s, (u32) cap_entries, (u32) n_candidates, (u32) n_big, false, 0xffffffffu, 0xffffffffu, x_lo_threshold,
+    rc = enqueue_phase2(values, p, method, b, s, (u32) cap_entries, (u32) n_candidates, (u32) n_big, false, 0xffffffffu, 0xffffffffu, 0,
+                        x_lo_threshold,
                         x_hi_threshold, V, F, stream);
     if (rc != OK) return rc;
     u32 h[C_COUNT];
@@ -542,13 +545,14 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
 // The caller provides output / scratch capacities (typically the sizes of the previous extraction of the
 // same grid): V has room for cand_cap rows, F for tri_cap rows, scratch for cand_cap candidates.
 // Returns ISOEXT_OK with counts_out = {S, T, Vc, n_big, V, n_lo, n_hi} when everything fitted; returns
-// 1 ("not completed") with counts_out[0..3] filled when a capacity was exceeded or the radix fallback is
-// needed (n_big > 0) -- outputs are then undefined and the caller uses count + emit.
+// 1 ("not completed") with counts_out[0..3] filled when a capacity was exceeded (entries, candidates,
+// triangles, or big_cap = the number of candidates in oversized x-buckets the radix fallback was sized for;
+// 0 = do not enqueue the fallback) -- outputs are then undefined and the caller uses count + emit.
 int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                         const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
-                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, float x_lo_threshold, float x_hi_threshold,
-                        float *V, int32_t *F, void *stream_, int64_t *counts_out) {
+                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, float x_lo_threshold,
+                        float x_hi_threshold, float *V, int32_t *F, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
@@ -566,15 +570,16 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
     const u32 cap = (u32) cap_entries;
     rc = enqueue_phase1(values, p, method, b, cap, stream);
     if (rc != OK) return rc;
+    if (big_cap < 0 || big_cap > cand_cap) return fail(E_INVALID, "big_cap out of range");
     rc = enqueue_phase2(values, p, method, b, s, cap, 0, 0, true, (u32) cand_cap, (u32) (tri_cap > 0xffffffffLL ? 0xffffffffLL : tri_cap),
-                        x_lo_threshold, x_hi_threshold, V, F, stream);
+                        (u32) big_cap, x_lo_threshold, x_hi_threshold, V, F, stream);
     if (rc != OK) return rc;
     u32 h[C_COUNT];
     rc = read_counters(b, h, stream);
     if (rc != OK) return rc;
     counts_out[0] = h[C_S]; counts_out[1] = h[C_T]; counts_out[2] = h[C_VC]; counts_out[3] = h[C_NBIG];
     counts_out[4] = h[C_V]; counts_out[5] = h[C_NLO]; counts_out[6] = h[C_NHI];
-    if (h[C_S] > cap || h[C_VC] > (u32) cand_cap || (i64) h[C_T] > tri_cap || h[C_NBIG] > 0) return 1;
+    if (h[C_S] > cap || h[C_VC] > (u32) cand_cap || (i64) h[C_T] > tri_cap || h[C_NBIG] > (u32) big_cap) return 1;
     return OK;
 }
 

@@ -43,8 +43,10 @@ struct RadixBuffers {
 };
 
 static __global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
-                                                    const u32 *__restrict__ kz, u32 n, u32 *__restrict__ hist) {
+                                                    const u32 *__restrict__ kz, u32 n, u32 *__restrict__ hist,
+                                                    const u32 *__restrict__ n_dev) {
     __shared__ u32 sh[RADIX_PASSES * 256];
+    if (n_dev) n = *n_dev;
     for (int i = threadIdx.x; i < RADIX_PASSES * 256; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -121,8 +123,10 @@ template <bool GATHER, bool IDENTITY>
 static __global__ void __launch_bounds__(RADIX_THREADS)
 k_radix_pass(const u32 *__restrict__ key_in, const u32 *__restrict__ perm_in, u32 *__restrict__ key_out,
              u32 *__restrict__ perm_out, const u32 *__restrict__ src_keys, u32 shift,
-             const u32 *__restrict__ gprefix, u64 *__restrict__ desc, u32 *__restrict__ ticket, u32 epoch, u32 n) {
+             const u32 *__restrict__ gprefix, u64 *__restrict__ desc, u32 *__restrict__ ticket, u32 epoch, u32 n,
+             const u32 *__restrict__ n_dev) {
     __shared__ u32 cnt[RADIX_THREADS / 32][256];
+    if (n_dev) n = *n_dev;       // device-side count: blocks beyond the last tile leave right after their ticket
     __shared__ u32 gbase[256];
     __shared__ u32 s_tile;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,6 +134,7 @@ k_radix_pass(const u32 *__restrict__ key_in, const u32 *__restrict__ perm_in, u3
     for (int i = threadIdx.x; i < (RADIX_THREADS / 32) * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
+    if (tile * RADIX_TILE >= n) return;
     const u32 base = tile * RADIX_TILE + warp * (32 * RADIX_ITEMS);
 
     u32 key[RADIX_ITEMS], perm[RADIX_ITEMS], rank[RADIX_ITEMS];
@@ -193,9 +198,10 @@ k_radix_pass(const u32 *__restrict__ key_in, const u32 *__restrict__ perm_in, u3
 }
 
 // Enqueue the whole sort on `stream`.  Result: b.perm[0] holds the sorted order (item ids).
-// kx/ky/kz: order-preserving u32 keys (float_key).  n may be 0.
+// kx/ky/kz: order-preserving u32 keys (float_key).  n may be 0.  If n_dev != nullptr the item count is read
+// on the device (it must be <= n, which then only sizes the launches and the descriptor reset).
 static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const RadixBuffers &b,
-                                       cudaStream_t stream) {
+                                       cudaStream_t stream, const u32 *n_dev = nullptr) {
     if (n == 0) return cudaSuccess;
     const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
     cudaError_t e = cudaMemsetAsync(b.hist, 0, (RADIX_PASSES * 256 + 16) * sizeof(u32), stream);
@@ -204,7 +210,7 @@ static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *
     if (e != cudaSuccess) return e;
     u32 hist_blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (hist_blocks > 148 * 4) hist_blocks = 148 * 4;
-    ISX_LAUNCH(k_radix_hist, hist_blocks, 256, 0, stream, kx, ky, kz, n, b.hist);
+    ISX_LAUNCH(k_radix_hist, hist_blocks, 256, 0, stream, kx, ky, kz, n, b.hist, n_dev);
     ISX_LAUNCH(k_radix_prefix, 1, 32 * RADIX_PASSES, 0, stream, b.hist);
     const u32 *src[3] = {kz, ky, kx};
     for (int p = 0; p < RADIX_PASSES; p++) {
@@ -212,14 +218,14 @@ static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *
         const u32 shift = 8 * (p & 3);
         const u32 *coord = src[p >> 2];
         if (p == 0)
-            ISX_LAUNCH((k_radix_pass<true, true>), ntiles, RADIX_THREADS, 0, stream, 
-                b.key[in], b.perm[in], b.key[out], b.perm[out], coord, shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n);
+            ISX_LAUNCH((k_radix_pass<true, true>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
+                       shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
         else if ((p & 3) == 0)
-            ISX_LAUNCH((k_radix_pass<true, false>), ntiles, RADIX_THREADS, 0, stream, 
-                b.key[in], b.perm[in], b.key[out], b.perm[out], coord, shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n);
+            ISX_LAUNCH((k_radix_pass<true, false>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
+                       shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
         else
-            ISX_LAUNCH((k_radix_pass<false, false>), ntiles, RADIX_THREADS, 0, stream, 
-                b.key[in], b.perm[in], b.key[out], b.perm[out], coord, shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n);
+            ISX_LAUNCH((k_radix_pass<false, false>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
+                       shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
     }
     return cudaGetLastError();
 }

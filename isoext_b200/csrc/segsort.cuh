@@ -299,12 +299,14 @@ static __global__ void __launch_bounds__(256) k_seg_big_gather(u32 nb, const u32
     }
 }
 // sorted rank r of the big list -> final position: the big list is ordered by bucket (x decides the bucket)
-static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const u32 *__restrict__ sorted, const u32 *__restrict__ bid,
+static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const u32 *__restrict__ nbig_dev, const u32 *__restrict__ sorted,
+                                                                const u32 *__restrict__ bid,
                                                                 const u32 *__restrict__ cbucket, const u32 *__restrict__ start,
                                                                 const u32 *__restrict__ bigoff, u32 *__restrict__ perm,
                                                                 const u32 *__restrict__ bkx, const u32 *__restrict__ bky,
                                                                 const u32 *__restrict__ bkz, u32 *__restrict__ skx, u32 *__restrict__ sky,
                                                                 u32 *__restrict__ skz) {
+    if (nbig_dev) n_big = *nbig_dev;
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_big; r += gridDim.x * blockDim.x) {
         const u32 j = sorted[r];
         const u32 id = bid[j];
@@ -315,12 +317,15 @@ static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const
     }
 }
 
-// Phase-2 part of the segmented sort: group by bucket, sort the small buckets in shared memory, and --
-// if the host learned at the phase-1 sync that big buckets exist (n_big > 0) -- run the radix fallback.
-// The histogram (h.count) and its scan (h.start / h.bigoff) were produced in phase 1.
-// n_dev != nullptr: the item count is read on the device (must be <= n_cap); grid_n sizes the launches.
+// Phase-2 part of the segmented sort: group by bucket, sort the small buckets in shared memory, and run the
+// radix fallback for the oversized buckets.  The histogram (h.count) and its scan (h.start / h.bigoff) were
+// produced in phase 1.
+//   two-phase path : n, n_big known on the host (n_dev = nbig_dev = nullptr); the fallback runs iff n_big > 0
+//   single-sync path: counts live on the device; n_cap sizes the launches; the fallback is enqueued iff
+//                    big_cap > 0 (the caller's guess) and does nothing when the device count is 0
 static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const u32 *n_dev, u32 n_cap, u32 grid_n,
-                                       u32 nb, u32 n_big, const SegHead &h, const SegScratch &b, cudaStream_t stream) {
+                                       u32 nb, u32 n_big, const u32 *nbig_dev, u32 big_cap, const SegHead &h, const SegScratch &b,
+                                       cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEG_SMEM);
@@ -330,14 +335,15 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
     ISX_LAUNCH(k_seg_scatter, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap);
     ISX_LAUNCH(k_seg_sort, nb, SEG_THREADS, SEG_SMEM, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm, b.skx, b.sky,
                b.skz, n_dev, n_cap);
-    if (n_big > 0) {
+    const u32 fb_n = nbig_dev ? big_cap : n_big;
+    if (fb_n > 0) {
         dim3 grid(32, nb < 1024 ? nb : 1024);
         ISX_LAUNCH(k_seg_big_gather, grid, 256, 0, stream, nb, h.count, h.start, h.bigoff, b.perm0, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid);
-        cudaError_t e = radix_sort96(b.bkx, b.bky, b.bkz, n_big, b.radix, stream);
+        cudaError_t e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, nbig_dev);
         if (e != cudaSuccess) return e;
-        const int bb = (int) ((n_big + 255) / 256 > 148 * 8 ? 148 * 8 : (n_big + 255) / 256);
-        ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, n_big, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx, b.bky,
-                   b.bkz, b.skx, b.sky, b.skz);
+        const int bb = (int) ((fb_n + 255) / 256 > 148 * 8 ? 148 * 8 : (fb_n + 255) / 256);
+        ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, fb_n, nbig_dev, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx,
+                   b.bky, b.bkz, b.skx, b.sky, b.skz);
     }
     return cudaGetLastError();
 }

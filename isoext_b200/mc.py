@@ -47,19 +47,21 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     cap = max(int(cap_hint), _initial_cap(shape))
     thr_lo, thr_hi = float(x_thresholds[0]), float(x_thresholds[1])
 
-    if hints is not None and hints.get("Vc", 0) > 0 and hints.get("T", 0) > 0 and not hints.get("big", False):
+    if hints is not None and hints.get("Vc", 0) > 0 and hints.get("T", 0) > 0:
         cand_cap = hints["Vc"] + (hints["Vc"] >> 6) + 16
         tri_cap = hints["T"] + (hints["T"] >> 6) + 16
+        nb_hint = hints.get("n_big", 0)
+        big_cap = min(cand_cap, nb_hint + (nb_hint >> 6) + 16) if nb_hint > 0 else 0
         wsbuf = ws.get("mc_ws", lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap), dev)
         scratch = ws.get("mc_scratch", lib.isoext_mc_dense_scratch_bytes(cand_cap), dev)
         V = torch.empty((cand_cap, 3), dtype=torch.float32, device=dev)
         F = torch.empty((tri_cap, 3), dtype=torch.int32, device=dev)
         rc = lib.isoext_mc_dense_run(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
                                      wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(), cand_cap, tri_cap,
-                                     thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), stream, counts)
+                                     big_cap, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), stream, counts)
         if rc == 0:
             S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
-            hints.update(Vc=Vc, T=T)
+            hints.update(Vc=Vc, T=T, n_big=int(counts[3]))
             if Vc == 0:
                 return None, None, 0, 0, cap
             return V[:int(counts[4])], F[:T], int(counts[5]), int(counts[6]), max(cap, S)
@@ -83,7 +85,7 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         break
     S, T, Vc, n_big = int(counts[0]), int(counts[1]), int(counts[2]), int(counts[3])
     if hints is not None:
-        hints.update(Vc=Vc, T=T, big=n_big > 0)
+        hints.update(Vc=Vc, T=T, n_big=n_big)
     if Vc == 0:   # no vertex at all (T == 0 alone is not enough: a slab may own vertices that only
         return None, None, 0, 0, cap   # its neighbour's faces reference)
     sbytes = lib.isoext_mc_dense_scratch_bytes(Vc)
