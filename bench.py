@@ -255,7 +255,10 @@ def run_ours(args):
 
     if rank == 0:
         # roofline of the dominant kernel (k_signbits: the one volume-sized HBM stream); 4 B/voxel algorithmic
+        # large grids are streamed as several x-chunks per step: bytes per launch = 4 B x voxels of that launch
         local_vox = voxels if world == 1 else float(sg.local_points())
+        launches_per_step = max(1.0, sm_n.value / float(args.steps))
+        local_vox = local_vox / launches_per_step
         k_ms = sm_ms.value / max(1, sm_n.value)
         achieved = 4.0 * local_vox / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         traffic = None
@@ -278,7 +281,7 @@ def run_ours(args):
             "gpu_launches": int(launches.value),
             "roofline": {"bound": "hbm", "kernel": "k_signbits", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": k_ms, "kernel_launches_timed": int(sm_n.value),
+                         "kernel_ms": k_ms, "kernel_launches_timed": int(sm_n.value), "kernel_launches_per_step": launches_per_step,
                          "algorithmic_bytes_per_launch": 4.0 * local_vox,
                          "whole_path_frac": (4.0 * voxels + 12.0 * nV + 12.0 * nT) / (ms_step * 1e-3) / 1e9 / peak / world},
         }

@@ -27,6 +27,7 @@ SIGNATURES = {
     "isoext_debug_set_signbits_variant": (_int, [_int]),
     "isoext_debug_detail_enable": (_int, [_int]),
     "isoext_debug_detail_report": (_int, [C.c_char_p, _int]),
+    "isoext_debug_detail_timeline": (_int, [C.c_char_p, _int]),
     "isoext_profile_begin": (_int, []),
     "isoext_profile_end": (_int, [C.POINTER(C.c_double), _pi64, _pi64]),
     "isoext_grid_points_dense": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp]),
@@ -65,6 +66,9 @@ SIGNATURES = {
                                      _vp, _pi64]),
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
+    "isoext_mc_dense_run_chunked": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64, _f32, _f32, _int,
+                                           _vp, _sz, _i64, _vp, _sz, _pi64, _pi64, _pi64, _vp, _pi64, _vp, _pi64, _vp, _i64, _vp,
+                                           _i64, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
 }
 

@@ -48,6 +48,26 @@ int isoext_debug_set_signbits_variant(int v) { isx::g_signbits_variant = v; retu
 // Development: per-kernel CUDA-event timing.  enable(1) starts collecting; report() synchronises, writes
 // "name total_us launches" lines into buf and clears the records.
 int isoext_debug_detail_enable(int on) { isx::g_detail_timing = on != 0; return 0; }
+// timeline variant: one line per launch "name start_us end_us" relative to the first recorded event
+int isoext_debug_detail_timeline(char *buf, int buf_size) {
+    cudaDeviceSynchronize();
+    std::string out;
+    if (!isx::g_detail.empty()) {
+        cudaEvent_t first = isx::g_detail.front().e0;
+        for (auto &r : isx::g_detail) {
+            float t0 = 0, t1 = 0;
+            if (r.e1 && cudaEventElapsedTime(&t0, first, r.e0) == cudaSuccess && cudaEventElapsedTime(&t1, first, r.e1) == cudaSuccess) {
+                char line[256];
+                snprintf(line, sizeof(line), "%-28s %10.1f %10.1f\n", r.name, t0 * 1e3, t1 * 1e3);
+                out += line;
+            }
+        }
+        for (auto &r : isx::g_detail) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        isx::g_detail.clear();
+    }
+    snprintf(buf, buf_size, "%s", out.c_str());
+    return 0;
+}
 int isoext_debug_detail_report(char *buf, int buf_size) {
     cudaDeviceSynchronize();
     std::map<std::string, std::pair<double, int>> acc;

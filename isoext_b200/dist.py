@@ -155,15 +155,15 @@ def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae"
     p = sg.plan
     X, Y, Z = sg.shape
     with torch.cuda.device(sg.device):
-        v_ext, f, n_lo, n_hi, cap = mc_dense_raw(sg._ext, (p["n_ext"], Y, Z), sg.aabb_min, sg.aabb_max, level, mid, sg._ws,
+        v_own, f, n_lo, n_hi, cap = mc_dense_raw(sg._ext, (p["n_ext"], Y, Z), sg.aabb_min, sg.aabb_max, level, mid, sg._ws,
                                                  cap_hint=sg._cap_hint, x_offset=p["ext_lo"], x_global=X,
                                                  emit_range=(p["emit_lo"], p["emit_hi"]), x_thresholds=sg.thresholds,
                                                  hints=sg._hints)
     sg._cap_hint = cap
-    if v_ext is None:
+    if v_own is None:
         return (torch.empty((0, 3), dtype=torch.float32, device=sg.device),
                 torch.empty((0, 3), dtype=torch.int32, device=sg.device), 0, 0)
-    return v_ext[n_lo:n_hi], f, n_lo, n_hi
+    return v_own, f, n_lo, n_hi
 
 
 def relabel_faces_(f: torch.Tensor, n_lo: int, n_hi: int, base_mine: int, base_next: int) -> None:
