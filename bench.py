@@ -289,6 +289,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline_port()
         print(json.dumps(line), flush=True)
     if world > 1:
+        sg.close()
         dist.destroy_process_group()
 
 

@@ -224,6 +224,36 @@ int isoext_mc_dense_run_chunked(const float *values, int64_t X, int64_t Y, int64
 int isoext_relabel_faces(int32_t *F, int64_t n_ids, int64_t n_lo, int64_t n_hi, int64_t base_mine,
                          int64_t base_next, void *stream);
 
+/* ---- NVLink / NVSwitch peer transport of the slab-sharded path (no reference counterpart: the
+ * reference is single-GPU; replaces NCCL send/recv + all_gather on one node) ---------------------
+ * Every rank allocates its value slab and a SYNC block of isoext_peer_sync_words() u64 with
+ * isoext_peer_alloc (cudaMalloc + cudaIpcGetMemHandle), ships the 64-byte handles to the other ranks
+ * (any host channel) and maps theirs with isoext_peer_open.  SYNC words: [0] READY epoch, [1] DONE epoch,
+ * [2 + 4*s ..] ring of 32 count slots {epoch, n_own, n_tri, -}.  err_mapped points to host-mapped
+ * (pinned) memory: a kernel that waits longer than 20 s for a peer sets it to 1 and stops waiting. */
+int isoext_peer_sync_words(void);
+int isoext_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle64);
+int isoext_peer_free(void *d_ptr);
+int isoext_peer_open(const unsigned char *handle64, void **d_ptr);
+int isoext_peer_close(void *d_ptr);
+/* *d_flag = value with release semantics at system scope, after everything enqueued before on `stream`. */
+int isoext_peer_publish(uint64_t *d_flag, uint64_t value, void *stream);
+/* Wait on the stream until *flag >= want for each non-null flag (peer memory). */
+int isoext_peer_wait(const uint64_t *d_flag_a, const uint64_t *d_flag_b, uint64_t want, uint32_t *err_mapped, void *stream);
+/* One kernel: wait until the owners of the two source segments have published READY >= epoch, then copy
+ * n0 / n1 floats from their slabs (peer memory) into the local halo planes. */
+int isoext_peer_halo_pull(float *d_dst0, const float *peer_src0, int64_t n0, const uint64_t *peer_ready0, float *d_dst1,
+                          const float *peer_src1, int64_t n1, const uint64_t *peer_ready1, uint64_t epoch,
+                          uint32_t *err_mapped, void *stream);
+/* Publish this rank's (owned vertices, triangles) of `epoch` in its SYNC block. */
+int isoext_peer_publish_counts(uint64_t *d_sync, uint64_t epoch, int64_t n_own, int64_t n_tri, void *stream);
+/* isoext_relabel_faces with the bases computed on the device: base_mine = sum of n_own over the ranks
+ * below `rank`, read from their SYNC blocks (peer_syncs: host array of >= rank device pointers).
+ * d_bases_out (optional, 2 x int64): {vertex base, face base}. */
+int isoext_relabel_faces_peer(int32_t *d_F, int64_t n_ids, int64_t n_lo, int64_t n_hi, int64_t n_own,
+                              const uint64_t *const *peer_syncs, int rank, uint64_t epoch, int64_t *d_bases_out,
+                              uint32_t *err_mapped, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,16 @@ SIGNATURES = {
                                            _vp, _sz, _i64, _vp, _sz, _pi64, _pi64, _pi64, _vp, _pi64, _vp, _pi64, _vp, _i64, _vp,
                                            _i64, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "isoext_peer_sync_words": (_int, []),
+    "isoext_peer_alloc": (_int, [_sz, C.POINTER(_vp), C.POINTER(C.c_ubyte)]),
+    "isoext_peer_free": (_int, [_vp]),
+    "isoext_peer_open": (_int, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
+    "isoext_peer_close": (_int, [_vp]),
+    "isoext_peer_publish": (_int, [_vp, C.c_uint64, _vp]),
+    "isoext_peer_wait": (_int, [_vp, _vp, C.c_uint64, _vp, _vp]),
+    "isoext_peer_halo_pull": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, C.c_uint64, _vp, _vp]),
+    "isoext_peer_publish_counts": (_int, [_vp, C.c_uint64, _i64, _i64, _vp]),
+    "isoext_relabel_faces_peer": (_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_vp), _int, C.c_uint64, _vp, _vp, _vp]),
 }
 
 _lib = None

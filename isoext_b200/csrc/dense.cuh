@@ -47,7 +47,12 @@ struct DenseParams {
     u32 R;       // rows = X*Y
     float level;
     u32 emit_lo, emit_hi;   // local cell-x range [lo,hi) whose faces / quads are emitted
+    // sort buckets (segsort.cuh): every x-layer [px[b], px[b+1]) is cut into gy groups of vertices lying exactly
+    // on plane b (split by y) and gx groups of vertices inside the layer (split by x)
+    u32 gy, gx, ystep;
 };
+__host__ __device__ __forceinline__ u32 sort_nsub(const DenseParams &p) { return p.gy + p.gx; }
+__host__ __device__ __forceinline__ u32 sort_buckets(const DenseParams &p) { return ((u32) p.g.X + 2) * (p.gy + p.gx); }
 
 constexpr u32 ENT_Z_MASK = 0xffffu;
 __device__ __forceinline__ u32 ent_z(u32 w) { return w & ENT_Z_MASK; }

@@ -12,6 +12,7 @@
 //   k_unique                  positional welding of candidates that snapped onto a shared corner
 //   k_emit_faces              LUT-driven face emission with final vertex ids
 // Every arithmetic step that decides a bit of the output uses explicit _rn intrinsics.
+#include <cstdlib>
 #include "dense.cuh"
 #include "radix.cuh"
 #include "weld.cuh"
@@ -46,8 +47,8 @@ struct McBuffers {
     unsigned char *span_cnt;   // entries per 128-point span (span fast path)
     u32 *heavy_list;           // rows filled cooperatively (k_rowfill_heavy)
     size_t zero_bytes;       // bytes from `counters` that one memset clears at the start of a call
-    unsigned char *bdelta;   // per entry: x-bucket offset (+1) of its 3 owned edge vertices, 2 bits each
-    SegHead seg;             // bucket histogram / offsets over the X+2 x-plane buckets
+    u32 *bdelta;   // per entry: sort bucket (layer offset + sub-bucket) of its 3 owned edge vertices, one byte each
+    SegHead seg;             // bucket histogram / offsets over the sort buckets (sort_buckets(p))
 };
 
 static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *out) {
@@ -58,7 +59,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.descT = c.take<u64>(cap / SE_TILE + 2);
     b.descU = c.take<u64>(cap / SE_TILE + 2);
     b.descV = c.take<u64>(3 * cap / UQ_TILE + 2);
-    SegHead::carve(c, (size_t) p.g.X + 2, &b.seg);
+    SegHead::carve(c, (size_t) sort_buckets(p), &b.seg);
     b.row_start = c.take<u32>((size_t) p.R + 2);   // accumulates the per-row entry counts before it is scanned
     b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
     b.used = c.take<unsigned char>(3 * (cap + 2));
@@ -71,7 +72,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.trimask = c.take<unsigned char>(cap);
     b.tri_off = c.take<u32>(cap);
     b.cand_info = c.take<u32>(cap + 1);
-    b.bdelta = c.take<unsigned char>(cap + 1);
+    b.bdelta = c.take<u32>(cap + 1);
     b.heavy_list = c.take<u32>(compact_heavy_cap((u32) cap));
     if (out) *out = b;
     return c.bytes();
@@ -94,37 +95,68 @@ static size_t carve_mc_scratch(Carver &c, size_t nc, McScratch *out) {
     return c.bytes();
 }
 
-// x-plane bucket of the vertices on the entry's owned edges, relative to the entry's own plane x:
-// code = delta + 1 in {0,1,2}, 2 bits per axis (bit 0-1: +z edge, 2-3: +y, 4-5: +x).  The bucket of a
-// position is b = #{i : px[i] <= x'} - 1, a monotone function of x' (segsort.cuh); for a vertex owned by
-// plane x it is x-1 (an in-plane vertex whose x rounded just below px[x]), x, or x+1 (an x-edge vertex
-// that landed exactly on the next plane).
-__device__ __forceinline__ u32 owned_bucket_deltas(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, u32 own) {
-    if (!own) return 0x15u;
+// Sort bucket of the vertices on the entry's owned edges (segsort.cuh).  Any function of the position that is
+// monotone in the lexicographic (x, y, z) order will do; this one is exact float compares only:
+//   layer  b = #{i : px[i] <= x'} - 1; for a vertex owned by plane x it is x-1 (an in-plane vertex whose x rounded
+//            just below px[x]), x, or x+1 (an x-edge vertex that landed on the next plane): code = delta+1 in {0,1,2}
+//   inside a layer: vertices with x' == px[b] exactly come first, cut into gy groups by y (thresholds are the
+//            y-plane positions py[g*ystep]); then the vertices with x' > px[b], cut into gx groups by
+//            floor((x' - px[b]) * gx / (px[b+1] - px[b])) (monotone in x').
+// Encoding: one byte per owned axis (0: +z edge, 1: +y, 2: +x) = code | sub << 2.
+__device__ __forceinline__ u32 sub_bucket(const DenseParams &p, i64 xb /* global layer index */, float xv, float yv, u32 y) {
+    if (xb < 0) return 0u;
+    const u32 resx = (u32) p.g.Xg - 1;
+    const float pb = axis_pos((u32) xb, resx, p.g.amin[0], p.g.asize[0]);
+    if (xv == pb) {
+        if (p.gy == 1) return 0u;
+        const u32 g0 = y / p.ystep;
+        const u32 resy = (u32) p.g.Y - 1;
+        if (g0 >= 1 && yv < axis_pos(g0 * p.ystep, resy, p.g.amin[1], p.g.asize[1])) return g0 - 1;
+        if (g0 + 1 < p.gy && yv >= axis_pos((g0 + 1) * p.ystep, resy, p.g.amin[1], p.g.asize[1])) return g0 + 1;
+        return g0;
+    }
+    if (p.gx == 1) return p.gy;
+    const float pb1 = axis_pos((u32) xb + 1, resx, p.g.amin[0], p.g.asize[0]);
+    const float f = __fmul_rn(__fsub_rn(xv, pb), __fdiv_rn((float) p.gx, __fsub_rn(pb1, pb)));
+    u32 k = f > 0.f ? (u32) f : 0u;   // NaN / negative -> 0; monotone
+    if (k > p.gx - 1) k = p.gx - 1;
+    return p.gy + k;
+}
+
+__device__ __forceinline__ u32 owned_buckets(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, u32 own) {
+    if (!own) return 0u;
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
-    const u32 x = r / Y;
+    const u32 x = r / Y, y = r - x * Y;
     const i64 n = (i64) r * Z + z;
     const u32 xg = x + (u32) p.g.x_off;
     const float v0 = __ldg(values + n);
     const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
-    u32 code = 0x15u;   // delta 0 everywhere
+    const float py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
+    u32 out = 0;
     if (own & 1u) {
         const float t = edge_t(v0, __ldg(values + n + 1), p.level);
-        if (lerp_ref(t, px0, px0) < px0) code = (code & ~0x03u) | 0x00u;
+        const float xv = lerp_ref(t, px0, px0);
+        const u32 code = xv < px0 ? 0u : 1u;
+        out |= code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py0), y) << 2);
     }
     if (own & 2u) {
         const float t = edge_t(v0, __ldg(values + n + Z), p.level);
-        if (lerp_ref(t, px0, px0) < px0) code = (code & ~0x0cu) | 0x00u;
+        const float xv = lerp_ref(t, px0, px0);
+        const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
+        const u32 code = xv < px0 ? 0u : 1u;
+        out |= (code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py1), y) << 2)) << 8;
     }
     if (own & 4u) {
         const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
         const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
         const float xv = lerp_ref(t, px0, px1);
-        if (xv >= px1) code = (code & ~0x30u) | 0x20u;
-        else if (xv < px0) code = (code & ~0x30u) | 0x00u;
+        const u32 code = xv >= px1 ? 2u : (xv < px0 ? 0u : 1u);
+        out |= (code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py0), y) << 2)) << 16;
     }
-    return code;
+    return out;
 }
+// bucket id from the byte of one owned axis
+__device__ __forceinline__ u32 bucket_of(u32 x, u32 byte, u32 nsub) { return (x + (byte & 3u)) * nsub + ((byte >> 2) & 63u); }
 
 // ---------------------------------------------------------------------------------------------
 // K3: one thread per entry that is a valid cell.
@@ -133,14 +165,14 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
                                                    const uint2 *__restrict__ entries, const u32 *__restrict__ row_start,
                                                    u32 cap, const u32 *__restrict__ counters, u32 *__restrict__ nb,
                                                    unsigned char *__restrict__ ntri, unsigned char *__restrict__ trimask,
-                                                   unsigned char *__restrict__ used, unsigned char *__restrict__ bdelta) {
+                                                   unsigned char *__restrict__ used, u32 *__restrict__ bdelta) {
     const u32 S = counters[C_S];
     if (S > cap) return;
     const u32 Y = (u32) p.g.Y;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const uint2 e = entries[s];
         const u32 w = e.y;
-        bdelta[s] = (unsigned char) owned_bucket_deltas(values, p, e.x, ent_z(w), ent_own(w));
+        bdelta[s] = owned_buckets(values, p, e.x, ent_z(w), ent_own(w));
         if (!ent_cell(w) || ent_case(w) == 0u || ent_case(w) == 255u) {
             ntri[s] = 0;
             trimask[s] = 0;
@@ -195,13 +227,13 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
 __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__ counters, const unsigned char *__restrict__ ntri,
                                                       const unsigned char *__restrict__ used, u32 *__restrict__ tri_off,
                                                       u32 *__restrict__ cand_info, u64 *__restrict__ descT, u64 *__restrict__ descU,
-                                                      const uint2 *__restrict__ entries, const unsigned char *__restrict__ bdelta,
-                                                      u32 Y, u32 *__restrict__ bucket_count, u32 nb, SegHead seg) {
+                                                      const uint2 *__restrict__ entries, const u32 *__restrict__ bdelta,
+                                                      u32 Y, u32 nsub, u32 *__restrict__ bucket_count, u32 nb, SegHead seg) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_preT, s_preU;
     // x-bucket histogram window: the entries of a tile are sorted by x, so almost all of its vertices fall
     // into a handful of consecutive buckets; count those in shared memory, the rest directly in L2
-    constexpr u32 WIN = 32;
+    constexpr u32 WIN = 256;
     __shared__ u32 s_hist[WIN];
     __shared__ u32 s_last, s4[4];
     const u32 S = counters[C_S];
@@ -214,7 +246,7 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
-        const u32 win0 = entries[tile * SE_TILE].x / Y;   // bucket of plane x-1 of the tile's first entry
+        const u32 win0 = (entries[tile * SE_TILE].x / Y) * nsub;   // first bucket of layer x-1 of the tile's first entry
         const u32 s0 = tile * SE_TILE + threadIdx.x * SE_ITEMS;
         u32 nt[SE_ITEMS], um[SE_ITEMS], sumT = 0, sumU = 0;
 #pragma unroll
@@ -230,7 +262,7 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
 #pragma unroll
                     for (int a = 0; a < 3; a++)
                         if ((um[j] >> a) & 1u) {
-                            const u32 bkt = x + ((bd >> (2 * a)) & 3u);
+                            const u32 bkt = bucket_of(x, bd >> (8 * a), nsub);
                             if (bkt - win0 < WIN) atomicAdd(&s_hist[bkt - win0], 1u);
                             else atomicAdd(&bucket_count[bkt], 1u);
                         }
@@ -285,12 +317,12 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
-                                                  const u32 *__restrict__ cand_info, const unsigned char *__restrict__ bdelta,
+                                                  const u32 *__restrict__ cand_info, const u32 *__restrict__ bdelta,
                                                   u32 *__restrict__ kx, u32 *__restrict__ ky, u32 *__restrict__ kz,
                                                   u32 *__restrict__ cbucket, u32 cand_cap, u32 entry_cap) {
     const u32 S = counters[C_S];
     if (S > entry_cap || counters[C_VC] > cand_cap) return;   // single-call fast path: the host re-runs with larger buffers
-    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, nsub = sort_nsub(p);
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const u32 ci = cand_info[s];
         const u32 um = ci >> 29;
@@ -312,7 +344,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             kx[id] = float_key(lerp_ref(t, px0, px0));
             ky[id] = float_key(lerp_ref(t, py0, py0));
             kz[id] = float_key(lerp_ref(t, pz0, pz1));
-            cbucket[id] = x + (bd & 3u);
+            cbucket[id] = bucket_of(x, bd, nsub);
             id++;
         }
         if (um & 2u) {   // +y edge
@@ -321,7 +353,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             kx[id] = float_key(lerp_ref(t, px0, px0));
             ky[id] = float_key(lerp_ref(t, py0, py1));
             kz[id] = float_key(lerp_ref(t, pz0, pz0));
-            cbucket[id] = x + ((bd >> 2) & 3u);
+            cbucket[id] = bucket_of(x, bd >> 8, nsub);
             id++;
         }
         if (um & 4u) {   // +x edge
@@ -330,7 +362,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             kx[id] = float_key(lerp_ref(t, px0, px1));
             ky[id] = float_key(lerp_ref(t, py0, py0));
             kz[id] = float_key(lerp_ref(t, pz0, pz0));
-            cbucket[id] = x + ((bd >> 4) & 3u);
+            cbucket[id] = bucket_of(x, bd >> 16, nsub);
         }
     }
 }
@@ -397,6 +429,24 @@ int make_dense_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin,
     p.level = level;
     p.emit_lo = (u32) (emit_lo < 0 ? 0 : emit_lo);
     p.emit_hi = (u32) (emit_hi < 0 ? 0 : emit_hi);
+    // sort buckets: a layer holds ~ (2..8) * max(Y,Z) vertices and a bucket must stay below SEG_CAP = 4096 for
+    // the shared-memory sort; finer buckets do not sort faster (measured: profiles/r1_sort_group_sweep.txt)
+    const i64 m = Y > Z ? Y : Z;
+    u32 gy = 1;
+    while (gy < 16 && (i64) gy * 2 * 1024 <= m) gy *= 2;
+    p.gy = gy;
+    p.gx = gy > 1 ? gy / 2 : 1;
+    {   // tuning hook (tools/tune_sort_groups.py): ISX_SORT_GY / ISX_SORT_GX override the heuristic
+        static int egy = -1, egx = -1;
+        if (egy < 0) {
+            const char *a = getenv("ISX_SORT_GY"), *b = getenv("ISX_SORT_GX");
+            egy = a ? atoi(a) : 0;
+            egx = b ? atoi(b) : 0;
+        }
+        if (egy > 0 && egy <= 32) p.gy = (u32) egy;
+        if (egx > 0 && egx <= 32) p.gx = (u32) egx;
+    }
+    p.ystep = (u32) ((Y + p.gy - 1) / p.gy);
     *out = p;
     return OK;
 }
@@ -445,11 +495,11 @@ static void enqueue_compact(const DenseParams &p, const McBuffers &b, u32 cap, c
 }
 static int enqueue_analysis(const float *values, const DenseParams &p, int method, const McBuffers &b, u32 cap, cudaStream_t stream) {
     const int sms = device_sms();
-    const u32 nb = (u32) p.g.X + 2;   // x-plane buckets (local planes -1 .. X)
+    const u32 nb = sort_buckets(p);
     ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                b.trimask, b.used, b.bdelta);
     ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
-               b.entries, b.bdelta, (u32) p.g.Y, b.seg.count, nb, b.seg);
+               b.entries, b.bdelta, (u32) p.g.Y, sort_nsub(p), b.seg.count, nb, b.seg);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }
@@ -472,7 +522,7 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const u32 grid_n = device_counts ? cand_cap : host_nc;
     ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, s.kx, s.ky, s.kz,
                s.seg.cbucket, cand_cap, entry_cap);
-    ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, (u32) p.g.X + 2, n_big,
+    ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg, stream));
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,

@@ -80,27 +80,38 @@ static __global__ void __launch_bounds__(256) k_seg_count(const u32 *__restrict_
     }
 }
 
-// Executed by ONE block (any blockDim that is a multiple of 32, <= 1024): exclusive scan over nb buckets;
-// big buckets (> SEG_CAP) also get offsets in the compacted big list.  `count` is read with L2 loads
-// (it was produced by atomics of other blocks).
+// Executed by ONE block (any blockDim that is a multiple of 32, <= 1024): exclusive scan over nb buckets
+// (SS_ITEMS consecutive buckets per thread); big buckets (> SEG_CAP) also get offsets in the compacted big
+// list.  `count` is read with L2 loads (it was produced by atomics of other blocks).
+constexpr int SS_ITEMS = 16;
 __device__ __forceinline__ void seg_scan_block(u32 nb, const u32 *__restrict__ count, u32 *__restrict__ start, u32 *__restrict__ cursor,
                                                u32 *__restrict__ bigoff, u32 *__restrict__ info_nbig, u32 *__restrict__ info_max,
                                                u32 *sw /* >= 33 */, u32 *s4 /* >= 4 */) {
     if (threadIdx.x == 0) { s4[0] = 0; s4[1] = 0; s4[2] = 0; }
     __syncthreads();
-    for (u32 base = 0; base < nb; base += blockDim.x) {
-        const u32 b = base + threadIdx.x;
-        const u32 c = b < nb ? __ldcg(count + b) : 0u;
-        const u32 cb = c > (u32) SEG_CAP ? c : 0u;
-        u32 tot, totb;
-        const u32 ex = block_exclusive_scan(c, &tot, sw);
-        const u32 exb = block_exclusive_scan(cb, &totb, sw);
-        if (b < nb) {
-            start[b] = s4[0] + ex;
-            cursor[b] = 0;
-            bigoff[b] = s4[1] + exb;
-            if (c) atomicMax(&s4[2], c);
+    for (u32 base = 0; base < nb; base += blockDim.x * SS_ITEMS) {
+        const u32 b0 = base + threadIdx.x * SS_ITEMS;
+        u32 c[SS_ITEMS], sum = 0, sumb = 0, mx = 0;
+#pragma unroll
+        for (int j = 0; j < SS_ITEMS; j++) {
+            c[j] = b0 + j < nb ? __ldcg(count + b0 + j) : 0u;
+            sum += c[j];
+            sumb += c[j] > (u32) SEG_CAP ? c[j] : 0u;
+            mx = c[j] > mx ? c[j] : mx;
         }
+        u32 tot, totb;
+        u32 ex = block_exclusive_scan(sum, &tot, sw) + s4[0];
+        u32 exb = block_exclusive_scan(sumb, &totb, sw) + s4[1];
+#pragma unroll
+        for (int j = 0; j < SS_ITEMS; j++)
+            if (b0 + j < nb) {
+                start[b0 + j] = ex;
+                cursor[b0 + j] = 0;
+                bigoff[b0 + j] = exb;
+                ex += c[j];
+                exb += c[j] > (u32) SEG_CAP ? c[j] : 0u;
+            }
+        if (mx) atomicMax(&s4[2], mx);
         __syncthreads();
         if (threadIdx.x == 0) { s4[0] += tot; s4[1] += totb; }
         __syncthreads();
@@ -146,156 +157,194 @@ __device__ __forceinline__ bool key_less(u32 ax, u32 ay, u32 az, u32 bx, u32 by,
     return ax < bx || (ax == bx && (ay < by || (ay == by && az < bz)));
 }
 
-// One block per bucket: LSD radix sort (8-bit digits) entirely in shared memory.
-//   keys stay in place (sk[3][SEG_CAP]); only 16-bit local indices move (ord ping-pong);
+// One block per bucket (block-stride loop): LSD radix sort (8-bit digits) entirely in shared memory.
+//   keys stay in place (sk[3][CAP]); only 16-bit local indices move (ord ping-pong);
 //   ranking is stable: each warp owns a contiguous run of positions, ranks 32 of them at a time with
 //   match_any against its private digit counters, then a (digit, warp) exclusive scan gives the bases;
 //   digit places on which all keys of the bucket agree (typically the high bytes of x) are skipped.
-// Shared memory: 3*16 KB keys + 16 KB ids + 16 KB ord + 16 KB counters = 96 KB (dynamic).
-constexpr int SEG_WARPS = SEG_THREADS / 32;
-constexpr int SEG_CHUNKS = SEG_CAP / SEG_THREADS;          // 32-element chunks per warp at full capacity
-constexpr size_t SEG_SMEM = (size_t) SEG_CAP * 4 * 4       // sk[3] + ids
-                            + (size_t) SEG_CAP * 2 * 2     // ord[2] (u16)
-                            + (size_t) SEG_WARPS * 256 * 4 // cnt
-                            + (256 + 64) * 4;              // digit bases + vary + scan scratch
+// Two instances: <SEG_CAP, 512> (96 KB, 2 blocks/SM) for buckets of SEG_SMALL+1 .. SEG_CAP elements and
+// <SEG_SMALL, 128> (25 KB, 8 blocks/SM) for the small buckets, which are the common case: a pass costs a
+// handful of block barriers whatever the bucket size, so many small blocks in flight hide them.
+constexpr int SEG_SMALL = 1024;
+template <int CAP, int THREADS>
+struct SegCfg {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int CHUNKS = CAP / THREADS;          // 32-element chunks per warp at full capacity
+    static constexpr size_t SMEM = (size_t) CAP * 4 * 4       // sk[3] + ids
+                                   + (size_t) CAP * 2 * 2     // ord[2] (u16)
+                                   + (size_t) WARPS * 256 * 4 // cnt
+                                   + (256 + 64) * 4;          // digit bases + vary + scan scratch
+};
 
-static __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
-                                                                 const u32 *__restrict__ kz, const u32 *__restrict__ count,
-                                                                 const u32 *__restrict__ start, const u32 *__restrict__ perm0,
-                                                                 u32 *__restrict__ perm, u32 *__restrict__ skx, u32 *__restrict__ sky,
-                                                                 u32 *__restrict__ skz, const u32 *__restrict__ n_dev, u32 n_cap) {
+template <int CAP, int THREADS, int MIN_N>
+static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
+                                                             const u32 *__restrict__ kz, const u32 *__restrict__ count,
+                                                             const u32 *__restrict__ start, const u32 *__restrict__ perm0,
+                                                             u32 *__restrict__ perm, u32 *__restrict__ skx, u32 *__restrict__ sky,
+                                                             u32 *__restrict__ skz, const u32 *__restrict__ n_dev, u32 n_cap, u32 nb) {
+    constexpr int WARPS = SegCfg<CAP, THREADS>::WARPS, CHUNKS = SegCfg<CAP, THREADS>::CHUNKS;
     extern __shared__ u32 smem[];
     if (n_dev && *n_dev > n_cap) return;
-    const u32 b = blockIdx.x;
-    const u32 n = count[b];
-    if (n == 0 || n > (u32) SEG_CAP) return;
-    const u32 s0 = start[b];
-    if (n == 1) {
-        if (threadIdx.x == 0) {
-            const u32 id = perm0[s0];
-            perm[s0] = id;
-            skx[s0] = kx[id]; sky[s0] = ky[id]; skz[s0] = kz[id];
-        }
-        return;
-    }
-    u32 *sk = smem;                                   // [3][SEG_CAP]: z, y, x keys (LSD order)
-    u32 *ids = smem + 3 * SEG_CAP;                    // [SEG_CAP]
-    unsigned short *ord = reinterpret_cast<unsigned short *>(smem + 4 * SEG_CAP);   // [2][SEG_CAP]
-    u32 *cnt = smem + 5 * SEG_CAP;                    // [SEG_WARPS][256]
-    u32 *dbase = cnt + SEG_WARPS * 256;               // [256]
+    u32 *sk = smem;                                   // [3][CAP]: z, y, x keys (LSD order)
+    u32 *ids = smem + 3 * CAP;                        // [CAP]
+    unsigned short *ord = reinterpret_cast<unsigned short *>(smem + 4 * CAP);   // [2][CAP]
+    u32 *cnt = smem + 5 * CAP;                        // [WARPS][256]
+    u32 *dbase = cnt + WARPS * 256;                   // [256]
     u32 *vary = dbase + 256;                          // [3] OR of (key ^ key[0]) per coordinate
     u32 *sw = vary + 4;                               // [33] scan scratch
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid < 3) vary[tid] = 0;
-    __syncthreads();
-    {
-        u32 vz = 0, vy = 0, vx = 0;
-        const u32 id0 = perm0[s0];
-        const u32 z0 = kz[id0], y0 = ky[id0], x0 = kx[id0];
-        for (u32 i = tid; i < n; i += SEG_THREADS) {
-            const u32 id = perm0[s0 + i];
-            const u32 z = kz[id], y = ky[id], x = kx[id];
-            sk[i] = z; sk[SEG_CAP + i] = y; sk[2 * SEG_CAP + i] = x;
-            ids[i] = id;
-            ord[i] = (unsigned short) i;
-            vz |= z ^ z0; vy |= y ^ y0; vx |= x ^ x0;
+    for (u32 b = blockIdx.x; b < nb; b += gridDim.x) {
+        const u32 n = count[b];
+        if (n < (u32) MIN_N || n > (u32) CAP) continue;
+        const u32 s0 = start[b];
+        if (n == 1) {
+            if (tid == 0) {
+                const u32 id = perm0[s0];
+                perm[s0] = id;
+                skx[s0] = kx[id]; sky[s0] = ky[id]; skz[s0] = kz[id];
+            }
+            continue;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            vz |= __shfl_xor_sync(0xffffffffu, vz, o);
-            vy |= __shfl_xor_sync(0xffffffffu, vy, o);
-            vx |= __shfl_xor_sync(0xffffffffu, vx, o);
-        }
-        if (lane == 0) { atomicOr(&vary[0], vz); atomicOr(&vary[1], vy); atomicOr(&vary[2], vx); }
-    }
-    __syncthreads();
-    // contiguous run of positions per warp, a multiple of 32
-    const u32 run = ((n + SEG_WARPS - 1) / SEG_WARPS + 31) & ~31u;
-    const u32 nchunks = run >> 5;                     // <= SEG_CHUNKS
-    const u32 wbase = warp * run;
-    u32 cur = 0;
-    for (int pass = 0; pass < 12; pass++) {
-        const u32 c = pass >> 2, shift = 8 * (pass & 3);
-        if (((vary[c] >> shift) & 255u) == 0) continue;   // all keys agree on this digit
-        const u32 *key = sk + c * SEG_CAP;
-        const unsigned short *oin = ord + cur * SEG_CAP;
-        unsigned short *oout = ord + (cur ^ 1) * SEG_CAP;
-        for (u32 i = tid; i < SEG_WARPS * 256; i += SEG_THREADS) cnt[i] = 0;
+        __syncthreads();   // shared memory of the previous bucket is free
+        if (tid < 3) vary[tid] = 0;
         __syncthreads();
-        u32 packed[SEG_CHUNKS];                       // li | digit << 16 | rank-in-warp << 24 .. (rank kept separately)
-        u32 rnk[SEG_CHUNKS];
+        {
+            u32 vz = 0, vy = 0, vx = 0;
+            const u32 id0 = perm0[s0];
+            const u32 z0 = kz[id0], y0 = ky[id0], x0 = kx[id0];
+            for (u32 i = tid; i < n; i += THREADS) {
+                const u32 id = perm0[s0 + i];
+                const u32 z = kz[id], y = ky[id], x = kx[id];
+                sk[i] = z; sk[CAP + i] = y; sk[2 * CAP + i] = x;
+                ids[i] = id;
+                ord[i] = (unsigned short) i;
+                vz |= z ^ z0; vy |= y ^ y0; vx |= x ^ x0;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                vz |= __shfl_xor_sync(0xffffffffu, vz, o);
+                vy |= __shfl_xor_sync(0xffffffffu, vy, o);
+                vx |= __shfl_xor_sync(0xffffffffu, vx, o);
+            }
+            if (lane == 0) { atomicOr(&vary[0], vz); atomicOr(&vary[1], vy); atomicOr(&vary[2], vx); }
+        }
+        __syncthreads();
+        // contiguous run of positions per warp, a multiple of 32
+        const u32 run = ((n + WARPS - 1) / WARPS + 31) & ~31u;
+        const u32 nchunks = run >> 5;                     // <= CHUNKS
+        const u32 wbase = warp * run;
+        u32 cur = 0;
+        for (int pass = 0; pass < 12; pass++) {
+            const u32 c = pass >> 2, shift = 8 * (pass & 3);
+            if (((vary[c] >> shift) & 255u) == 0) continue;   // all keys agree on this digit
+            const u32 *key = sk + c * CAP;
+            const unsigned short *oin = ord + cur * CAP;
+            unsigned short *oout = ord + (cur ^ 1) * CAP;
+            for (u32 i = tid; i < WARPS * 256; i += THREADS) cnt[i] = 0;
+            __syncthreads();
+            u32 packed[CHUNKS];                           // local index | digit << 16
+            u32 rnk[CHUNKS];
 #pragma unroll
-        for (int j = 0; j < SEG_CHUNKS; j++) {
-            packed[j] = 0xffffffffu;
-            rnk[j] = 0;
-            if ((u32) j < nchunks) {
-                const u32 i = wbase + j * 32 + lane;
-                const bool valid = i < n;
-                const u32 active = __ballot_sync(0xffffffffu, valid);
-                if (valid) {
-                    const u32 li = oin[i];
-                    const u32 d = (key[li] >> shift) & 255u;
-                    const u32 peers = __match_any_sync(active, d);
-                    const u32 leader = __ffs(peers) - 1;
-                    u32 old = 0;
-                    if (lane == leader) {
-                        old = cnt[warp * 256 + d];
-                        cnt[warp * 256 + d] = old + __popc(peers);
+            for (int j = 0; j < CHUNKS; j++) {
+                packed[j] = 0xffffffffu;
+                rnk[j] = 0;
+                if ((u32) j < nchunks) {
+                    const u32 i = wbase + j * 32 + lane;
+                    const bool valid = i < n;
+                    const u32 active = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        const u32 li = oin[i];
+                        const u32 d = (key[li] >> shift) & 255u;
+                        const u32 peers = __match_any_sync(active, d);
+                        const u32 leader = __ffs(peers) - 1;
+                        u32 old = 0;
+                        if (lane == leader) {
+                            old = cnt[warp * 256 + d];
+                            cnt[warp * 256 + d] = old + __popc(peers);
+                        }
+                        old = __shfl_sync(peers, old, leader);
+                        rnk[j] = old + __popc(peers & ((1u << lane) - 1u));
+                        packed[j] = li | (d << 16);
                     }
-                    old = __shfl_sync(peers, old, leader);
-                    rnk[j] = old + __popc(peers & ((1u << lane) - 1u));
-                    packed[j] = li | (d << 16);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
-        }
-        __syncthreads();
-        // digit totals over the warps (exclusive per warp), then exclusive scan over the 256 digits
-        u32 tot = 0;
-        if (tid < 256) {
+            __syncthreads();
+            // digit totals over the warps (exclusive per warp), then exclusive scan over the 256 digits
+            u32 ex;
+            if (THREADS >= 256) {
+                u32 tot = 0;
+                if (tid < 256) {
 #pragma unroll
-            for (int w = 0; w < SEG_WARPS; w++) {
-                const u32 t = cnt[w * 256 + tid];
-                cnt[w * 256 + tid] = tot;
-                tot += t;
-            }
-        }
-        u32 total;
-        const u32 ex = block_exclusive_scan(tot, &total, sw);
-        if (tid < 256) dbase[tid] = ex;
-        __syncthreads();
+                    for (int w = 0; w < WARPS; w++) {
+                        const u32 t = cnt[w * 256 + tid];
+                        cnt[w * 256 + tid] = tot;
+                        tot += t;
+                    }
+                }
+                u32 total;
+                ex = block_exclusive_scan(tot, &total, sw);
+                if (tid < 256) dbase[tid] = ex;
+            } else {
+                // fewer threads than digits: each thread owns 256/THREADS consecutive digits
+                constexpr int DPT = 256 / THREADS > 0 ? 256 / THREADS : 1;
+                u32 tots[DPT], sum = 0;
 #pragma unroll
-        for (int j = 0; j < SEG_CHUNKS; j++) {
-            if (packed[j] != 0xffffffffu) {
-                const u32 d = (packed[j] >> 16) & 255u;
-                oout[dbase[d] + cnt[warp * 256 + d] + rnk[j]] = (unsigned short) (packed[j] & 0xffffu);
+                for (int q = 0; q < DPT; q++) {
+                    const u32 d = tid * DPT + q;
+                    u32 tot = 0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++) {
+                        const u32 t = cnt[w * 256 + d];
+                        cnt[w * 256 + d] = tot;
+                        tot += t;
+                    }
+                    tots[q] = tot;
+                    sum += tot;
+                }
+                u32 total;
+                ex = block_exclusive_scan(sum, &total, sw);
+#pragma unroll
+                for (int q = 0; q < DPT; q++) {
+                    dbase[tid * DPT + q] = ex;
+                    ex += tots[q];
+                }
             }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < CHUNKS; j++) {
+                if (packed[j] != 0xffffffffu) {
+                    const u32 d = (packed[j] >> 16) & 255u;
+                    oout[dbase[d] + cnt[warp * 256 + d] + rnk[j]] = (unsigned short) (packed[j] & 0xffffu);
+                }
+            }
+            __syncthreads();
+            cur ^= 1;
         }
-        __syncthreads();
-        cur ^= 1;
-    }
-    const unsigned short *ofin = ord + cur * SEG_CAP;
-    for (u32 i = tid; i < n; i += SEG_THREADS) {
-        const u32 li = ofin[i];
-        perm[s0 + i] = ids[li];
-        skz[s0 + i] = sk[li]; sky[s0 + i] = sk[SEG_CAP + li]; skx[s0 + i] = sk[2 * SEG_CAP + li];
+        const unsigned short *ofin = ord + cur * CAP;
+        for (u32 i = tid; i < n; i += THREADS) {
+            const u32 li = ofin[i];
+            perm[s0 + i] = ids[li];
+            skz[s0 + i] = sk[li]; sky[s0 + i] = sk[CAP + li]; skx[s0 + i] = sk[2 * CAP + li];
+        }
     }
 }
 
 // ---- fallback for big buckets -------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) k_seg_big_gather(u32 nb, const u32 *__restrict__ count, const u32 *__restrict__ start,
+static __global__ void __launch_bounds__(256) k_seg_big_gather(u32 n, const u32 *__restrict__ n_dev, u32 n_cap,
+                                                               const u32 *__restrict__ count, const u32 *__restrict__ start,
                                                                const u32 *__restrict__ bigoff, const u32 *__restrict__ perm0,
+                                                               const u32 *__restrict__ cbucket,
                                                                const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                                const u32 *__restrict__ kz, u32 *__restrict__ bkx, u32 *__restrict__ bky,
                                                                u32 *__restrict__ bkz, u32 *__restrict__ bid) {
-    for (u32 b = blockIdx.y; b < nb; b += gridDim.y) {
-        const u32 n = count[b];
-        if (n <= (u32) SEG_CAP) continue;
-        const u32 s0 = start[b], o0 = bigoff[b];
-        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const u32 id = perm0[s0 + i];
-            bkx[o0 + i] = kx[id]; bky[o0 + i] = ky[id]; bkz[o0 + i] = kz[id]; bid[o0 + i] = id;
-        }
+    if (n_dev) n = *n_dev;
+    if (n > n_cap) return;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {   // position in the grouped list
+        const u32 id = perm0[i];
+        const u32 b = cbucket[id];
+        if (count[b] <= (u32) SEG_CAP) continue;
+        const u32 o = bigoff[b] + (i - start[b]);
+        bkx[o] = kx[id]; bky[o] = ky[id]; bkz[o] = kz[id]; bid[o] = id;
     }
 }
 // sorted rank r of the big list -> final position: the big list is ordered by bucket (x decides the bucket)
@@ -326,19 +375,24 @@ static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const
 static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const u32 *n_dev, u32 n_cap, u32 grid_n,
                                        u32 nb, u32 n_big, const u32 *nbig_dev, u32 big_cap, const SegHead &h, const SegScratch &b,
                                        cudaStream_t stream) {
+    constexpr size_t smem_big = SegCfg<SEG_CAP, SEG_THREADS>::SMEM, smem_small = SegCfg<SEG_SMALL, 128>::SMEM;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEG_SMEM);
+        cudaFuncSetAttribute(k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_big);
+        cudaFuncSetAttribute(k_seg_sort<SEG_SMALL, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_small);
         attr_set = true;
     }
     const int blocks = (int) ((grid_n + 255) / 256 > 148 * 8 ? 148 * 8 : (grid_n + 255) / 256);
     ISX_LAUNCH(k_seg_scatter, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap);
-    ISX_LAUNCH(k_seg_sort, nb, SEG_THREADS, SEG_SMEM, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm, b.skx, b.sky,
-               b.skz, n_dev, n_cap);
+    const u32 grid_small = nb < 148u * 32u ? nb : 148u * 32u, grid_large = nb < 148u * 8u ? nb : 148u * 8u;
+    ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
+               b.skx, b.sky, b.skz, n_dev, n_cap, nb);
+    ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>), grid_large, SEG_THREADS, smem_big, stream, kx, ky, kz, h.count,
+               h.start, b.perm0, b.perm, b.skx, b.sky, b.skz, n_dev, n_cap, nb);
     const u32 fb_n = nbig_dev ? big_cap : n_big;
     if (fb_n > 0) {
-        dim3 grid(32, nb < 1024 ? nb : 1024);
-        ISX_LAUNCH(k_seg_big_gather, grid, 256, 0, stream, nb, h.count, h.start, h.bigoff, b.perm0, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid);
+        ISX_LAUNCH(k_seg_big_gather, blocks < 1 ? 1 : blocks, 256, 0, stream, n, n_dev, n_cap, h.count, h.start, h.bigoff, b.perm0,
+                   b.cbucket, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid);
         cudaError_t e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, nbig_dev);
         if (e != cudaSuccess) return e;
         const int bb = (int) ((fb_n + 255) / 256 > 148 * 8 ? 148 * 8 : (fb_n + 255) / 256);

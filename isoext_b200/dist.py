@@ -15,11 +15,22 @@ The global (X, Y, Z) grid is cut along dim 0 (the slowest axis, so slabs are con
     neighbour can compute that vertex's global id locally from the all-gathered counts;
   * per-rank vertex and face lists concatenate (in rank order) to exactly the single-GPU result: V is
     sorted by x first and F is in ascending (x-major) cell order.
-Only counts cross ranks in the extraction step: one ``all_gather`` of two int64 per rank.
+Only counts cross ranks in the extraction step.
+
+Two transports.  On one node (the normal case: NVLink / NVSwitch) every rank exports its value slab and a
+small SYNC block through CUDA IPC and the two exchange steps are kernels of the library over peer memory
+(csrc/peer.cu): ``k_peer_pull`` waits for the neighbour's epoch flag and copies the halo planes straight out
+of the neighbour's slab; ``k_relabel_peer`` reads the lower ranks' vertex counts from their SYNC blocks, sums
+them and relabels the faces -- no host rendezvous, no NCCL call and no extra host synchronisation on the data
+path.  Otherwise (``ISOEXT_B200_PEER=0``, several nodes, gloo on CPU) the same steps run as NCCL/gloo
+``batch_isend_irecv`` of planes plus one ``all_gather`` of two int64 per rank.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
+import os
+import socket
 
 import torch
 import torch.distributed as dist
@@ -118,7 +129,14 @@ class SlabGrid:
         _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         X, Y, Z = self.shape
-        self._ext = torch.full((self.plan["n_ext"], Y, Z), float(default_value), dtype=torch.float32, device=self.device)
+        self._peer = None
+        want_peer = (rank is None and world is None and self.world > 1 and dist.is_initialized() and self.device.type == "cuda"
+                     and os.environ.get("ISOEXT_B200_PEER", "1") != "0")
+        if want_peer:
+            self._peer_setup((self.plan["n_ext"], Y, Z))
+        if self._peer is None:
+            self._ext = torch.empty((self.plan["n_ext"], Y, Z), dtype=torch.float32, device=self.device)
+        self._ext.fill_(float(default_value))
         self._ws = _Workspace()
         self._cap_hint = 0
         self._hints = {}
@@ -141,10 +159,128 @@ class SlabGrid:
         own = self.owned_values()
         if tuple(values.shape) != tuple(own.shape):
             raise RuntimeError("Cannot set values with different shapes")
+        self._guard_overwrite()
         own.copy_(values)
 
     def exchange_halos(self) -> None:
-        exchange_halos(self._ext, self.plan, self.rank, self.world, self.group)
+        if self._peer is not None:
+            self._peer_exchange()
+        else:
+            exchange_halos(self._ext, self.plan, self.rank, self.world, self.group)
+
+    # ---- NVLink peer transport (csrc/peer.cu) -------------------------------------------------------
+    def _peer_setup(self, ext_shape) -> None:
+        """Collective.  Allocate the value slab and the SYNC block as IPC-exportable memory, exchange the handles and
+        map the neighbours' slabs and everybody's SYNC block.  Leaves ``self._peer = None`` (NCCL transport) when the
+        ranks are not all on one host."""
+        from . import _lib
+        lib = _lib.lib()
+        n_floats = int(ext_shape[0]) * int(ext_shape[1]) * int(ext_shape[2])
+        words = int(lib.isoext_peer_sync_words())
+        hosts = [None] * self.world
+        dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
+        if len(set(hosts)) != 1:
+            return
+        with torch.cuda.device(self.device):
+            ext_ptr, sync_ptr = C.c_void_p(), C.c_void_p()
+            h_ext, h_sync = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+            _lib.check(lib.isoext_peer_alloc(n_floats * 4, C.byref(ext_ptr), h_ext))
+            _lib.check(lib.isoext_peer_alloc(words * 8, C.byref(sync_ptr), h_sync))
+            self._ext = _device_view(ext_ptr.value, n_floats, torch.float32, self.device).view(ext_shape)
+            sync = _device_view(sync_ptr.value, words, torch.int64, self.device)
+            sync.zero_()
+            torch.cuda.synchronize()
+            allh = [None] * self.world
+            dist.all_gather_object(allh, (bytes(h_ext), bytes(h_sync)), group=self.group)
+            peer_ext, peer_sync = {}, {}
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                _lib.check(lib.isoext_peer_open((C.c_ubyte * 64).from_buffer_copy(allh[r][1]), C.byref(p)))
+                peer_sync[r] = p.value
+                if abs(r - self.rank) == 1:
+                    p = C.c_void_p()
+                    _lib.check(lib.isoext_peer_open((C.c_ubyte * 64).from_buffer_copy(allh[r][0]), C.byref(p)))
+                    peer_ext[r] = p.value
+        err = torch.zeros(1, dtype=torch.int32).pin_memory()     # written by the kernels on a wait timeout
+        sync_ptrs = (C.c_void_p * 32)(*[peer_sync.get(r) for r in range(min(self.world, 32))])
+        self._peer = dict(ext_ptr=ext_ptr.value, sync_ptr=sync_ptr.value, sync=sync, peer_ext=peer_ext, peer_sync=peer_sync,
+                          sync_ptrs=sync_ptrs, err=err, epoch=0, counts_epoch=0)
+
+    def _peer_check(self) -> None:
+        if self._peer is not None and int(self._peer["err"][0]) != 0:
+            raise RuntimeError("isoext_b200.dist: timed out waiting for a peer rank (NVLink peer transport)")
+
+    def _guard_overwrite(self) -> None:
+        """Before the owned planes are overwritten the neighbours must have pulled their halos of the last exchange."""
+        pr = self._peer
+        if pr is None or pr["epoch"] == 0:
+            return
+        from . import _lib
+        from .grid import _stream_ptr
+        done = [pr["peer_sync"][r] + 8 if r in pr["peer_ext"] else None for r in (self.rank - 1, self.rank + 1)]
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().isoext_peer_wait(done[0], done[1], pr["epoch"], pr["err"].data_ptr(), _stream_ptr()))
+
+    def _peer_exchange(self) -> None:
+        from . import _lib
+        from .grid import _stream_ptr
+        lib, pr, p = _lib.lib(), self._peer, self.plan
+        X, Y, Z = self.shape
+        plane = Y * Z
+        self._peer_check()
+        pr["epoch"] += 1
+        e = pr["epoch"]
+        base = self._ext.data_ptr()
+        seg = [(None, None, 0, None), (None, None, 0, None)]
+        if self.rank > 0:
+            q = slab_plan(X, self.rank - 1, self.world)
+            src = pr["peer_ext"][self.rank - 1] + (p["halo_below"] - q["ext_lo"]) * plane * 4
+            seg[0] = (base + (p["halo_below"] - p["ext_lo"]) * plane * 4, src, plane, pr["peer_sync"][self.rank - 1])
+        if self.rank < self.world - 1 and p["halo_above"]:
+            q = slab_plan(X, self.rank + 1, self.world)
+            g0 = p["halo_above"][0]
+            src = pr["peer_ext"][self.rank + 1] + (g0 - q["ext_lo"]) * plane * 4
+            seg[1] = (base + (g0 - p["ext_lo"]) * plane * 4, src, plane * len(p["halo_above"]), pr["peer_sync"][self.rank + 1])
+        with torch.cuda.device(self.device):
+            st = _stream_ptr()
+            _lib.check(lib.isoext_peer_publish(pr["sync_ptr"], e, st))                        # my values of epoch e are in place
+            _lib.check(lib.isoext_peer_halo_pull(seg[0][0], seg[0][1], seg[0][2], seg[0][3], seg[1][0], seg[1][1], seg[1][2],
+                                                 seg[1][3], e, pr["err"].data_ptr(), st))
+            _lib.check(lib.isoext_peer_publish(pr["sync_ptr"] + 8, e, st))                    # I have pulled: neighbours may overwrite
+
+    def close(self) -> None:
+        """Collective: unmap the peers' memory and free the exported allocations."""
+        pr, self._peer = self._peer, None
+        if pr is None:
+            return
+        from . import _lib
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for ptr in list(pr["peer_ext"].values()) + list(pr["peer_sync"].values()):
+                lib.isoext_peer_close(ptr)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            self._ext = torch.empty(0, dtype=torch.float32, device=self.device)
+            pr["sync"] = None
+            lib.isoext_peer_free(pr["ext_ptr"])
+            lib.isoext_peer_free(pr["sync_ptr"])
+
+
+class _RawDevice:
+    """Zero-copy torch view of a raw device allocation (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _device_view(ptr: int, n: int, dtype, device) -> torch.Tensor:
+    typestr = {torch.float32: "<f4", torch.int64: "<i8"}[dtype]
+    return torch.as_tensor(_RawDevice(ptr, n, typestr), device=device)
 
 
 def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae"):
@@ -183,9 +319,30 @@ def marching_cubes(sg: SlabGrid, level: float = 0.0, method: str = "nagae", exch
     if exchange:
         sg.exchange_halos()
     v_own, f, n_lo, n_hi = marching_cubes_local(sg, level, method)
+    globalize_faces_(sg, f, n_lo, n_hi, peer=exchange)
+    return v_own, f
+
+
+def globalize_faces_(sg: SlabGrid, f: torch.Tensor, n_lo: int, n_hi: int, peer: bool = True) -> None:
+    """The cross-rank step after the local extraction (collective): local vertex ids in ``f`` -> global ids.
+
+    Peer transport (only right after a peer halo exchange of the same call, whose epoch tags the counts): publish
+    this rank's counts in its SYNC block and let the relabel kernel sum the lower ranks' counts over NVLink.
+    Otherwise: ``all_gather`` of the counts + the plain relabel kernel."""
+    pr = sg._peer
+    if pr is not None and peer:
+        from . import _lib
+        from .grid import _stream_ptr
+        lib = _lib.lib()
+        sg._peer_check()          # the local extraction synchronised the stream: a pull timeout is visible now
+        with torch.cuda.device(sg.device):
+            st = _stream_ptr()
+            _lib.check(lib.isoext_peer_publish_counts(pr["sync_ptr"], pr["epoch"], n_hi - n_lo, int(f.shape[0]), st))
+            _lib.check(lib.isoext_relabel_faces_peer(f.data_ptr(), f.numel(), n_lo, n_hi, n_hi - n_lo, pr["sync_ptrs"], sg.rank,
+                                                     pr["epoch"], None, pr["err"].data_ptr(), st))
+        return
     vb, fb, totals, _ = global_bases(n_hi - n_lo, int(f.shape[0]), sg.device, sg.group)
     relabel_faces_(f, n_lo, n_hi, vb, vb + (n_hi - n_lo))
-    return v_own, f
 
 
 def gather_mesh(v_own: torch.Tensor, f_own: torch.Tensor, group=None):

@@ -3,7 +3,8 @@
 * simulated ranks on ONE GPU (always runs): every rank's slab is extracted in turn with the real CUDA
   kernels (x_offset / emit range / position thresholds), parts are relabelled with the CUDA kernel and
   concatenated: must equal the single-GPU mesh bit for bit;
-* real ranks over NCCL (needs >= 2 GPUs, else skipped): halo send/recv + count all_gather."""
+* real ranks, one process per GPU (needs >= 2 GPUs, else skipped): the NVLink peer transport (halo pull and
+  count exchange as kernels over IPC-mapped peer memory) and the NCCL fallback (send/recv + all_gather)."""
 import os
 
 import numpy as np
@@ -50,8 +51,8 @@ def test_simulated_ranks_concatenate_to_single_gpu_mesh(iso, name, world, method
     assert torch.equal(f, gf)
 
 
-def _nccl_worker(rank, world, port, shape, field_name):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _nccl_worker(rank, world, port, transport, field_name):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ISOEXT_B200_PEER="1" if transport == "peer" else "0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -59,22 +60,36 @@ def _nccl_worker(rank, world, port, shape, field_name):
         from isoext_b200 import dist as idist
         vals = FIELDS[field_name]().cuda()
         sg = idist.SlabGrid(list(vals.shape))
+        assert (sg._peer is not None) == (transport == "peer")
         lo, hi = sg.owned_point_range()
-        sg.set_owned_values(vals[lo:hi].contiguous())
-        v_own, f_own = idist.marching_cubes(sg)
-        v, f = idist.gather_mesh(v_own, f_own)
         g = iso.UniformGrid(list(vals.shape))
-        g.set_values(vals)
-        gv, gf = iso.marching_cubes(g)
-        assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf), f"rank {rank}: mismatch"
+        # several steps with changing values: epochs, the overwrite guard and the count ring all advance
+        for step, (scale, level) in enumerate([(1.0, 0.0), (-1.0, 0.0), (1.0, 0.03), (0.5, 0.01), (1.0, 5.0)]):
+            cur = (vals * scale).contiguous()
+            sg.set_owned_values(cur[lo:hi].contiguous())
+            v_own, f_own = idist.marching_cubes(sg, level)
+            v, f = idist.gather_mesh(v_own, f_own)
+            g.set_values(cur)
+            gv, gf = iso.marching_cubes(g, level)
+            if gv is None:
+                assert len(v) == 0 and len(f) == 0, f"rank {rank} step {step}: expected an empty mesh"
+                continue
+            assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf), f"rank {rank} step {step}: mismatch"
+        # same values again without a new set_owned_values, and the explicit no-exchange variant
+        v_own, f_own = idist.marching_cubes(sg, 0.0)
+        v2_own, f2_own = idist.marching_cubes(sg, 0.0, exchange=False)
+        assert torch.equal(v_own, v2_own) and torch.equal(f_own, f2_own)
+        sg.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("field_name", ["cuboid65_faces_on_slab_planes", "torus_96x64x128"])
-def test_real_ranks_over_nccl(field_name):
+def test_real_ranks(field_name, transport):
+    """Real ranks, one process per GPU: NVLink peer transport (csrc/peer.cu) and the NCCL fallback."""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(n, 4)
-    mp.spawn(_nccl_worker, args=(world, 29610, None, field_name), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, 29610 + (1 if transport == "peer" else 0), transport, field_name), nprocs=world, join=True)
