@@ -13,7 +13,10 @@
 //   k_seg_scan     exclusive scan of the histogram (one block), big-bucket bookkeeping
 //   k_seg_scatter  group candidate ids by bucket (order inside a bucket is irrelevant: it is sorted next)
 //   k_seg_sort     one block per bucket: load keys, bitonic sort in smem, write sorted ids
-//   (fallback)     k_seg_big_gather -> radix_sort96 -> k_seg_big_scatter
+//   (oversized)    k_seg_big_gather -> k_big_plan -> k_big_sub -> k_seg_scan -> k_seg_scatter -> k_seg_sort:
+//                  a second level of buckets inside every oversized bucket (an axis-aligned face: nearly all
+//                  vertices share one x, so cut that value by y-plane and the rest of the x range uniformly)
+//   (last resort)  radix_sort96 over the oversized buckets if a second-level bucket is still too large
 // 4 launches instead of 14 in the common case.
 #pragma once
 #include "common.cuh"
@@ -30,13 +33,23 @@ struct SegHead {
     u32 *start;      // nb + 1
     u32 *cursor;     // nb + 1
     u32 *bigoff;     // nb + 1   (offset of a big bucket inside the compacted big list)
-    static size_t words(size_t nb) { return 4 * (nb + 1); }
+    u32 *xinvmin;    // nb + 1   max of ~xkey over a big bucket (zero-initialised, so a max)
+    u32 *xmax;       // nb + 1   max of xkey over a big bucket
+    u32 *sub_base;   // nb + 1   first second-level bucket of a big bucket
+    u32 *sub_par;    // nb + 1   how finely a big bucket is cut (k_big_plan)
+    u32 *sub_xm;     // nb + 1   the dominant x key of a big bucket
+    static size_t words(size_t nb) { return 9 * (nb + 1); }
     static void carve(Carver &c, size_t nb, SegHead *out) {
         SegHead h;
         h.count = c.take<u32>(words(nb));
         h.start = h.count + (nb + 1);
         h.cursor = h.start + (nb + 1);
         h.bigoff = h.cursor + (nb + 1);
+        h.xinvmin = h.bigoff + (nb + 1);
+        h.xmax = h.xinvmin + (nb + 1);
+        h.sub_base = h.xmax + (nb + 1);
+        h.sub_par = h.sub_base + (nb + 1);
+        h.sub_xm = h.sub_par + (nb + 1);
         if (out) *out = h;
     }
 };
@@ -46,8 +59,13 @@ struct SegScratch {
     u32 *perm0;      // n   ids grouped by bucket
     u32 *perm;       // n   ids in final sorted order
     u32 *skx, *sky, *skz;         // n   keys in final sorted order (so that the weld pass reads sequentially)
-    u32 *bkx, *bky, *bkz, *bid;   // fallback: compacted keys / ids of the big buckets
+    u32 *bkx, *bky, *bkz, *bid;   // compacted keys / ids of the big buckets
+    u32 *csub, *perm2;            // second level: bucket of every big-list element, big-list ids grouped by it
+    u32 *info2;                   // [8]: 0 second-level buckets, 1 elements in oversized ones, 2 largest, 3 overflow, 4 radix count, 5 no level 2, 6 abort
+    u32 *count2;                  // 4 * (subcap + 1): count / start / cursor / bigoff of the second-level buckets
+    u32 subcap;
     RadixBuffers radix;
+    static u32 sub_capacity(size_t n) { return (u32) (n / 64 + 64); }   // k_big_plan: nsub <= 3 * count / 512 per big bucket
     static void carve(Carver &c, size_t n, SegScratch *out) {
         SegScratch b;
         b.cbucket = c.take<u32>(n);
@@ -60,6 +78,11 @@ struct SegScratch {
         b.bky = c.take<u32>(n);
         b.bkz = c.take<u32>(n);
         b.bid = c.take<u32>(n);
+        b.csub = c.take<u32>(n);
+        b.perm2 = c.take<u32>(n);
+        b.subcap = sub_capacity(n);
+        b.info2 = c.take<u32>(8 + 4 * ((size_t) b.subcap + 1));   // info2 and count2 are cleared by one memset
+        b.count2 = b.info2 + 8;
         RadixBuffers::carve(c, n, &b.radix);
         if (out) *out = b;
     }
@@ -125,15 +148,18 @@ __device__ __forceinline__ void seg_scan_block(u32 nb, const u32 *__restrict__ c
 
 static __global__ void __launch_bounds__(1024) k_seg_scan(u32 nb, const u32 *__restrict__ count, u32 *__restrict__ start,
                                                            u32 *__restrict__ cursor, u32 *__restrict__ bigoff, u32 *__restrict__ info_nbig,
-                                                           u32 *__restrict__ info_max) {
+                                                           u32 *__restrict__ info_max, const u32 *__restrict__ nb_dev = nullptr) {
     __shared__ u32 sw[33];
     __shared__ u32 s4[4];
+    if (nb_dev && *nb_dev < nb) nb = *nb_dev;   // buckets in use (the rest of the table is empty)
     seg_scan_block(nb, count, start, cursor, bigoff, info_nbig, info_max, sw, s4);
 }
 
 static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restrict__ cbucket, u32 n, const u32 *__restrict__ start,
                                                             u32 *__restrict__ cursor, u32 *__restrict__ perm0,
-                                                            const u32 *__restrict__ n_dev, u32 n_cap) {
+                                                            const u32 *__restrict__ n_dev, u32 n_cap,
+                                                            const u32 *__restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     if (n_dev) n = *n_dev;
     if (n > n_cap) return;
     const u32 lane = threadIdx.x & 31;
@@ -176,15 +202,26 @@ struct SegCfg {
                                    + (256 + 64) * 4;          // digit bases + vary + scan scratch
 };
 
-template <int CAP, int THREADS, int MIN_N>
+// second level (k_seg_sort<.., true>): the "candidates" are positions of the big list (keys bk*, ids bid) and the
+// sorted run of a bucket goes to its place inside the first-level bucket it belongs to
+struct SegLevel2 {
+    const u32 *bid, *cbucket, *start1, *bigoff1, *skip, *nb_dev;
+};
+
+template <int CAP, int THREADS, int MIN_N, bool LEVEL2 = false>
 static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                              const u32 *__restrict__ kz, const u32 *__restrict__ count,
                                                              const u32 *__restrict__ start, const u32 *__restrict__ perm0,
                                                              u32 *__restrict__ perm, u32 *__restrict__ skx, u32 *__restrict__ sky,
-                                                             u32 *__restrict__ skz, const u32 *__restrict__ n_dev, u32 n_cap, u32 nb) {
+                                                             u32 *__restrict__ skz, const u32 *__restrict__ n_dev, u32 n_cap, u32 nb,
+                                                             SegLevel2 l2 = SegLevel2{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}) {
     constexpr int WARPS = SegCfg<CAP, THREADS>::WARPS, CHUNKS = SegCfg<CAP, THREADS>::CHUNKS;
     extern __shared__ u32 smem[];
     if (n_dev && *n_dev > n_cap) return;
+    if (LEVEL2) {
+        if (*l2.skip) return;
+        if (*l2.nb_dev < nb) nb = *l2.nb_dev;   // second-level buckets in use
+    }
     u32 *sk = smem;                                   // [3][CAP]: z, y, x keys (LSD order)
     u32 *ids = smem + 3 * CAP;                        // [CAP]
     unsigned short *ord = reinterpret_cast<unsigned short *>(smem + 4 * CAP);   // [2][CAP]
@@ -197,11 +234,16 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
         const u32 n = count[b];
         if (n < (u32) MIN_N || n > (u32) CAP) continue;
         const u32 s0 = start[b];
+        u32 o0 = s0;                                   // where the sorted run goes
+        if (LEVEL2) {
+            const u32 b1 = l2.cbucket[l2.bid[perm0[s0]]];
+            o0 = l2.start1[b1] + (s0 - l2.bigoff1[b1]);
+        }
         if (n == 1) {
             if (tid == 0) {
                 const u32 id = perm0[s0];
-                perm[s0] = id;
-                skx[s0] = kx[id]; sky[s0] = ky[id]; skz[s0] = kz[id];
+                perm[o0] = LEVEL2 ? l2.bid[id] : id;
+                skx[o0] = kx[id]; sky[o0] = ky[id]; skz[o0] = kz[id];
             }
             continue;
         }
@@ -323,8 +365,8 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
         const unsigned short *ofin = ord + cur * CAP;
         for (u32 i = tid; i < n; i += THREADS) {
             const u32 li = ofin[i];
-            perm[s0 + i] = ids[li];
-            skz[s0 + i] = sk[li]; sky[s0 + i] = sk[CAP + li]; skx[s0 + i] = sk[2 * CAP + li];
+            perm[o0 + i] = LEVEL2 ? l2.bid[ids[li]] : ids[li];
+            skz[o0 + i] = sk[li]; sky[o0 + i] = sk[CAP + li]; skx[o0 + i] = sk[2 * CAP + li];
         }
     }
 }
@@ -336,16 +378,165 @@ static __global__ void __launch_bounds__(256) k_seg_big_gather(u32 n, const u32 
                                                                const u32 *__restrict__ cbucket,
                                                                const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                                const u32 *__restrict__ kz, u32 *__restrict__ bkx, u32 *__restrict__ bky,
-                                                               u32 *__restrict__ bkz, u32 *__restrict__ bid) {
+                                                               u32 *__restrict__ bkz, u32 *__restrict__ bid, u32 *__restrict__ xinvmin,
+                                                               u32 *__restrict__ xmax) {
     if (n_dev) n = *n_dev;
     if (n > n_cap) return;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {   // position in the grouped list
-        const u32 id = perm0[i];
-        const u32 b = cbucket[id];
-        if (count[b] <= (u32) SEG_CAP) continue;
-        const u32 o = bigoff[b] + (i - start[b]);
-        bkx[o] = kx[id]; bky[o] = ky[id]; bkz[o] = kz[id]; bid[o] = id;
+    const u32 lane = threadIdx.x & 31;
+    constexpr int G = 4;   // independent load chains per thread (perm0 -> cbucket -> count)
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += G * stride) {
+        u32 id[G], bb[G], cc[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const u32 i = base + k * stride + lane;
+            id[k] = i < n ? perm0[i] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < G; k++) bb[k] = id[k] != 0xffffffffu ? cbucket[id[k]] : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < G; k++) cc[k] = bb[k] != 0xffffffffu ? count[bb[k]] : 0u;
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const u32 i = base + k * stride + lane;     // position in the grouped list
+            u32 b = 0xffffffffu, x = 0;
+            if (cc[k] > (u32) SEG_CAP) {
+                b = bb[k];
+                x = kx[id[k]];
+                const u32 o = bigoff[b] + (i - start[b]);
+                bkx[o] = x; bky[o] = ky[id[k]]; bkz[o] = kz[id[k]]; bid[o] = id[k];
+            }
+            // x range of every big bucket (the grouped list keeps a bucket contiguous: a warp sees one or two)
+            const u32 peers = __match_any_sync(0xffffffffu, b);
+            if (b != 0xffffffffu) {
+                const u32 mx = __reduce_max_sync(peers, x), mn = __reduce_max_sync(peers, ~x);
+                if (lane == (u32) (__ffs(peers) - 1)) {
+                    atomicMax(&xmax[b], mx);
+                    atomicMax(&xinvmin[b], mn);
+                }
+            }
+        }
     }
+}
+
+__host__ __device__ __forceinline__ u32 pow2ceil_u32(u32 v) {
+    u32 p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// One block: decide how every oversized bucket is cut and where its second-level buckets start.
+// An oversized bucket is almost always an axis-aligned face: nearly all its vertices share ONE x value xm (found
+// by majority vote over 32 samples), the rest is rounding noise and bystanders of the same layer.  Cut:
+//     x <  xm : w pieces, uniform in the key range [xmin, xm)
+//     x == xm : gy2 pieces by y-plane index (x is constant here, so y decides)
+//     x >  xm : w pieces, uniform in (xm, xmax]
+// with w = count / 1024 rounded up to a power of two.  Monotone in the lexicographic key order, so sorting the
+// pieces sorts the bucket; a slanted sheet (no dominant x) is spread by the two uniform ranges.
+static __global__ void __launch_bounds__(1024) k_big_plan(u32 nb, const u32 *__restrict__ count, const u32 *__restrict__ bigoff,
+                                                          const u32 *__restrict__ bkx, u32 *__restrict__ sub_base,
+                                                          u32 *__restrict__ sub_par, u32 *__restrict__ sub_xm, u32 Y, u32 subcap,
+                                                          u32 *__restrict__ info2, const u32 *__restrict__ n_dev, u32 n_cap) {
+    __shared__ u32 sw[33];
+    __shared__ u32 s_run;
+    const bool abort = n_dev && *n_dev > n_cap;   // the candidate buffers were too small: nothing valid to sort
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (u32 base = 0; base < nb; base += blockDim.x) {
+        const u32 b = base + threadIdx.x;
+        u32 nsub = 0, w = 0, xm = 0;
+        if (b < nb && !abort) {
+            const u32 c = __ldcg(count + b);
+            if (c > (u32) SEG_CAP) {
+                w = pow2ceil_u32((c + 1023u) / 1024u);
+                if (w > 4096u) w = 4096u;
+                const u32 o = bigoff[b], step = c / 32u;
+                u32 xs[32], best = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) xs[i] = bkx[o + (u32) i * step];
+#pragma unroll
+                for (int i = 0; i < 32; i++) {        // majority vote over 32 samples
+                    u32 votes = 0;
+#pragma unroll
+                    for (int k = 0; k < 32; k++) votes += xs[k] == xs[i] ? 1u : 0u;
+                    if (votes > best) { best = votes; xm = xs[i]; }
+                }
+                const u32 gy2 = w > pow2ceil_u32(Y) ? pow2ceil_u32(Y) : w;
+                nsub = 2 * w + gy2;
+            }
+        }
+        u32 tot;
+        const u32 ex = block_exclusive_scan(nsub, &tot, sw);
+        if (b < nb) {
+            sub_base[b] = s_run + ex;
+            sub_par[b] = w;
+            sub_xm[b] = xm;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        info2[0] = s_run;
+        info2[3] = s_run > subcap ? 1u : 0u;          // cannot be represented: the radix sort takes over
+        info2[5] = (abort || s_run > subcap) ? 1u : 0u;   // no second level
+        info2[6] = abort ? 1u : 0u;
+    }
+}
+
+struct SegGeom {   // what the second level needs to know about the grid: y-plane positions
+    float amin_y, asize_y;
+    u32 Y;
+};
+// index of the last y plane at or below y (0 if y is below all planes): exact float compares, monotone in y
+__device__ __forceinline__ u32 yplane_of(float y, const SegGeom &g) {
+    const u32 res = g.Y - 1;
+    float f = __fdiv_rn(__fsub_rn(y, g.amin_y), g.asize_y) * (float) res;
+    int j = f > 0.f ? (f < (float) res ? (int) f : (int) res) : 0;
+    while (j > 0 && axis_pos((u32) j, res, g.amin_y, g.asize_y) > y) j--;
+    while (j < (int) res && axis_pos((u32) j + 1, res, g.amin_y, g.asize_y) <= y) j++;
+    return (u32) j;
+}
+
+static __global__ void __launch_bounds__(256) k_big_sub(u32 n_big, const u32 *__restrict__ nbig_dev, const u32 *__restrict__ bkx,
+                                                        const u32 *__restrict__ bky, const u32 *__restrict__ bid,
+                                                        const u32 *__restrict__ cbucket, const u32 *__restrict__ xinvmin,
+                                                        const u32 *__restrict__ xmax, const u32 *__restrict__ sub_base,
+                                                        const u32 *__restrict__ sub_par, const u32 *__restrict__ sub_xm, SegGeom g,
+                                                        u32 *__restrict__ csub, u32 *__restrict__ count2, const u32 *__restrict__ info2) {
+    if (nbig_dev) n_big = *nbig_dev;
+    if (info2[5]) return;
+    const u32 lane = threadIdx.x & 31;
+    const u32 ypow = pow2ceil_u32(g.Y);
+    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_big; base += gridDim.x * blockDim.x) {
+        const u32 j = base + lane;
+        const bool valid = j < n_big;
+        const u32 active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const u32 b = cbucket[bid[j]];
+            const u32 w = sub_par[b], xm = sub_xm[b], x = bkx[j];
+            const u32 gy2 = w > ypow ? ypow : w;
+            u32 sub;
+            if (x < xm) {
+                const u32 xmin = ~xinvmin[b];
+                sub = (u32) (((u64) (x - xmin) * w) / (u64) (xm - xmin));
+            } else if (x == xm) {
+                sub = w + (u32) (((u64) yplane_of(key_float(bky[j]), g) * gy2) / g.Y);
+            } else {
+                sub = w + gy2 + (u32) (((u64) (x - xm - 1u) * w) / (u64) (xmax[b] - xm));
+            }
+            const u32 cs = sub_base[b] + sub;
+            csub[j] = cs;
+            const u32 peers = __match_any_sync(active, cs);
+            if (lane == (u32) (__ffs(peers) - 1)) atomicAdd(&count2[cs], (u32) __popc(peers));
+        }
+    }
+}
+
+// after the second-level scan: does the radix sort have to take over?  info2[4] = number of elements it sorts
+static __global__ void k_big_decide(u32 n_big, const u32 *__restrict__ nbig_dev, u32 *__restrict__ info2) {
+    if (nbig_dev) n_big = *nbig_dev;
+    info2[4] = info2[6] ? 0u : ((info2[3] || info2[2] > (u32) SEG_CAP) ? n_big : 0u);
 }
 // sorted rank r of the big list -> final position: the big list is ordered by bucket (x decides the bucket)
 static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const u32 *__restrict__ nbig_dev, const u32 *__restrict__ sorted,
@@ -374,12 +565,14 @@ static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const
 //                    big_cap > 0 (the caller's guess) and does nothing when the device count is 0
 static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const u32 *n_dev, u32 n_cap, u32 grid_n,
                                        u32 nb, u32 n_big, const u32 *nbig_dev, u32 big_cap, const SegHead &h, const SegScratch &b,
-                                       cudaStream_t stream) {
+                                       const SegGeom &geom, cudaStream_t stream) {
     constexpr size_t smem_big = SegCfg<SEG_CAP, SEG_THREADS>::SMEM, smem_small = SegCfg<SEG_SMALL, 128>::SMEM;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_big);
         cudaFuncSetAttribute(k_seg_sort<SEG_SMALL, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_small);
+        cudaFuncSetAttribute(k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_big);
+        cudaFuncSetAttribute(k_seg_sort<SEG_SMALL, 128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_small);
         attr_set = true;
     }
     const int blocks = (int) ((grid_n + 255) / 256 > 148 * 8 ? 148 * 8 : (grid_n + 255) / 256);
@@ -391,12 +584,31 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
                h.start, b.perm0, b.perm, b.skx, b.sky, b.skz, n_dev, n_cap, nb);
     const u32 fb_n = nbig_dev ? big_cap : n_big;
     if (fb_n > 0) {
-        ISX_LAUNCH(k_seg_big_gather, blocks < 1 ? 1 : blocks, 256, 0, stream, n, n_dev, n_cap, h.count, h.start, h.bigoff, b.perm0,
-                   b.cbucket, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid);
-        cudaError_t e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, nbig_dev);
+        // second level inside the oversized buckets
+        const u32 nb2 = b.subcap;
+        u32 *count2 = b.count2, *start2 = count2 + (nb2 + 1), *cursor2 = start2 + (nb2 + 1), *bigoff2 = cursor2 + (nb2 + 1);
+        cudaError_t e = cudaMemsetAsync(b.info2, 0, (8 + (size_t) nb2 + 1) * sizeof(u32), stream);
         if (e != cudaSuccess) return e;
+        ISX_LAUNCH(k_seg_big_gather, blocks < 1 ? 1 : blocks, 256, 0, stream, n, n_dev, n_cap, h.count, h.start, h.bigoff, b.perm0,
+                   b.cbucket, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid, h.xinvmin, h.xmax);
+        ISX_LAUNCH(k_big_plan, 1, 1024, 0, stream, nb, h.count, h.bigoff, b.bkx, h.sub_base, h.sub_par, h.sub_xm, geom.Y, nb2, b.info2,
+                   n_dev, n_cap);
         const int bb = (int) ((fb_n + 255) / 256 > 148 * 8 ? 148 * 8 : (fb_n + 255) / 256);
-        ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, fb_n, nbig_dev, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx,
+        ISX_LAUNCH(k_big_sub, bb, 256, 0, stream, fb_n, nbig_dev, b.bkx, b.bky, b.bid, b.cbucket, h.xinvmin, h.xmax, h.sub_base, h.sub_par,
+                   h.sub_xm, geom, b.csub, count2, b.info2);
+        ISX_LAUNCH(k_seg_scan, 1, 1024, 0, stream, nb2, count2, start2, cursor2, bigoff2, b.info2 + 1, b.info2 + 2, b.info2);
+        ISX_LAUNCH(k_big_decide, 1, 1, 0, stream, fb_n, nbig_dev, b.info2);
+        ISX_LAUNCH(k_seg_scatter, bb, 256, 0, stream, b.csub, fb_n, start2, cursor2, b.perm2, nbig_dev, 0xffffffffu, b.info2 + 5);
+        const SegLevel2 l2{b.bid, b.cbucket, h.start, h.bigoff, b.info2 + 5, b.info2};
+        const u32 g2s = nb2 < 148u * 32u ? nb2 : 148u * 32u, g2l = nb2 < 148u * 8u ? nb2 : 148u * 8u;
+        ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1, true>), g2s, 128, smem_small, stream, b.bkx, b.bky, b.bkz, count2, start2, b.perm2, b.perm,
+                   b.skx, b.sky, b.skz, nullptr, 0u, nb2, l2);
+        ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1, true>), g2l, SEG_THREADS, smem_big, stream, b.bkx, b.bky, b.bkz, count2,
+                   start2, b.perm2, b.perm, b.skx, b.sky, b.skz, nullptr, 0u, nb2, l2);
+        // last resort: a second-level bucket is still oversized (info2[4] != 0): global radix sort of the big list
+        e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, b.info2 + 4);
+        if (e != cudaSuccess) return e;
+        ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, fb_n, b.info2 + 4, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx,
                    b.bky, b.bkz, b.skx, b.sky, b.skz);
     }
     return cudaGetLastError();

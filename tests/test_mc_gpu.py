@@ -56,7 +56,20 @@ CASES = {
     "all_positive_empty": lambda: (torch.ones(8, 8, 8), 0.0, BOX),
     "all_negative_empty": lambda: (-torch.ones(9, 8, 7), 0.0, BOX),
     "single_exact_zero_point": lambda: (_single_zero(), 0.0, BOX),
+    # oversized sort buckets (> 4096 vertices in one x layer) and how they are cut a second time (segsort.cuh):
+    "xface_6x200x200_second_level_by_y": lambda: (_plane((6, 200, 200), (1.0, 0.0, 0.0), 0.13), 0.0, BOX),
+    "xface_5x3x9000_radix_last_resort": lambda: (_plane((5, 3, 9000), (1.0, 0.0, 0.0), 0.13), 0.0, BOX),
+    "tilted_7x160x160_second_level_by_x": lambda: (_plane((7, 160, 160), (1.0, 0.013, 0.007), 0.05), 0.0, BOX),
+    "xface_on_plane_5x96x96_exact_hits": lambda: (_plane((5, 96, 96), (1.0, 0.0, 0.0), 0.5), 0.0, BOX),
+    "box_4x150x150_two_xfaces": lambda: (fields.eval_field(S.CuboidSDF([0.9, 1.5, 1.5]), (4, 150, 150)), 0.0, BOX),
 }
+
+
+def _plane(shape, normal, offset):
+    """n . p - offset on the [-1,1]^3 grid: a face (nearly) perpendicular to x puts all its vertices in one x layer."""
+    ax = [fields.axis(n) for n in shape]
+    X, Y, Z = torch.meshgrid(*ax, indexing="ij")
+    return (normal[0] * X + normal[1] * Y + normal[2] * Z - offset).contiguous()
 
 
 def _single_zero():
