@@ -156,6 +156,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     peak, peak_src = load_peaks()
 
+    cuts = None
     if world == 1:
         vals = build_field_gpu(fn, n, 0, n, dev)
         grid = iso.UniformGrid([n, n, n])
@@ -168,6 +169,19 @@ def run_ours(args):
         sg = idist.SlabGrid([n, n, n], group=dist.group.WORLD)
         x0, x1 = sg.owned_point_range()
         sg.set_owned_values(build_field_gpu(fn, n, x0, x1, dev))
+        cuts = None
+        if not args.even_slabs:
+            # cut the slabs by measured load (setup, untimed): one extraction on even slabs gives the vertices per
+            # cell layer; cost(layer) = time to stream one plane + surface-stage time per vertex
+            v0, _ = idist.marching_cubes(sg)
+            hist = idist.vertex_layer_histogram(v0, n, -1.0, 1.0, dist.group.WORLD)
+            plane_s, vertex_s = 4.0 * n * n / (peak * 1e9), 0.43e-9
+            cuts = idist.balanced_cuts((plane_s + vertex_s * hist).tolist(), world, ghost_cost=(vertex_s * hist).tolist())
+            del v0
+            sg.close()
+            sg = idist.SlabGrid([n, n, n], group=dist.group.WORLD, cuts=cuts)
+            x0, x1 = sg.owned_point_range()
+            sg.set_owned_values(build_field_gpu(fn, n, x0, x1, dev))
 
         def step():
             return idist.marching_cubes(sg)
@@ -275,7 +289,9 @@ def run_ours(args):
             "data": "synthetic", "impl": "ours",
             "config": {"workload": f"{wl_name}: {wl['desc']}", "shape": [n, n, n], "level": 0.0, "method": "nagae",
                        "vertices": nV, "triangles": nT, "l2_policy": "inputs larger than L2 (no flush needed)",
-                       "parallelism": "single GPU" if world == 1 else f"dim-0 slabs x{world}, NCCL halo + count all_gather"},
+                       "parallelism": "single GPU" if world == 1 else
+                       f"dim-0 slabs x{world}; halo pull + vertex-id bases as kernels over NVLink peer memory"
+                       + (f"; slab cuts balanced by measured load {cuts}" if cuts else "; even slabs")},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches.value),
@@ -363,6 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--even-slabs", action="store_true", help="N > 1: keep the even dim-0 split (default: cuts balanced by measured load)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

@@ -190,15 +190,18 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
 /* Single-call fast path of marching_cubes on a UniformGrid: both phases enqueued back to back, ONE
  * stream synchronisation.  The caller supplies capacities (typically the sizes of the previous extraction
  * of this grid): V holds cand_cap rows, F tri_cap rows, scratch = isoext_mc_dense_scratch_bytes(cand_cap).
- * Returns 0 with counts_out[0..6] = {S, T, Vc, n_big, V, n_lo, n_hi}; returns 1 ("not completed",
- * counts_out[0..3] valid, outputs undefined) if a capacity was exceeded -- entries, candidates, triangles,
- * or big_cap (candidates in oversized x-buckets that the radix fallback was sized for; 0 = fallback not
- * enqueued) -- the caller then uses isoext_mc_dense_count + isoext_mc_dense_emit. */
+ * Returns 0 with counts_out[0..7] = {S, T, Vc, n_big, V, n_lo, n_hi, n_radix}; returns 1 ("not completed",
+ * counts_out[0..3] and [7] valid, outputs undefined) if a capacity was exceeded -- entries, candidates,
+ * triangles, or big_cap (candidates in oversized sort buckets that the second bucket level was sized for;
+ * 0 = not enqueued) -- or if n_radix > 0 candidates needed the radix last resort of the sort while
+ * radix == 0 (not enqueued): the caller then uses isoext_mc_dense_count + isoext_mc_dense_emit and passes
+ * radix = 1 next time. */
 int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                         const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
-                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, float x_lo_threshold,
-                        float x_hi_threshold, float *V, int32_t *F, void *stream, int64_t *counts_out);
+                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, int radix,
+                        float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
+                        int64_t *counts_out);
 
 /* Chunked, overlapped single-call path for large grids: the slab is cut into n_chunks (<= 8) sub-slabs along
  * x -- the same extended-slab / ownership-by-position logic as the multi-GPU path -- that are enqueued

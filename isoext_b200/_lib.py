@@ -65,7 +65,7 @@ SIGNATURES = {
     "isoext_dc_sparse_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i64, _vp, _vp, _vp,
                                      _vp, _pi64]),
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
-                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
+                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _vp, _vp, _vp, _pi64]),
     "isoext_mc_dense_run_chunked": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64, _f32, _f32, _int,
                                            _vp, _sz, _i64, _vp, _sz, _pi64, _pi64, _pi64, _vp, _pi64, _vp, _pi64, _vp, _i64, _vp,
                                            _i64, _vp, _vp, _pi64]),

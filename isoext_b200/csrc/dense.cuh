@@ -35,7 +35,8 @@ enum Counter : int {
     C_NBIG = 13,      // candidates in x-buckets larger than SEG_CAP (radix fallback needed if > 0)
     C_MAXB = 14,      // largest x-bucket
     C_NHEAVY = 15,    // rows handed to k_rowfill_heavy
-    C_COUNT = 16
+    C_RADIX = 16,     // candidates that need the radix last resort of the segmented sort (0 = none)
+    C_COUNT = 20
 };
 
 struct DenseParams {

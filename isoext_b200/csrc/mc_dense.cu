@@ -515,7 +515,7 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
 // the kernels then read the counts from the counter block and do nothing if a capacity is exceeded.
 static int enqueue_phase2(const float *values, const DenseParams &p, int method, const McBuffers &b, const McScratch &s,
                           u32 entry_cap, u32 host_nc, u32 n_big, bool device_counts, u32 cand_cap, u32 tri_cap, u32 big_cap,
-                          float x_lo_threshold,
+                          bool allow_radix, float x_lo_threshold,
                           float x_hi_threshold, float *V, int32_t *F, cudaStream_t stream) {
     const int sms = device_sms();
     const u32 *n_dev = device_counts ? b.counters + C_VC : nullptr;
@@ -524,7 +524,7 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
                s.seg.cbucket, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg,
-                          SegGeom{p.g.amin[1], p.g.asize[1], (u32) p.g.Y}, stream));
+                          SegGeom{p.g.amin[1], p.g.asize[1], (u32) p.g.Y}, allow_radix, b.counters + C_RADIX, stream));
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
                b.descV, klo, khi, n_dev, cand_cap, true);
@@ -594,7 +594,7 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
     Carver cs(scratch);
     McScratch s;
     if (carve_mc_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
-    rc = enqueue_phase2(values, p, method, b, s, (u32) cap_entries, (u32) n_candidates, (u32) n_big, false, 0xffffffffu, 0xffffffffu, 0,
+    rc = enqueue_phase2(values, p, method, b, s, (u32) cap_entries, (u32) n_candidates, (u32) n_big, false, 0xffffffffu, 0xffffffffu, 0, true,
                         x_lo_threshold,
                         x_hi_threshold, V, F, stream);
     if (rc != OK) return rc;
@@ -617,7 +617,7 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
 int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                         const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
-                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, float x_lo_threshold,
+                        size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, int radix, float x_lo_threshold,
                         float x_hi_threshold, float *V, int32_t *F, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
@@ -638,14 +638,15 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
     if (rc != OK) return rc;
     if (big_cap < 0 || big_cap > cand_cap) return fail(E_INVALID, "big_cap out of range");
     rc = enqueue_phase2(values, p, method, b, s, cap, 0, 0, true, (u32) cand_cap, (u32) (tri_cap > 0xffffffffLL ? 0xffffffffLL : tri_cap),
-                        (u32) big_cap, x_lo_threshold, x_hi_threshold, V, F, stream);
+                        (u32) big_cap, radix != 0, x_lo_threshold, x_hi_threshold, V, F, stream);
     if (rc != OK) return rc;
     u32 h[C_COUNT];
     rc = read_counters(b, h, stream);
     if (rc != OK) return rc;
     counts_out[0] = h[C_S]; counts_out[1] = h[C_T]; counts_out[2] = h[C_VC]; counts_out[3] = h[C_NBIG];
-    counts_out[4] = h[C_V]; counts_out[5] = h[C_NLO]; counts_out[6] = h[C_NHI];
+    counts_out[4] = h[C_V]; counts_out[5] = h[C_NLO]; counts_out[6] = h[C_NHI]; counts_out[7] = h[C_RADIX];
     if (h[C_S] > cap || h[C_VC] > (u32) cand_cap || (i64) h[C_T] > tri_cap || h[C_NBIG] > (u32) big_cap) return 1;
+    if (h[C_RADIX] > 0 && !radix) return 1;   // the radix last resort was needed but not enqueued
     return OK;
 }
 
@@ -812,7 +813,7 @@ int isoext_mc_dense_run_chunked(const float *values, int64_t X, int64_t Y, int64
         enqueue_compact(p, b, (u32) cap_entries, s_k);
         rc = enqueue_analysis(vals_k, p, method, b, (u32) cap_entries, s_k);
         if (rc != OK) return rc;
-        rc = enqueue_phase2(vals_k, p, method, b, s, (u32) cap_entries, 0, 0, true, (u32) cand_cap[k], tcap, (u32) big_cap[k], q.thr_lo,
+        rc = enqueue_phase2(vals_k, p, method, b, s, (u32) cap_entries, 0, 0, true, (u32) cand_cap[k], tcap, (u32) big_cap[k], true, q.thr_lo,
                             q.thr_hi, Vk, Fk, s_k);
         if (rc != OK) return rc;
         ISX_LAUNCH(k_chunk_save, 1, 32, 0, s_k, b.counters, cc + 8 * k, (u32) cap_entries, (u32) cand_cap[k], tcap, (u32) big_cap[k]);

@@ -11,9 +11,10 @@
 //
 //   k_seg_count    histogram of bucket ids
 //   k_seg_scan     exclusive scan of the histogram (one block), big-bucket bookkeeping
-//   k_seg_scatter  group candidate ids by bucket (order inside a bucket is irrelevant: it is sorted next)
+//   k_seg_scatter  group candidate ids by bucket (order inside a bucket is irrelevant: it is sorted next);
+//                  elements of oversized buckets go straight to a compacted list of keys
 //   k_seg_sort     one block per bucket: load keys, bitonic sort in smem, write sorted ids
-//   (oversized)    k_seg_big_gather -> k_big_plan -> k_big_sub -> k_seg_scan -> k_seg_scatter -> k_seg_sort:
+//   (oversized)    k_big_plan -> k_big_sub -> k_seg_scan -> k_seg_scatter -> k_seg_sort:
 //                  a second level of buckets inside every oversized bucket (an axis-aligned face: nearly all
 //                  vertices share one x, so cut that value by y-plane and the rest of the x range uniformly)
 //   (last resort)  radix_sort96 over the oversized buckets if a second-level bucket is still too large
@@ -155,10 +156,18 @@ static __global__ void __launch_bounds__(1024) k_seg_scan(u32 nb, const u32 *__r
     seg_scan_block(nb, count, start, cursor, bigoff, info_nbig, info_max, sw, s4);
 }
 
+// Group candidate ids by bucket.  WITH_BIG (first level): the elements of oversized buckets go straight to the
+// compacted big list (keys + ids, at bigoff[b] + position inside the bucket) and the x range of every oversized
+// bucket is accumulated for k_big_plan -- the order inside a bucket is irrelevant, it is sorted next.
+struct SegBigOut {
+    const u32 *count, *bigoff, *kx, *ky, *kz;
+    u32 *bkx, *bky, *bkz, *bid, *xinvmin, *xmax;
+};
+template <bool WITH_BIG>
 static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restrict__ cbucket, u32 n, const u32 *__restrict__ start,
                                                             u32 *__restrict__ cursor, u32 *__restrict__ perm0,
                                                             const u32 *__restrict__ n_dev, u32 n_cap,
-                                                            const u32 *__restrict__ skip = nullptr) {
+                                                            const u32 *__restrict__ skip, SegBigOut big) {
     if (skip && *skip) return;
     if (n_dev) n = *n_dev;
     if (n > n_cap) return;
@@ -173,8 +182,18 @@ static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restric
             const u32 leader = __ffs(peers) - 1;
             u32 off = 0;
             if (lane == leader) off = atomicAdd(&cursor[b], (u32) __popc(peers));
-            off = __shfl_sync(peers, off, leader);
-            perm0[start[b] + off + __popc(peers & ((1u << lane) - 1u))] = i;
+            off = __shfl_sync(peers, off, leader) + __popc(peers & ((1u << lane) - 1u));
+            if (WITH_BIG && big.count[b] > (u32) SEG_CAP) {
+                const u32 o = big.bigoff[b] + off, x = big.kx[i];
+                big.bkx[o] = x; big.bky[o] = big.ky[i]; big.bkz[o] = big.kz[i]; big.bid[o] = i;
+                const u32 mx = __reduce_max_sync(peers, x), mn = __reduce_max_sync(peers, ~x);
+                if (lane == leader) {
+                    atomicMax(&big.xmax[b], mx);
+                    atomicMax(&big.xinvmin[b], mn);
+                }
+            } else {
+                perm0[start[b] + off] = i;
+            }
         }
     }
 }
@@ -371,54 +390,7 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
     }
 }
 
-// ---- fallback for big buckets -------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) k_seg_big_gather(u32 n, const u32 *__restrict__ n_dev, u32 n_cap,
-                                                               const u32 *__restrict__ count, const u32 *__restrict__ start,
-                                                               const u32 *__restrict__ bigoff, const u32 *__restrict__ perm0,
-                                                               const u32 *__restrict__ cbucket,
-                                                               const u32 *__restrict__ kx, const u32 *__restrict__ ky,
-                                                               const u32 *__restrict__ kz, u32 *__restrict__ bkx, u32 *__restrict__ bky,
-                                                               u32 *__restrict__ bkz, u32 *__restrict__ bid, u32 *__restrict__ xinvmin,
-                                                               u32 *__restrict__ xmax) {
-    if (n_dev) n = *n_dev;
-    if (n > n_cap) return;
-    const u32 lane = threadIdx.x & 31;
-    constexpr int G = 4;   // independent load chains per thread (perm0 -> cbucket -> count)
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += G * stride) {
-        u32 id[G], bb[G], cc[G];
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            const u32 i = base + k * stride + lane;
-            id[k] = i < n ? perm0[i] : 0xffffffffu;
-        }
-#pragma unroll
-        for (int k = 0; k < G; k++) bb[k] = id[k] != 0xffffffffu ? cbucket[id[k]] : 0xffffffffu;
-#pragma unroll
-        for (int k = 0; k < G; k++) cc[k] = bb[k] != 0xffffffffu ? count[bb[k]] : 0u;
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            const u32 i = base + k * stride + lane;     // position in the grouped list
-            u32 b = 0xffffffffu, x = 0;
-            if (cc[k] > (u32) SEG_CAP) {
-                b = bb[k];
-                x = kx[id[k]];
-                const u32 o = bigoff[b] + (i - start[b]);
-                bkx[o] = x; bky[o] = ky[id[k]]; bkz[o] = kz[id[k]]; bid[o] = id[k];
-            }
-            // x range of every big bucket (the grouped list keeps a bucket contiguous: a warp sees one or two)
-            const u32 peers = __match_any_sync(0xffffffffu, b);
-            if (b != 0xffffffffu) {
-                const u32 mx = __reduce_max_sync(peers, x), mn = __reduce_max_sync(peers, ~x);
-                if (lane == (u32) (__ffs(peers) - 1)) {
-                    atomicMax(&xmax[b], mx);
-                    atomicMax(&xinvmin[b], mn);
-                }
-            }
-        }
-    }
-}
-
+// ---- oversized buckets ----------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u32 pow2ceil_u32(u32 v) {
     u32 p = 1;
     while (p < v) p <<= 1;
@@ -534,9 +506,10 @@ static __global__ void __launch_bounds__(256) k_big_sub(u32 n_big, const u32 *__
 }
 
 // after the second-level scan: does the radix sort have to take over?  info2[4] = number of elements it sorts
-static __global__ void k_big_decide(u32 n_big, const u32 *__restrict__ nbig_dev, u32 *__restrict__ info2) {
+static __global__ void k_big_decide(u32 n_big, const u32 *__restrict__ nbig_dev, u32 *__restrict__ info2, u32 *__restrict__ radix_needed) {
     if (nbig_dev) n_big = *nbig_dev;
     info2[4] = info2[6] ? 0u : ((info2[3] || info2[2] > (u32) SEG_CAP) ? n_big : 0u);
+    if (radix_needed) *radix_needed = info2[4];
 }
 // sorted rank r of the big list -> final position: the big list is ordered by bucket (x decides the bucket)
 static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const u32 *__restrict__ nbig_dev, const u32 *__restrict__ sorted,
@@ -561,11 +534,11 @@ static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const
 // radix fallback for the oversized buckets.  The histogram (h.count) and its scan (h.start / h.bigoff) were
 // produced in phase 1.
 //   two-phase path : n, n_big known on the host (n_dev = nbig_dev = nullptr); the fallback runs iff n_big > 0
-//   single-sync path: counts live on the device; n_cap sizes the launches; the fallback is enqueued iff
+//   single-sync path: counts live on the device; n_cap sizes the launches; the second level is enqueued iff
 //                    big_cap > 0 (the caller's guess) and does nothing when the device count is 0
 static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const u32 *n_dev, u32 n_cap, u32 grid_n,
                                        u32 nb, u32 n_big, const u32 *nbig_dev, u32 big_cap, const SegHead &h, const SegScratch &b,
-                                       const SegGeom &geom, cudaStream_t stream) {
+                                       const SegGeom &geom, bool allow_radix, u32 *radix_needed, cudaStream_t stream) {
     constexpr size_t smem_big = SegCfg<SEG_CAP, SEG_THREADS>::SMEM, smem_small = SegCfg<SEG_SMALL, 128>::SMEM;
     static bool attr_set = false;
     if (!attr_set) {
@@ -576,7 +549,9 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         attr_set = true;
     }
     const int blocks = (int) ((grid_n + 255) / 256 > 148 * 8 ? 148 * 8 : (grid_n + 255) / 256);
-    ISX_LAUNCH(k_seg_scatter, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap);
+    const SegBigOut big{h.count, h.bigoff, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid, h.xinvmin, h.xmax};
+    ISX_LAUNCH(k_seg_scatter<true>, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap,
+               nullptr, big);
     const u32 grid_small = nb < 148u * 32u ? nb : 148u * 32u, grid_large = nb < 148u * 8u ? nb : 148u * 8u;
     ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
                b.skx, b.sky, b.skz, n_dev, n_cap, nb);
@@ -589,23 +564,25 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         u32 *count2 = b.count2, *start2 = count2 + (nb2 + 1), *cursor2 = start2 + (nb2 + 1), *bigoff2 = cursor2 + (nb2 + 1);
         cudaError_t e = cudaMemsetAsync(b.info2, 0, (8 + (size_t) nb2 + 1) * sizeof(u32), stream);
         if (e != cudaSuccess) return e;
-        ISX_LAUNCH(k_seg_big_gather, blocks < 1 ? 1 : blocks, 256, 0, stream, n, n_dev, n_cap, h.count, h.start, h.bigoff, b.perm0,
-                   b.cbucket, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid, h.xinvmin, h.xmax);
         ISX_LAUNCH(k_big_plan, 1, 1024, 0, stream, nb, h.count, h.bigoff, b.bkx, h.sub_base, h.sub_par, h.sub_xm, geom.Y, nb2, b.info2,
                    n_dev, n_cap);
         const int bb = (int) ((fb_n + 255) / 256 > 148 * 8 ? 148 * 8 : (fb_n + 255) / 256);
         ISX_LAUNCH(k_big_sub, bb, 256, 0, stream, fb_n, nbig_dev, b.bkx, b.bky, b.bid, b.cbucket, h.xinvmin, h.xmax, h.sub_base, h.sub_par,
                    h.sub_xm, geom, b.csub, count2, b.info2);
         ISX_LAUNCH(k_seg_scan, 1, 1024, 0, stream, nb2, count2, start2, cursor2, bigoff2, b.info2 + 1, b.info2 + 2, b.info2);
-        ISX_LAUNCH(k_big_decide, 1, 1, 0, stream, fb_n, nbig_dev, b.info2);
-        ISX_LAUNCH(k_seg_scatter, bb, 256, 0, stream, b.csub, fb_n, start2, cursor2, b.perm2, nbig_dev, 0xffffffffu, b.info2 + 5);
+        ISX_LAUNCH(k_big_decide, 1, 1, 0, stream, fb_n, nbig_dev, b.info2, radix_needed);
+        ISX_LAUNCH(k_seg_scatter<false>, bb, 256, 0, stream, b.csub, fb_n, start2, cursor2, b.perm2, nbig_dev, 0xffffffffu, b.info2 + 5,
+                   SegBigOut{});
         const SegLevel2 l2{b.bid, b.cbucket, h.start, h.bigoff, b.info2 + 5, b.info2};
         const u32 g2s = nb2 < 148u * 32u ? nb2 : 148u * 32u, g2l = nb2 < 148u * 8u ? nb2 : 148u * 8u;
         ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1, true>), g2s, 128, smem_small, stream, b.bkx, b.bky, b.bkz, count2, start2, b.perm2, b.perm,
                    b.skx, b.sky, b.skz, nullptr, 0u, nb2, l2);
         ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1, true>), g2l, SEG_THREADS, smem_big, stream, b.bkx, b.bky, b.bkz, count2,
                    start2, b.perm2, b.perm, b.skx, b.sky, b.skz, nullptr, 0u, nb2, l2);
-        // last resort: a second-level bucket is still oversized (info2[4] != 0): global radix sort of the big list
+        // last resort: a second-level bucket is still oversized (info2[4] != 0): global radix sort of the big list.
+        // 14 launches that do nothing in the common case, so the single-sync path only enqueues them when the
+        // previous extraction of the grid needed them (*radix_needed tells the host)
+        if (!allow_radix) return cudaGetLastError();
         e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, b.info2 + 4);
         if (e != cudaSuccess) return e;
         ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, fb_n, b.info2 + 4, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx,

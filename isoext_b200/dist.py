@@ -46,9 +46,76 @@ def partition_cells(X: int, world: int) -> list[int]:
     return [(layers * r) // world for r in range(world + 1)]
 
 
-def slab_plan(X: int, rank: int, world: int) -> dict:
+def check_cuts(X: int, world: int, cuts) -> list[int]:
+    """Validate explicit cell-layer boundaries c_0..c_world (every slab needs at least 2 layers: the halo
+    planes of a rank come from its immediate neighbours only)."""
+    cuts = [int(c) for c in cuts]
+    if len(cuts) != world + 1 or cuts[0] != 0 or cuts[-1] != X - 1:
+        raise RuntimeError(f"cuts must be {world + 1} boundaries from 0 to {X - 1}")
+    if any(b - a < 2 for a, b in zip(cuts[:-1], cuts[1:])):
+        raise RuntimeError("every slab needs at least 2 cell layers")
+    return cuts
+
+
+def balanced_cuts(layer_cost, world: int, ghost_cost=None) -> list[int]:
+    """Cell-layer boundaries c_0..c_world that minimise the most expensive slab (exact dynamic programme).
+
+    ``layer_cost[l]``: cost of owning cell layer l (X-1 non-negative numbers).  ``ghost_cost[l]`` (optional): what a
+    slab pays for layer l when l is one of its two ghost layers (the layer just below its first and the one just
+    above its last: they are evaluated for welding but emit no faces) -- normally the surface part of
+    ``layer_cost``.  Every slab gets at least 2 layers.  Any boundaries give the same global mesh bit for bit;
+    these only move work, e.g. away from the ranks next to an axis-aligned face."""
+    cost = torch.as_tensor([float(c) for c in layer_cost], dtype=torch.float64)
+    L = int(cost.numel())
+    if L < 2 * world:
+        raise RuntimeError(f"cannot cut {L} cell layers into {world} slabs of at least 2 layers")
+    ghost = torch.zeros(L, dtype=torch.float64) if ghost_cost is None else torch.as_tensor([float(c) for c in ghost_cost], dtype=torch.float64)
+    if world == 1:
+        return [0, L]
+    step = max(1, (L + 4095) // 4096)                 # boundaries on a coarser lattice for very deep grids
+    pos = list(range(0, L, step))
+    if pos[-1] != L:
+        pos.append(L)
+    P = torch.tensor(pos)
+    prefix = torch.cat([torch.zeros(1, dtype=torch.float64), cost.cumsum(0)])
+    below = torch.cat([torch.zeros(1, dtype=torch.float64), ghost])        # below[a] = ghost cost of layer a-1
+    above = torch.cat([ghost, torch.zeros(1, dtype=torch.float64)])        # above[b] = ghost cost of layer b
+    # C[i, j] = cost of the slab [pos_i, pos_j)
+    C = (prefix[P][None, :] - prefix[P][:, None]) + below[P][:, None] + above[P][None, :]
+    C = torch.where((P[None, :] - P[:, None]) >= 2, C, torch.full_like(C, float("inf")))
+    n = len(pos)
+    dp = C[0].clone()                                  # one slab [0, pos_j)
+    choice = []
+    for _ in range(1, world):
+        M = torch.maximum(dp[:, None], C)              # last slab [pos_i, pos_j) after an optimal prefix ending at pos_i
+        dp, arg = M.min(dim=0)
+        choice.append(arg)
+    if not math.isfinite(float(dp[n - 1])):
+        raise RuntimeError(f"cannot cut {L} cell layers into {world} slabs of at least 2 layers")
+    cuts, j = [L], n - 1
+    for arg in reversed(choice):
+        j = int(arg[j])
+        cuts.append(pos[j])
+    return [0] + cuts[::-1]
+
+
+def vertex_layer_histogram(v_own: torch.Tensor, X: int, aabb_min_x: float, aabb_max_x: float, group=None) -> torch.Tensor:
+    """Vertices per cell layer of the GLOBAL mesh (sum over ranks of this rank's owned vertices): the measured
+    surface load behind ``balanced_cuts``."""
+    layers = X - 1
+    if v_own.numel():
+        t = (v_own[:, 0].double() - aabb_min_x) / (aabb_max_x - aabb_min_x) * layers
+        h = torch.bincount(t.floor().clamp_(0, layers - 1).long(), minlength=layers).to(torch.float64)
+    else:
+        h = torch.zeros(layers, dtype=torch.float64, device=v_own.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(h, group=group)
+    return h
+
+
+def slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
     """Everything rank `rank` needs to know about its slab (all plane indices are GLOBAL)."""
-    c = partition_cells(X, world)
+    c = partition_cells(X, world) if cuts is None else check_cuts(X, world, cuts)
     c_lo, c_hi = c[rank], c[rank + 1]
     own_lo, own_hi = c_lo, (c_hi if rank < world - 1 else X)        # owned point planes [own_lo, own_hi)
     ext_lo, ext_hi = max(0, c_lo - 1), min(X - 1, c_hi + 1)           # extended slab planes [ext_lo, ext_hi]
@@ -112,10 +179,13 @@ def relabel_ids_torch(F: torch.Tensor, n_lo: int, n_hi: int, base_mine: int, bas
 
 # ---- GPU layer -------------------------------------------------------------------------------------
 class SlabGrid:
-    """This rank's slab of a global UniformGrid (same constructor arguments as ``UniformGrid``)."""
+    """This rank's slab of a global UniformGrid (same constructor arguments as ``UniformGrid``).
+
+    ``cuts`` (optional, identical on all ranks): explicit cell-layer boundaries c_0..c_world instead of the even
+    split, e.g. from ``balanced_cuts`` -- the extracted mesh does not depend on them."""
 
     def __init__(self, shape, aabb_min=(-1.0, -1.0, -1.0), aabb_max=(1.0, 1.0, 1.0), default_value=3.4028234663852886e38,
-                 group=None, device=None, rank=None, world=None):
+                 group=None, device=None, rank=None, world=None, cuts=None):
         from . import _lib
         from .grid import _Workspace
         self.shape = tuple(int(s) for s in shape)
@@ -125,7 +195,8 @@ class SlabGrid:
         # rank/world may be given explicitly to simulate a slab without a process group (tests)
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
-        self.plan = slab_plan(self.shape[0], self.rank, self.world)
+        self.cuts = None if cuts is None else check_cuts(self.shape[0], self.world, cuts)   # explicit slab boundaries
+        self.plan = slab_plan(self.shape[0], self.rank, self.world, self.cuts)
         _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         X, Y, Z = self.shape
@@ -235,11 +306,11 @@ class SlabGrid:
         base = self._ext.data_ptr()
         seg = [(None, None, 0, None), (None, None, 0, None)]
         if self.rank > 0:
-            q = slab_plan(X, self.rank - 1, self.world)
+            q = slab_plan(X, self.rank - 1, self.world, self.cuts)
             src = pr["peer_ext"][self.rank - 1] + (p["halo_below"] - q["ext_lo"]) * plane * 4
             seg[0] = (base + (p["halo_below"] - p["ext_lo"]) * plane * 4, src, plane, pr["peer_sync"][self.rank - 1])
         if self.rank < self.world - 1 and p["halo_above"]:
-            q = slab_plan(X, self.rank + 1, self.world)
+            q = slab_plan(X, self.rank + 1, self.world, self.cuts)
             g0 = p["halo_above"][0]
             src = pr["peer_ext"][self.rank + 1] + (g0 - q["ext_lo"]) * plane * 4
             seg[1] = (base + (g0 - p["ext_lo"]) * plane * 4, src, plane * len(p["halo_above"]), pr["peer_sync"][self.rank + 1])

@@ -64,7 +64,8 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         F = torch.empty((tri_cap, 3), dtype=torch.int32, device=dev)
         rc = lib.isoext_mc_dense_run(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
                                      wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(), cand_cap, tri_cap,
-                                     big_cap, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), stream, counts)
+                                     big_cap, 1 if hints.get("radix") else 0, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), stream, counts)
+        hints["radix"] = int(counts[7]) > 0     # the sort's radix last resort is only enqueued when it was needed last time
         if rc == 0:
             S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
             hints.update(Vc=Vc, T=T, n_big=int(counts[3]))

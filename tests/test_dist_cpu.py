@@ -61,10 +61,10 @@ def px(i, X, lo=-1.0, hi=1.0):
     return float(_lib.lib().isoext_axis_position(i, X, lo, hi))
 
 
-def simulate_rank(vals, rank, world, method):
+def simulate_rank(vals, rank, world, method, cuts=None):
     """What one rank computes, with the oracle standing in for the CUDA pipeline."""
     X = vals.shape[0]
-    p = idist.slab_plan(X, rank, world)
+    p = idist.slab_plan(X, rank, world, cuts)
     v_ext, f_ext, _ = oracle.mc_dense(vals, 0.0, method, x_range=(p["ext_lo"], p["ext_hi"]))
     n_below = len(oracle.mc_dense(vals, 0.0, method, x_range=(p["ext_lo"], p["c_lo"]))[1])
     n_own = len(oracle.mc_dense(vals, 0.0, method, x_range=(p["c_lo"], p["c_hi"]))[1])
@@ -94,13 +94,9 @@ def _plane_field():
     return f
 
 
-@pytest.mark.parametrize("method", ["nagae", "lorensen"])
-@pytest.mark.parametrize("world", [2, 3, 4])
-@pytest.mark.parametrize("name", sorted(FIELDS))
-def test_per_rank_parts_concatenate_to_the_single_device_mesh(name, world, method):
-    vals = FIELDS[name]().numpy()
+def _concat_check(vals, world, method, cuts=None):
     gv, gf, _ = oracle.mc_dense(vals, 0.0, method)
-    parts = [simulate_rank(vals, r, world, method) for r in range(world)]
+    parts = [simulate_rank(vals, r, world, method, cuts) for r in range(world)]
     owned = [len(p[0]) for p in parts]
     bases = np.concatenate([[0], np.cumsum(owned)])
     vs, fs = [], []
@@ -111,3 +107,47 @@ def test_per_rank_parts_concatenate_to_the_single_device_mesh(name, world, metho
     f = np.concatenate(fs)
     assert v.shape == gv.shape and np.array_equal(v.view(np.uint32), gv.view(np.uint32))
     assert np.array_equal(f, gf)
+
+
+@pytest.mark.parametrize("method", ["nagae", "lorensen"])
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("name", sorted(FIELDS))
+def test_per_rank_parts_concatenate_to_the_single_device_mesh(name, world, method):
+    _concat_check(FIELDS[name]().numpy(), world, method)
+
+
+@pytest.mark.parametrize("name,cuts", [("cuboid33_faces_on_slab_planes", [0, 2, 16, 18, 32]), ("csg36", [0, 9, 11, 35]),
+                                       ("planes_exactly_at_level", [0, 8, 12, 14, 24]), ("noise24", [0, 2, 4, 6, 21, 23])])
+def test_uneven_slab_boundaries_give_the_same_mesh(name, cuts):
+    """Explicit (load-balancing) cuts: the mesh must not depend on where the slabs are cut, including cuts right
+    on planes that carry box faces / exact-level planes and minimal 2-layer slabs."""
+    _concat_check(FIELDS[name]().numpy(), len(cuts) - 1, "nagae", cuts)
+
+
+def test_balanced_cuts_properties():
+    import random
+    rng = random.Random(1)
+    assert idist.balanced_cuts([1.0] * 64, 8) == [0, 8, 16, 24, 32, 40, 48, 56, 64]
+    for _ in range(300):
+        layers = rng.randint(4, 80)
+        world = rng.randint(1, layers // 2)
+        cost = [rng.random() ** 4 * rng.choice([1, 100]) for _ in range(layers)]
+        cuts = idist.balanced_cuts(cost, world)
+        assert idist.check_cuts(layers + 1, world, cuts) == cuts
+    # a lump (an axis-aligned face) is isolated: the slab holding it is much thinner than the others
+    cost = [1.0] * 100
+    cost[30] = 60.0
+    cuts = idist.balanced_cuts(cost, 4)
+    width = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+    r = next(i for i in range(4) if cuts[i] <= 30 < cuts[i + 1])
+    assert width[r] == min(width) and max(sum(cost[a:b]) for a, b in zip(cuts[:-1], cuts[1:])) < 0.5 * sum(cost)
+    with pytest.raises(RuntimeError):
+        idist.balanced_cuts([1.0] * 5, 3)
+    with pytest.raises(RuntimeError):
+        idist.check_cuts(10, 2, [0, 1, 9])
+
+
+def test_vertex_layer_histogram_counts_every_vertex_once():
+    v = torch.tensor([[-1.0, 0, 0], [-0.01, 0, 0], [0.0, 0, 0], [0.99, 0, 0], [1.0, 0, 0]])
+    h = idist.vertex_layer_histogram(v, 5, -1.0, 1.0)
+    assert h.tolist() == [1.0, 1.0, 1.0, 2.0]

@@ -51,6 +51,28 @@ def test_simulated_ranks_concatenate_to_single_gpu_mesh(iso, name, world, method
     assert torch.equal(f, gf)
 
 
+@pytest.mark.parametrize("name,cuts", [("cuboid65_faces_on_slab_planes", [0, 2, 32, 34, 48, 64]), ("csg72", [0, 30, 32, 71]),
+                                       ("noise_40x20x24", [0, 2, 4, 37, 39])])
+def test_simulated_ranks_with_uneven_cuts(iso, name, cuts):
+    """Load-balancing cuts (dist.balanced_cuts) only move work: same mesh bit for bit."""
+    from isoext_b200 import dist as idist
+    vals = FIELDS[name]().cuda()
+    g = iso.UniformGrid(list(vals.shape))
+    g.set_values(vals)
+    gv, gf = iso.marching_cubes(g)
+    world, parts = len(cuts) - 1, []
+    for r in range(world):
+        sg = idist.SlabGrid(list(vals.shape), rank=r, world=world, cuts=cuts)
+        p = sg.plan
+        sg._ext.copy_(vals[p["ext_lo"]:p["ext_hi"] + 1])
+        parts.append(idist.marching_cubes_local(sg))
+    bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])])
+    for r, (v_own, f, n_lo, n_hi) in enumerate(parts):
+        idist.relabel_faces_(f, n_lo, n_hi, int(bases[r]), int(bases[r + 1]))
+    v, f = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf)
+
+
 def _nccl_worker(rank, world, port, transport, field_name):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ISOEXT_B200_PEER="1" if transport == "peer" else "0")
     torch.cuda.set_device(rank)
@@ -79,6 +101,17 @@ def _nccl_worker(rank, world, port, transport, field_name):
         v_own, f_own = idist.marching_cubes(sg, 0.0)
         v2_own, f2_own = idist.marching_cubes(sg, 0.0, exchange=False)
         assert torch.equal(v_own, v2_own) and torch.equal(f_own, f2_own)
+        # re-cut the slabs by measured load: the global mesh must not change
+        hist = idist.vertex_layer_histogram(v_own, vals.shape[0], -1.0, 1.0)
+        cuts = idist.balanced_cuts((hist + 1.0).tolist(), world, ghost_cost=hist.tolist())
+        sg.close()
+        sg = idist.SlabGrid(list(vals.shape), cuts=cuts)
+        lo, hi = sg.owned_point_range()
+        sg.set_owned_values(vals[lo:hi].contiguous())
+        v, f = idist.gather_mesh(*idist.marching_cubes(sg))
+        g.set_values(vals)
+        gv, gf = iso.marching_cubes(g)
+        assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf), f"rank {rank}: balanced cuts {cuts}"
         sg.close()
     finally:
         dist.destroy_process_group()
