@@ -47,42 +47,58 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled from a
+    thread every few ms (the timed region of the headline workload is only tens of ms long, far below what an
+    `nvidia-smi -lms` loop resolves); nvidia-smi is the fallback when the NVML binding is missing."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
+
+    def _poll_nvml(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self._thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.source = "nvidia-smi"
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        if self.source == "nvml":
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+        if not self.sm:   # fallback: one nvidia-smi query right after the timed region
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+                self.sm, self.max_mhz = [float(out[0])], float(out[1])
+                for (bit, _), val in zip(self.REASONS, out[2:6]):
+                    if val.strip().lower().startswith("active"):
+                        self.mask |= bit
+                self.source = "nvidia-smi (one query after the timed region)"
             except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for bit, name in self.REASONS if self.mask & bit), "samples": len(self.sm),
+                "source": self.source}
 
 
 def field_fn(name):

@@ -51,6 +51,9 @@ struct DenseParams {
     // sort buckets (segsort.cuh): every x-layer [px[b], px[b+1]) is cut into gy groups of vertices lying exactly
     // on plane b (split by y) and gx groups of vertices inside the layer (split by x)
     u32 gy, gx, ystep;
+    // k_cell_tris fast path: an edge whose crossing parameter t lies in [eps2[a], 1 - eps2[a]] (a = axis of the edge:
+    // 0 x, 1 y, 2 z) is provably more than an ulp away from both end points, see cell_is_plain()
+    float eps2[3];
 };
 __host__ __device__ __forceinline__ u32 sort_nsub(const DenseParams &p) { return p.gy + p.gx; }
 __host__ __device__ __forceinline__ u32 sort_buckets(const DenseParams &p) { return ((u32) p.g.X + 2) * (p.gy + p.gx); }
@@ -682,6 +685,49 @@ struct CellData {
     float px[2], py[2], pz[2];
 };
 
+__device__ __forceinline__ void load_cell_values(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, CellData &c) {
+    const u32 Z = (u32) p.g.Z;
+    const i64 n = (i64) r * Z + z;
+    c.v[0] = __ldg(values + n);
+    c.v[1] = __ldg(values + n + 1);
+    c.v[2] = __ldg(values + n + Z);
+    c.v[3] = __ldg(values + n + Z + 1);
+    c.v[4] = __ldg(values + n + p.YZ);
+    c.v[5] = __ldg(values + n + p.YZ + 1);
+    c.v[6] = __ldg(values + n + p.YZ + Z);
+    c.v[7] = __ldg(values + n + p.YZ + Z + 1);
+}
+__device__ __forceinline__ void load_cell_positions(const DenseParams &p, u32 r, u32 z, CellData &c) {
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 x = r / Y, y = r - x * Y;
+    const u32 xg = x + (u32) p.g.x_off;
+    c.px[0] = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+    c.px[1] = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+    c.py[0] = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
+    c.py[1] = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
+    c.pz[0] = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
+    c.pz[1] = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
+}
+// True if no two crossing points of the cell can be bit-equal, so that no triangle of the cell is degenerate
+// (src/mc/nagae.cu:71) and the positions need not be evaluated to know it.  Two points on different edges of a
+// cell can only coincide near a corner the edges share.  With a = level - v0, d = v1 - v0 (the operands of the
+// reference's t = a / d), 2 eps |d| <= |a| <= (1 - 2 eps) |d| gives eps <= t <= 1 - eps after rounding, hence
+// the point is at least eps * cell - 2 ulp away from both end points along the edge axis, while a point on
+// another edge through the same corner stays within 1 ulp of the corner along that axis.  eps * cell = 16 ulp of
+// the largest coordinate (make_dense_params), so the two differ.  NaN fails the comparisons -> not plain.
+__device__ __forceinline__ bool cell_is_plain(const CellData &c, u32 status, const DenseParams &p) {
+    bool plain = true;
+#pragma unroll
+    for (int k = 0; k < 12; k++)
+        if ((status >> k) & 1u) {
+            const int p0 = edge_c0(k), p1 = edge_c1(k);
+            const int axis = (p0 ^ p1) == 4 ? 0 : ((p0 ^ p1) == 2 ? 1 : 2);
+            const float a = fabsf(__fsub_rn(p.level, c.v[p0])), d = fabsf(__fsub_rn(c.v[p1], c.v[p0]));
+            const float e2 = p.eps2[axis];
+            plain = plain && (a >= e2 * d) && (a <= (1.0f - e2) * d);
+        }
+    return plain;
+}
 __device__ __forceinline__ void load_cell(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, CellData &c) {
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
     const u32 x = r / Y, y = r - x * Y;

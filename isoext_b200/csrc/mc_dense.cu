@@ -12,6 +12,7 @@
 //   k_unique                  positional welding of candidates that snapped onto a shared corner
 //   k_emit_faces              LUT-driven face emission with final vertex ids
 // Every arithmetic step that decides a bit of the output uses explicit _rn intrinsics.
+#include <cmath>
 #include <cstdlib>
 #include "dense.cuh"
 #include "radix.cuh"
@@ -187,18 +188,27 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
         nb[3 * s + 2] = lbXY;
 
         CellData c;
-        load_cell(values, p, r, z, c);
+        load_cell_values(values, p, r, z, c);
         const u32 status = edge_mask_of_case(cs);
+        u32 slot[12];
+        cell_edge_slots(entries, s, z, lbY, lbX, lbXY, S, slot);
+        const u64 word = tri_word(method, cs);
+        const u32 nt = (u32) (word >> 60);
+        u32 mask = 0, cnt = 0;
+        if (cell_is_plain(c, status, p)) {
+            // no crossing is near a cell corner: every LUT triangle is kept and every sign-change edge is used
+            // (the LUT rows use exactly the sign-change edges of their case: tools/gen_luts.py checks it)
+            mask = (1u << nt) - 1u;
+            cnt = nt;
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if ((status >> k) & 1u) used[slot[k]] = 1;
+        } else {
+        load_cell_positions(p, r, z, c);
         float ex[12], ey[12], ez[12];
 #pragma unroll
         for (int k = 0; k < 12; k++)
             if ((status >> k) & 1u) cell_edge_point(c, k, p.level, ex[k], ey[k], ez[k]);
-        u32 slot[12];
-        cell_edge_slots(entries, s, z, lbY, lbX, lbXY, S, slot);
-
-        const u64 word = tri_word(method, cs);
-        const u32 nt = (u32) (word >> 60);
-        u32 mask = 0, cnt = 0;
         for (u32 k = 0; k < nt; k++) {
             const u32 a = (u32) (word >> (12 * k)) & 15u, b = (u32) (word >> (12 * k + 4)) & 15u,
                       d = (u32) (word >> (12 * k + 8)) & 15u;
@@ -213,6 +223,7 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
                 used[slot[b]] = 1;
                 used[slot[d]] = 1;
             }
+        }
         }
         const u32 x = r / Y;
         const bool emit = x >= p.emit_lo && x < p.emit_hi;
@@ -447,6 +458,17 @@ int make_dense_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin,
         if (egx > 0 && egx <= 32) p.gx = (u32) egx;
     }
     p.ystep = (u32) ((Y + p.gy - 1) / p.gy);
+    {   // k_cell_tris fast path (dense.cuh: cell_is_plain): eps * cell = 16 ulp of the largest coordinate of the axis
+        const i64 res[3] = {Xg, Y, Z};
+        for (int a = 0; a < 3; a++) {
+            const double lo = p.g.amin[a], hi = (double) p.g.amin[a] + (double) p.g.asize[a];
+            const double big = fabs(lo) > fabs(hi) ? fabs(lo) : fabs(hi);
+            const double cell = res[a] > 1 ? fabs((double) p.g.asize[a]) / (double) (res[a] - 1) : 0.0;
+            double e2 = cell > 0.0 ? 2.0 * 16.0 * big * 1.1920928955078125e-7 / cell : 1.0;
+            if (!(e2 < 0.25)) e2 = 1.0;   // cells of a few ulp (or NaN boxes): every cell takes the exact path
+            p.eps2[a] = (float) e2;
+        }
+    }
     *out = p;
     return OK;
 }
