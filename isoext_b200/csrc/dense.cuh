@@ -321,46 +321,6 @@ struct SpanBits {
     bool hasX, hasY, last;        // last: this span ends the row (no z+1 neighbour for its last point)
 };
 
-// Loads the span's four rows from the shared-memory tile: plane 0 = rows [r0, r0+R], plane 1 = rows
-// [r0+Y, r0+Y+R] of the bit volume (spr uint4 per row), staged by k_compact128.
-__device__ __forceinline__ void span_load(const u32 *__restrict__ sm0, const u32 *__restrict__ sm1, const DenseParams &p, u32 r,
-                                          u32 rl, u32 x, u32 y, u32 c4, u32 spr, SpanBits &k) {
-    k.r = r;
-    k.z0 = c4 * 128u;
-    k.hasY = y + 1u < (u32) p.g.Y;
-    k.hasX = x + 1u < (u32) p.g.X;
-    k.last = c4 + 1u == spr;
-    const u32 wpr = spr * 4u;                 // words per row
-    const u32 o = rl * wpr + c4 * 4u;         // word offset of the span inside a plane of the tile
-    const uint4 A = *reinterpret_cast<const uint4 *>(sm0 + o);
-    k.a[0] = A.x; k.a[1] = A.y; k.a[2] = A.z; k.a[3] = A.w;
-    k.a[4] = k.last ? 0u : sm0[o + 4];
-    if (k.hasY) {
-        const uint4 B = *reinterpret_cast<const uint4 *>(sm0 + o + wpr);
-        k.b[0] = B.x; k.b[1] = B.y; k.b[2] = B.z; k.b[3] = B.w;
-        k.b[4] = k.last ? 0u : sm0[o + wpr + 4];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 5; j++) k.b[j] = k.a[j];
-    }
-    if (k.hasX) {
-        const uint4 Cc = *reinterpret_cast<const uint4 *>(sm1 + o);
-        k.c[0] = Cc.x; k.c[1] = Cc.y; k.c[2] = Cc.z; k.c[3] = Cc.w;
-        k.c[4] = k.last ? 0u : sm1[o + 4];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 5; j++) k.c[j] = k.a[j];
-    }
-    if (k.hasX && k.hasY) {
-        const uint4 D = *reinterpret_cast<const uint4 *>(sm1 + o + wpr);
-        k.d[0] = D.x; k.d[1] = D.y; k.d[2] = D.z; k.d[3] = D.w;
-        k.d[4] = k.last ? 0u : sm1[o + wpr + 4];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 5; j++) k.d[j] = k.hasX ? k.c[j] : (k.hasY ? k.b[j] : k.a[j]);
-    }
-}
-
 // true if some pair of the span's 4x129 sign bits differs (=> the span may own an entry)
 __device__ __forceinline__ bool span_mixed(const SpanBits &k) {
     u32 any = 0, all = 0xffffffffu;

@@ -9,7 +9,7 @@
 // face lying inside one slab) are sorted together by the global radix sort (radix.cuh); their
 // elements are already grouped by bucket in that sort's output because x decides the bucket.
 //
-//   k_seg_count    histogram of bucket ids
+//   (histogram of bucket ids: built by the caller while it scans its entries, mc_dense.cu k_scan_entries)
 //   k_seg_scan     exclusive scan of the histogram (one block), big-bucket bookkeeping
 //   k_seg_scatter  group candidate ids by bucket (order inside a bucket is irrelevant: it is sorted next);
 //                  elements of oversized buckets go straight to a compacted list of keys
@@ -88,21 +88,6 @@ struct SegScratch {
         if (out) *out = b;
     }
 };
-
-static __global__ void __launch_bounds__(256) k_seg_count(const u32 *__restrict__ cbucket, u32 n, u32 *__restrict__ count) {
-    const u32 lane = threadIdx.x & 31;
-    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
-        const u32 i = base + lane;
-        const bool valid = i < n;
-        const u32 active = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            // consecutive candidates mostly share a bucket: aggregate per warp before touching L2
-            const u32 b = cbucket[i];
-            const u32 peers = __match_any_sync(active, b);
-            if (lane == (u32) (__ffs(peers) - 1)) atomicAdd(&count[b], (u32) __popc(peers));
-        }
-    }
-}
 
 // Executed by ONE block (any blockDim that is a multiple of 32, <= 1024): exclusive scan over nb buckets
 // (SS_ITEMS consecutive buckets per thread); big buckets (> SEG_CAP) also get offsets in the compacted big
@@ -196,10 +181,6 @@ static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restric
             }
         }
     }
-}
-
-__device__ __forceinline__ bool key_less(u32 ax, u32 ay, u32 az, u32 bx, u32 by, u32 bz) {
-    return ax < bx || (ax == bx && (ay < by || (ay == by && az < bz)));
 }
 
 // One block per bucket (block-stride loop): LSD radix sort (8-bit digits) entirely in shared memory.

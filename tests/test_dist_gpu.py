@@ -73,6 +73,58 @@ def test_simulated_ranks_with_uneven_cuts(iso, name, cuts):
     assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf)
 
 
+def test_c3_2048_csg_two_slabs_equal_single_gpu():
+    """BASELINE.json configs[2] at FULL size on one GPU: the 2048^3 CSG field extracted whole and as two simulated
+    slabs with load-balanced cuts must agree bit for bit; the mesh is a closed genus-0 surface whose x-sorted
+    vertices all lie on the box or the sphere.  (The reference cannot represent this grid at all.)"""
+    import isoext_b200 as iso
+    from isoext_b200 import dist as idist
+    if torch.cuda.mem_get_info()[0] < 110e9:
+        pytest.skip("needs ~100 GB of free device memory")
+    n = 2048
+    fn = fields.csg_box_minus_sphere()
+    g = iso.UniformGrid([n] * 3)
+    ax = fields.axis(n).cuda()
+    vals = g.values_view()
+    for x0 in range(0, n, 16):
+        P = torch.stack(torch.meshgrid(ax[x0:x0 + 16], ax, ax, indexing="ij"), dim=-1)
+        vals[x0:x0 + 16] = fn(P)
+        del P
+    v, f = iso.marching_cubes(g)
+    # x-major sorted, strictly increasing lexicographically
+    a, b = v[:-1], v[1:]
+    lt = (a[:, 0] < b[:, 0]) | ((a[:, 0] == b[:, 0]) & ((a[:, 1] < b[:, 1]) | ((a[:, 1] == b[:, 1]) & (a[:, 2] < b[:, 2]))))
+    assert bool(lt.all())
+    del a, b, lt
+    # closed 2-manifold of genus 0: every edge in exactly two triangles, V - E + F = 2
+    f64 = f.long()
+    e = torch.cat([f64[:, [0, 1]], f64[:, [1, 2]], f64[:, [2, 0]]])
+    key = torch.minimum(e[:, 0], e[:, 1]) * len(v) + torch.maximum(e[:, 0], e[:, 1])
+    del e, f64
+    uniq, cnt = torch.unique(key, return_counts=True)
+    assert bool((cnt == 2).all()) and len(v) - len(uniq) + len(f) == 2
+    del key, uniq, cnt
+    # every vertex lies on the surface (linear interpolation of an exact SDF: within a fraction of a cell)
+    worst = 0.0
+    for i in range(0, len(v), 1 << 22):
+        worst = max(worst, float(fn(v[i:i + (1 << 22)]).abs().max()))
+    assert worst < 0.5 * 2.0 / (n - 1)
+    # two slabs with cuts balanced by the measured load
+    hist = idist.vertex_layer_histogram(v, n, -1.0, 1.0)
+    cuts = idist.balanced_cuts((2.6e-6 + 0.43e-9 * hist).tolist(), 2, ghost_cost=(0.43e-9 * hist).tolist())
+    parts = []
+    for r in range(2):
+        sg = idist.SlabGrid([n] * 3, rank=r, world=2, cuts=cuts)
+        p = sg.plan
+        sg._ext.copy_(vals[p["ext_lo"]:p["ext_hi"] + 1])
+        parts.append(idist.marching_cubes_local(sg))
+        del sg
+    idist.relabel_faces_(parts[0][1], parts[0][2], parts[0][3], 0, len(parts[0][0]))
+    idist.relabel_faces_(parts[1][1], parts[1][2], parts[1][3], len(parts[0][0]), len(parts[0][0]) + len(parts[1][0]))
+    assert torch.equal(torch.cat([parts[0][0], parts[1][0]]).view(torch.int32), v.view(torch.int32))
+    assert torch.equal(torch.cat([parts[0][1], parts[1][1]]), f)
+
+
 def _nccl_worker(rank, world, port, transport, field_name):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ISOEXT_B200_PEER="1" if transport == "peer" else "0")
     torch.cuda.set_device(rank)

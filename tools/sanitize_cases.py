@@ -22,6 +22,14 @@ for vals in (fields.eval_field(S.SphereSDF(0.5), (24, 24, 24)), fields.noise((9,
 g = dense(fields.eval_field(fields.csg_box_minus_sphere(), (40, 160, 128)))
 for _ in range(2): iso.marching_cubes(g)
 iso.dual_contouring(g)
+# second-level sort buckets (x-face inside one layer), the radix last resort (Z > 4096 on such a face) and a slanted sheet
+ax = [fields.axis(n) for n in (6, 96, 96)]; X, Y, Z = torch.meshgrid(*ax, indexing="ij")
+for vals in ((X - 0.13).contiguous(), (X + 0.013 * Y + 0.007 * Z - 0.05).contiguous()):
+    g = dense(vals)
+    for _ in range(3): iso.marching_cubes(g)
+ax = [fields.axis(n) for n in (5, 3, 9000)]; X, Y, Z = torch.meshgrid(*ax, indexing="ij")
+g = dense((X - 0.13).contiguous())
+for _ in range(3): iso.marching_cubes(g)
 # slabs
 vals = fields.eval_field(S.CuboidSDF([1, 1, 1]), (33, 20, 24)).cuda()
 for r in range(3):
