@@ -183,6 +183,25 @@ static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restric
     }
 }
 
+// Grid facts the sort uses: plane positions along x and y and how the first-level buckets were cut (mc_dense.cu
+// sub_bucket): bucket id = layer * (gy + gx) + sub, layer = local x plane + 1 (x_off = global index of local plane 0).
+struct SegGeom {
+    float amin_x, asize_x, amin_y, asize_y;
+    u32 Xg, Y;           // global points along x, points along y
+    i64 x_off;
+    u32 gy, gx, ystep;
+    bool grouped;        // the group stage of k_seg_sort is usable (ystep + 2 <= SEG_GROUPS)
+};
+// index of the last y plane at or below y (0 if y is below all planes): exact float compares, monotone in y
+__device__ __forceinline__ u32 yplane_of(float y, const SegGeom &g) {
+    const u32 res = g.Y - 1;
+    float f = __fdiv_rn(__fsub_rn(y, g.amin_y), g.asize_y) * (float) res;
+    int j = f > 0.f ? (f < (float) res ? (int) f : (int) res) : 0;
+    while (j > 0 && axis_pos((u32) j, res, g.amin_y, g.asize_y) > y) j--;
+    while (j < (int) res && axis_pos((u32) j + 1, res, g.amin_y, g.asize_y) <= y) j++;
+    return (u32) j;
+}
+
 // One block per bucket (block-stride loop): LSD radix sort (8-bit digits) entirely in shared memory.
 //   keys stay in place (sk[3][CAP]); only 16-bit local indices move (ord ping-pong);
 //   ranking is stable: each warp owns a contiguous run of positions, ranks 32 of them at a time with
@@ -190,14 +209,22 @@ static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restric
 //   digit places on which all keys of the bucket agree (typically the high bytes of x) are skipped.
 // Two instances by bucket size: <SEG_SMALL, 128> (25 KB, 8 blocks/SM) and <SEG_CAP, 512> (96 KB, 2 blocks/SM).
 // (A third <2048, 256> instance was measured slower overall: 209 vs 181 us at 1024^3.)
+// Group stage (first level only), tried before the radix passes: inside a bucket all keys share x exactly (vertices
+// lying on an x plane) or are spread in x (vertices inside a layer), so a fine monotone index -- the y-plane index
+// resp. 1/1024 of the layer thickness -- cuts the bucket into groups of a handful of elements: ONE counting pass in
+// shared memory, then every element finds its rank inside its group by comparing full keys (O(group size) each).  If some group is larger than
+// SEG_GROUP_MAX (a face inside the bucket) the radix passes run instead.
 constexpr int SEG_SMALL = 1024;
+constexpr int SEG_GROUPS = 1026;     // group ids 0 .. SEG_GROUPS-1
+constexpr int SEG_GROUP_MAX = 192;
 template <int CAP, int THREADS>
 struct SegCfg {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int CHUNKS = CAP / THREADS;          // 32-element chunks per warp at full capacity
+    static constexpr int CNT_WORDS = WARPS * 256 > SEG_GROUPS + 2 ? WARPS * 256 : SEG_GROUPS + 2;   // digit counters / group table
     static constexpr size_t SMEM = (size_t) CAP * 4 * 4       // sk[3] + ids
                                    + (size_t) CAP * 2 * 2     // ord[2] (u16)
-                                   + (size_t) WARPS * 256 * 4 // cnt
+                                   + (size_t) CNT_WORDS * 4   // cnt
                                    + (256 + 64) * 4;          // digit bases + vary + scan scratch
 };
 
@@ -213,6 +240,7 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
                                                              const u32 *__restrict__ start, const u32 *__restrict__ perm0,
                                                              u32 *__restrict__ perm, u32 *__restrict__ skx, u32 *__restrict__ sky,
                                                              u32 *__restrict__ skz, const u32 *__restrict__ n_dev, u32 n_cap, u32 nb,
+                                                             SegGeom geom,
                                                              SegLevel2 l2 = SegLevel2{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}) {
     constexpr int WARPS = SegCfg<CAP, THREADS>::WARPS, CHUNKS = SegCfg<CAP, THREADS>::CHUNKS;
     extern __shared__ u32 smem[];
@@ -224,8 +252,8 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
     u32 *sk = smem;                                   // [3][CAP]: z, y, x keys (LSD order)
     u32 *ids = smem + 3 * CAP;                        // [CAP]
     unsigned short *ord = reinterpret_cast<unsigned short *>(smem + 4 * CAP);   // [2][CAP]
-    u32 *cnt = smem + 5 * CAP;                        // [WARPS][256]
-    u32 *dbase = cnt + WARPS * 256;                   // [256]
+    u32 *cnt = smem + 5 * CAP;                        // [WARPS][256] digit counters; group table of the group stage
+    u32 *dbase = cnt + SegCfg<CAP, THREADS>::CNT_WORDS;   // [256]
     u32 *vary = dbase + 256;                          // [3] OR of (key ^ key[0]) per coordinate
     u32 *sw = vary + 4;                               // [33] scan scratch
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -269,18 +297,103 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
             if (lane == 0) { atomicOr(&vary[0], vz); atomicOr(&vary[1], vy); atomicOr(&vary[2], vx); }
         }
         __syncthreads();
+        u32 cur = 0;
+        bool grouped = false;
+        if (!LEVEL2 && geom.grouped && b >= geom.gy + geom.gx) {   // (layer 0 = below the first plane: radix passes)
+            const u32 nsub = geom.gy + geom.gx;
+            const u32 L = b / nsub, sub = b - L * nsub;
+            const u32 xb = (u32) ((i64) L - 1 + geom.x_off);    // global index of the layer's lower plane
+            u32 *gtab = cnt;                                    // [SEG_GROUPS + 1]: counts -> starts -> ends
+            unsigned short *gid = ord + CAP;                    // group of every element (second half of ord as temp)
+            for (u32 i = tid; i < (u32) SEG_GROUPS + 2; i += THREADS) gtab[i] = 0;
+            if (tid == 0) vary[3] = 0;
+            __syncthreads();
+            if (sub < geom.gy) {          // all keys share x: groups by y plane
+                const int j0 = (int) (sub * geom.ystep) - 1;
+                for (u32 i = tid; i < n; i += THREADS) {
+                    int g = (int) yplane_of(key_float(sk[CAP + i]), geom) - j0;
+                    g = g < 0 ? 0 : (g > SEG_GROUPS - 1 ? SEG_GROUPS - 1 : g);
+                    gid[i] = (unsigned short) g;
+                    atomicAdd(&gtab[g], 1u);
+                }
+            } else {                      // keys spread in x inside the layer: groups uniform in x
+                const float pb = axis_pos(xb, geom.Xg - 1, geom.amin_x, geom.asize_x);
+                const float pb1 = axis_pos(xb + 1, geom.Xg - 1, geom.amin_x, geom.asize_x);
+                const float scale = __fdiv_rn((float) (SEG_GROUPS - 1), __fsub_rn(pb1, pb));
+                for (u32 i = tid; i < n; i += THREADS) {
+                    const float f = __fmul_rn(__fsub_rn(key_float(sk[2 * CAP + i]), pb), scale);
+                    u32 g = f > 0.f ? (u32) f : 0u;
+                    g = g > (u32) SEG_GROUPS - 1 ? (u32) SEG_GROUPS - 1 : g;
+                    gid[i] = (unsigned short) g;
+                    atomicAdd(&gtab[g], 1u);
+                }
+            }
+            __syncthreads();
+            {   // exclusive scan of the group counts (consecutive groups per thread), largest group
+                constexpr int GPT = (SEG_GROUPS + THREADS - 1) / THREADS;
+                u32 c[GPT], sum = 0, mx = 0;
+#pragma unroll
+                for (int q = 0; q < GPT; q++) {
+                    const u32 g = tid * GPT + q;
+                    c[q] = g < (u32) SEG_GROUPS ? gtab[g] : 0u;
+                    sum += c[q];
+                    mx = c[q] > mx ? c[q] : mx;
+                }
+                if (mx > (u32) SEG_GROUP_MAX) vary[3] = 1;      // benign race: every writer stores 1
+                u32 total;
+                u32 ex = block_exclusive_scan(sum, &total, sw);
+#pragma unroll
+                for (int q = 0; q < GPT; q++) {
+                    const u32 g = tid * GPT + q;
+                    if (g < (u32) SEG_GROUPS) gtab[g] = ex;
+                    ex += c[q];
+                }
+            }
+            __syncthreads();
+            grouped = vary[3] == 0;
+            if (grouped) {
+                for (u32 i = tid; i < n; i += THREADS) ord[atomicAdd(&gtab[gid[i]], 1u)] = (unsigned short) i;   // gtab: starts -> ends
+                __syncthreads();
+                // rank of every element inside its group on the full key (ties cannot occur between different elements
+                // other than exact duplicates, which are ordered by their slot): O(group size) per element, all threads busy
+                u32 dst[CHUNKS];
+#pragma unroll
+                for (int q = 0; q < CHUNKS; q++) {
+                    const u32 i = tid + (u32) q * THREADS;
+                    dst[q] = 0xffffffffu;
+                    if (i < n) {
+                        const u32 g = gid[i];
+                        const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
+                        const u32 x = sk[2 * CAP + i], y = sk[CAP + i], z = sk[i];
+                        u32 r = 0;
+                        for (u32 j = s1; j < e1; j++) {
+                            const u32 lj = ord[j];
+                            const u32 xj = sk[2 * CAP + lj], yj = sk[CAP + lj], zj = sk[lj];
+                            const bool before = xj < x || (xj == x && (yj < y || (yj == y && (zj < z || (zj == z && lj < i)))));
+                            r += before ? 1u : 0u;
+                        }
+                        dst[q] = s1 + r;
+                    }
+                }
+                __syncthreads();          // everybody has read ord (group order) and gid
+#pragma unroll
+                for (int q = 0; q < CHUNKS; q++)
+                    if (dst[q] != 0xffffffffu) gid[dst[q]] = (unsigned short) (tid + (u32) q * THREADS);   // second half of ord = result
+                cur = 1;
+            }
+            __syncthreads();
+        }
         // contiguous run of positions per warp, a multiple of 32
         const u32 run = ((n + WARPS - 1) / WARPS + 31) & ~31u;
         const u32 nchunks = run >> 5;                     // <= CHUNKS
         const u32 wbase = warp * run;
-        u32 cur = 0;
-        for (int pass = 0; pass < 12; pass++) {
+        for (int pass = 0; pass < (grouped ? 0 : 12); pass++) {
             const u32 c = pass >> 2, shift = 8 * (pass & 3);
             if (((vary[c] >> shift) & 255u) == 0) continue;   // all keys agree on this digit
             const u32 *key = sk + c * CAP;
             const unsigned short *oin = ord + cur * CAP;
             unsigned short *oout = ord + (cur ^ 1) * CAP;
-            for (u32 i = tid; i < WARPS * 256; i += THREADS) cnt[i] = 0;
+            for (u32 i = tid; i < (u32) WARPS * 256; i += THREADS) cnt[i] = 0;
             __syncthreads();
             u32 packed[CHUNKS];                           // local index | digit << 16
             u32 rnk[CHUNKS];
@@ -436,20 +549,6 @@ static __global__ void __launch_bounds__(1024) k_big_plan(u32 nb, const u32 *__r
     }
 }
 
-struct SegGeom {   // what the second level needs to know about the grid: y-plane positions
-    float amin_y, asize_y;
-    u32 Y;
-};
-// index of the last y plane at or below y (0 if y is below all planes): exact float compares, monotone in y
-__device__ __forceinline__ u32 yplane_of(float y, const SegGeom &g) {
-    const u32 res = g.Y - 1;
-    float f = __fdiv_rn(__fsub_rn(y, g.amin_y), g.asize_y) * (float) res;
-    int j = f > 0.f ? (f < (float) res ? (int) f : (int) res) : 0;
-    while (j > 0 && axis_pos((u32) j, res, g.amin_y, g.asize_y) > y) j--;
-    while (j < (int) res && axis_pos((u32) j + 1, res, g.amin_y, g.asize_y) <= y) j++;
-    return (u32) j;
-}
-
 static __global__ void __launch_bounds__(256) k_big_sub(u32 n_big, const u32 *__restrict__ nbig_dev, const u32 *__restrict__ bkx,
                                                         const u32 *__restrict__ bky, const u32 *__restrict__ bid,
                                                         const u32 *__restrict__ cbucket, const u32 *__restrict__ xinvmin,
@@ -534,9 +633,9 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
                nullptr, big);
     const u32 grid_small = nb < 148u * 32u ? nb : 148u * 32u, grid_large = nb < 148u * 8u ? nb : 148u * 8u;
     ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
-               b.skx, b.sky, b.skz, n_dev, n_cap, nb);
+               b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
     ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>), grid_large, SEG_THREADS, smem_big, stream, kx, ky, kz, h.count,
-               h.start, b.perm0, b.perm, b.skx, b.sky, b.skz, n_dev, n_cap, nb);
+               h.start, b.perm0, b.perm, b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
     const u32 fb_n = nbig_dev ? big_cap : n_big;
     if (fb_n > 0) {
         // second level inside the oversized buckets
@@ -556,9 +655,9 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         const SegLevel2 l2{b.bid, b.cbucket, h.start, h.bigoff, b.info2 + 5, b.info2};
         const u32 g2s = nb2 < 148u * 32u ? nb2 : 148u * 32u, g2l = nb2 < 148u * 8u ? nb2 : 148u * 8u;
         ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1, true>), g2s, 128, smem_small, stream, b.bkx, b.bky, b.bkz, count2, start2, b.perm2, b.perm,
-                   b.skx, b.sky, b.skz, nullptr, 0u, nb2, l2);
+                   b.skx, b.sky, b.skz, nullptr, 0u, nb2, geom, l2);
         ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1, true>), g2l, SEG_THREADS, smem_big, stream, b.bkx, b.bky, b.bkz, count2,
-                   start2, b.perm2, b.perm, b.skx, b.sky, b.skz, nullptr, 0u, nb2, l2);
+                   start2, b.perm2, b.perm, b.skx, b.sky, b.skz, nullptr, 0u, nb2, geom, l2);
         // last resort: a second-level bucket is still oversized (info2[4] != 0): global radix sort of the big list.
         // 14 launches that do nothing in the common case, so the single-sync path only enqueues them when the
         // previous extraction of the grid needed them (*radix_needed tells the host)
