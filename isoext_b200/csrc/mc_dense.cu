@@ -546,7 +546,8 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
                s.seg.cbucket, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg,
-                          SegGeom{p.g.amin[0], p.g.asize[0], p.g.amin[1], p.g.asize[1], (u32) p.g.Xg, (u32) p.g.Y, p.g.x_off, p.gy, p.gx, p.ystep,
+                          SegGeom{p.g.amin[0], p.g.asize[0], p.g.amin[1], p.g.asize[1], p.g.amin[2], p.g.asize[2], (u32) p.g.Xg, (u32) p.g.Y,
+                                  (u32) p.g.Z, p.g.x_off, p.gy, p.gx, p.ystep,
                                   p.ystep + 2 <= (u32) SEG_GROUPS && !getenv("ISX_SORT_NO_GROUPS")},
                           allow_radix, b.counters + C_RADIX, stream));
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);

@@ -186,21 +186,21 @@ static __global__ void __launch_bounds__(256) k_seg_scatter(const u32 *__restric
 // Grid facts the sort uses: plane positions along x and y and how the first-level buckets were cut (mc_dense.cu
 // sub_bucket): bucket id = layer * (gy + gx) + sub, layer = local x plane + 1 (x_off = global index of local plane 0).
 struct SegGeom {
-    float amin_x, asize_x, amin_y, asize_y;
-    u32 Xg, Y;           // global points along x, points along y
+    float amin_x, asize_x, amin_y, asize_y, amin_z, asize_z;
+    u32 Xg, Y, Z;        // global points along x, points along y and z
     i64 x_off;
     u32 gy, gx, ystep;
     bool grouped;        // the group stage of k_seg_sort is usable (ystep + 2 <= SEG_GROUPS)
 };
-// index of the last y plane at or below y (0 if y is below all planes): exact float compares, monotone in y
-__device__ __forceinline__ u32 yplane_of(float y, const SegGeom &g) {
-    const u32 res = g.Y - 1;
-    float f = __fdiv_rn(__fsub_rn(y, g.amin_y), g.asize_y) * (float) res;
+// index of the last plane at or below v along an axis (0 if v is below all planes): exact float compares, monotone in v
+__device__ __forceinline__ u32 plane_index(float v, float amin, float asize, u32 res) {
+    float f = __fdiv_rn(__fsub_rn(v, amin), asize) * (float) res;
     int j = f > 0.f ? (f < (float) res ? (int) f : (int) res) : 0;
-    while (j > 0 && axis_pos((u32) j, res, g.amin_y, g.asize_y) > y) j--;
-    while (j < (int) res && axis_pos((u32) j + 1, res, g.amin_y, g.asize_y) <= y) j++;
+    while (j > 0 && axis_pos((u32) j, res, amin, asize) > v) j--;
+    while (j < (int) res && axis_pos((u32) j + 1, res, amin, asize) <= v) j++;
     return (u32) j;
 }
+__device__ __forceinline__ u32 yplane_of(float y, const SegGeom &g) { return plane_index(y, g.amin_y, g.asize_y, g.Y - 1); }
 
 // One block per bucket (block-stride loop): LSD radix sort (8-bit digits) entirely in shared memory.
 //   keys stay in place (sk[3][CAP]); only 16-bit local indices move (ord ping-pong);
@@ -212,11 +212,14 @@ __device__ __forceinline__ u32 yplane_of(float y, const SegGeom &g) {
 // Group stage (first level only), tried before the radix passes: inside a bucket all keys share x exactly (vertices
 // lying on an x plane) or are spread in x (vertices inside a layer), so a fine monotone index -- the y-plane index
 // resp. 1/1024 of the layer thickness -- cuts the bucket into groups of a handful of elements: ONE counting pass in
-// shared memory, then every element finds its rank inside its group by comparing full keys (O(group size) each).  If some group is larger than
-// SEG_GROUP_MAX (a face inside the bucket) the radix passes run instead.
+// shared memory, then every element finds its rank inside its group by comparing full keys (O(group size) each).
+// A group larger than SEG_GROUP_MAX is a face row inside the bucket; if all its keys share (x, y) exactly -- the
+// axis-aligned case -- the <SEG_CAP> instance cuts it once more by z-plane index (a second counting pass) and ranks
+// inside those pieces.  Anything else (or more than SEG_LARGE_MAX such groups) falls back to the radix passes.
 constexpr int SEG_SMALL = 1024;
 constexpr int SEG_GROUPS = 1026;     // group ids 0 .. SEG_GROUPS-1
 constexpr int SEG_GROUP_MAX = 192;
+constexpr int SEG_LARGE_MAX = 8;      // large groups handled per bucket by the nested z stage
 template <int CAP, int THREADS>
 struct SegCfg {
     static constexpr int WARPS = THREADS / 32;
@@ -235,7 +238,7 @@ struct SegLevel2 {
 };
 
 template <int CAP, int THREADS, int MIN_N, bool LEVEL2 = false>
-static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
+static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_sort(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                              const u32 *__restrict__ kz, const u32 *__restrict__ count,
                                                              const u32 *__restrict__ start, const u32 *__restrict__ perm0,
                                                              u32 *__restrict__ perm, u32 *__restrict__ skx, u32 *__restrict__ sky,
@@ -350,8 +353,15 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
                 }
             }
             __syncthreads();
-            grouped = vary[3] == 0;
+            // nested z stage available?  (needs room for one counter per z plane behind the group table)
+            constexpr u32 ZCAP = (u32) SegCfg<CAP, THREADS>::CNT_WORDS > (u32) SEG_GROUPS + 2 + 64
+                                     ? (u32) SegCfg<CAP, THREADS>::CNT_WORDS - ((u32) SEG_GROUPS + 2) : 0u;
+            const bool nested_ok = ZCAP > 0 && geom.Z + 1 <= ZCAP;
+            grouped = vary[3] == 0 || nested_ok;
             if (grouped) {
+                u32 *zc = cnt + SEG_GROUPS + 2;                 // [Z + 1] z-plane counters of one large group
+                u32 *s_nl = dbase, *s_lg = dbase + 1, *s_bad = dbase + 1 + SEG_LARGE_MAX;   // dbase is free outside the radix passes
+                if (tid == 0) { *s_nl = 0; *s_bad = 0; }
                 for (u32 i = tid; i < n; i += THREADS) ord[atomicAdd(&gtab[gid[i]], 1u)] = (unsigned short) i;   // gtab: starts -> ends
                 __syncthreads();
                 // rank of every element inside its group on the full key (ties cannot occur between different elements
@@ -364,6 +374,7 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
                     if (i < n) {
                         const u32 g = gid[i];
                         const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
+                        if (e1 - s1 > (u32) SEG_GROUP_MAX) continue;   // member of a large group: nested stage below
                         const u32 x = sk[2 * CAP + i], y = sk[CAP + i], z = sk[i];
                         u32 r = 0;
                         for (u32 j = s1; j < e1; j++) {
@@ -375,11 +386,104 @@ static __global__ void __launch_bounds__(THREADS) k_seg_sort(const u32 *__restri
                         dst[q] = s1 + r;
                     }
                 }
-                __syncthreads();          // everybody has read ord (group order) and gid
+                if (vary[3]) {   // list the large groups
+                    for (u32 g = tid; g < (u32) SEG_GROUPS; g += THREADS) {
+                        const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
+                        if (e1 - s1 > (u32) SEG_GROUP_MAX) {
+                            const u32 k = atomicAdd(s_nl, 1u);
+                            if (k < (u32) SEG_LARGE_MAX) s_lg[k] = g;
+                        }
+                    }
+                }
+                __syncthreads();          // everybody has read ord (group order) and gid: the second half of ord is free
+                const u32 nl = *s_nl;
+                if (nl > (u32) SEG_LARGE_MAX) grouped = false;
+                for (u32 t = 0; grouped && t < nl; t++) {
+                    const u32 g = s_lg[t];
+                    const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
+                    for (u32 i = tid; i < geom.Z + 1; i += THREADS) zc[i] = 0;
+                    __syncthreads();
+                    // (x, y) constant over the group?  z-plane index of every member
+                    const u32 l0 = ord[s1];
+                    const u32 x0 = sk[2 * CAP + l0], y0 = sk[CAP + l0];
+                    u32 lq[CHUNKS], hq[CHUNKS];
 #pragma unroll
-                for (int q = 0; q < CHUNKS; q++)
-                    if (dst[q] != 0xffffffffu) gid[dst[q]] = (unsigned short) (tid + (u32) q * THREADS);   // second half of ord = result
-                cur = 1;
+                    for (int q = 0; q < CHUNKS; q++) {
+                        const u32 j = s1 + tid + (u32) q * THREADS;
+                        lq[q] = 0xffffffffu;
+                        hq[q] = 0;
+                        if (j < e1) {
+                            const u32 li = ord[j];
+                            if (sk[2 * CAP + li] != x0 || sk[CAP + li] != y0) *s_bad = 1;
+                            const float zf = key_float(sk[li]);
+                            // planes 0..Z-1 -> 1..Z; below the first plane (or NaN) -> 0
+                            u32 h = plane_index(zf, geom.amin_z, geom.asize_z, geom.Z - 1) + 1;
+                            if (!(axis_pos(0u, geom.Z - 1, geom.amin_z, geom.asize_z) <= zf)) h = 0;
+                            lq[q] = li;
+                            hq[q] = h;
+                            atomicAdd(&zc[h], 1u);
+                        }
+                    }
+                    __syncthreads();
+                    if (*s_bad) { grouped = false; break; }
+                    {   // exclusive scan of the z-plane counters
+                        constexpr int ZPT = (int) ((ZCAP + THREADS - 1) / THREADS) > 0 ? (int) ((ZCAP + THREADS - 1) / THREADS) : 1;
+                        u32 c[ZPT], sum = 0;
+#pragma unroll
+                        for (int q = 0; q < ZPT; q++) {
+                            const u32 k = tid * ZPT + q;
+                            c[q] = k < geom.Z + 1 ? zc[k] : 0u;
+                            sum += c[q];
+                        }
+                        u32 total;
+                        u32 ex = block_exclusive_scan(sum, &total, sw);
+#pragma unroll
+                        for (int q = 0; q < ZPT; q++) {
+                            const u32 k = tid * ZPT + q;
+                            if (k < geom.Z + 1) zc[k] = ex;
+                            ex += c[q];
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int q = 0; q < CHUNKS; q++)
+                        if (lq[q] != 0xffffffffu) {
+                            const u32 pos = s1 + atomicAdd(&zc[hq[q]], 1u);      // zc: starts -> ends
+                            ord[pos] = (unsigned short) lq[q];
+                            gid[pos] = (unsigned short) hq[q];
+                        }
+                    __syncthreads();
+                    u32 pq[CHUNKS];
+#pragma unroll
+                    for (int q = 0; q < CHUNKS; q++) {
+                        const u32 j = s1 + tid + (u32) q * THREADS;
+                        pq[q] = 0xffffffffu;
+                        if (j < e1) {
+                            const u32 li = ord[j], h = gid[j];
+                            const u32 a0 = s1 + (h ? zc[h - 1] : 0u), a1 = s1 + zc[h];
+                            const u32 z = sk[li];
+                            u32 r = 0;
+                            for (u32 k = a0; k < a1; k++) {
+                                const u32 lk = ord[k];
+                                const u32 zk = sk[lk];
+                                r += (zk < z || (zk == z && lk < li)) ? 1u : 0u;     // x and y are equal throughout
+                            }
+                            pq[q] = a0 + r;
+                            lq[q] = li;
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int q = 0; q < CHUNKS; q++)
+                        if (pq[q] != 0xffffffffu) gid[pq[q]] = (unsigned short) lq[q];   // result, second half of ord
+                    __syncthreads();
+                }
+                if (grouped) {
+#pragma unroll
+                    for (int q = 0; q < CHUNKS; q++)
+                        if (dst[q] != 0xffffffffu) gid[dst[q]] = (unsigned short) (tid + (u32) q * THREADS);   // second half of ord = result
+                    cur = 1;
+                }
             }
             __syncthreads();
         }
