@@ -7,7 +7,9 @@ One "step" = one pass of the hot path (marching_cubes, default LUT method "nagae
 synthetic analytic field:
   N = 1  : BASELINE.json configs[1], 512^3 dense torus SDF (R=.5, r=.2) on [-1,1]^3      ("c2")
   N > 1  : BASELINE.json configs[2], 2048^3 CSG box-minus-sphere, slab-sharded on dim 0      ("c3")
-           one process per GPU (torchrun), NVLink halo exchange + count all-gather; strong scaling.
+           one process per GPU (torchrun), halo pull + vertex-id bases as kernels over NVLink peer memory, slab cuts
+           balanced by measured load; strong scaling.  The N = 1 line also carries "scaling_base": the same c3
+           workload timed on the single GPU, so that 1 -> N comparisons have a same-workload base.
 Metric: Gvoxels/s = X*Y*Z / t / 1e9 (whole job).  `value` is timed with the field resident in HBM
 (CUDA events, max over ranks); `e2e` goes through the public API from pinned HOST memory, H2D copy of
 the field and D2H read of the mesh inside the timed region.  Inputs (537 MB / 34 GB) are larger than
@@ -319,6 +321,32 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port()
+        if world == 1 and wl_name == "c2" and not args.no_scaling_base:
+            # The N > 1 lines run c3 (2048^3 CSG, BASELINE.json configs[2], "sharded at 1/2/4/8 B200"): time the same
+            # workload on this single GPU as well, so that a 1 -> N comparison has a same-workload base.
+            try:
+                del vals, grid, grid2, dbuf, host
+                torch.cuda.empty_cache()
+                n3 = WORKLOADS["c3"]["n"]
+                g3 = iso.UniformGrid([n3] * 3)
+                view = g3.values_view()
+                fn3 = field_fn(WORKLOADS["c3"]["field"])
+                for a in range(0, n3, 64):
+                    view[a:a + 64] = build_field_gpu(fn3, n3, a, min(n3, a + 64), dev)
+                for _ in range(3):
+                    iso.marching_cubes(g3)
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(5):
+                    iso.marching_cubes(g3)
+                s1.record()
+                torch.cuda.synchronize()
+                ms3 = s0.elapsed_time(s1) / 5
+                line["scaling_base"] = {"workload": "c3: " + WORKLOADS["c3"]["desc"] + " on this single GPU (the N > 1 lines run c3)",
+                                        "value": float(n3) ** 3 / (ms3 * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms3, "steps": 5}
+            except Exception as exc:   # e.g. a GPU with less memory: the headline line must still be printed
+                line["scaling_base"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         sg.close()
@@ -397,6 +425,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--even-slabs", action="store_true", help="N > 1: keep the even dim-0 split (default: cuts balanced by measured load)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-base", action="store_true", help="N = 1: skip the extra c3 timing on one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
