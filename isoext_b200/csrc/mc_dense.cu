@@ -326,54 +326,110 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
 // ---------------------------------------------------------------------------------------------
 // K5: positions (as sortable keys) of the used edge slots, computed once by the owning entry.
 // ---------------------------------------------------------------------------------------------
+// Where the candidates go: straight to their place in the bucket-grouped arrays of the segmented sort (the bucket
+// offsets were scanned in phase 1), so no separate scatter pass and the sort reads its keys contiguously.  Elements of
+// oversized buckets go to the compacted big list instead and feed the x range of their bucket (segsort.cuh).
+struct CandOut {
+    u32 *gkx, *gky, *gkz, *gid;        // grouped by bucket: keys + candidate id
+    u32 *cbucket;                      // bucket of every candidate (candidate order)
+    const u32 *count, *start, *bigoff;
+    u32 *cursor;
+    u32 *bkx, *bky, *bkz, *bid, *xinvmin, *xmax;
+};
+// executed by all 32 lanes; `has` = this lane emits a candidate
+__device__ __forceinline__ void emit_candidate(bool has, u32 b, u32 id, u32 kxv, u32 kyv, u32 kzv, const CandOut &o) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 act = __ballot_sync(0xffffffffu, has);
+    if (!has) return;
+    const u32 peers = __match_any_sync(act, b);
+    const u32 leader = __ffs(peers) - 1;
+    u32 off = 0;
+    if (lane == leader) off = atomicAdd(&o.cursor[b], (u32) __popc(peers));
+    off = __shfl_sync(peers, off, leader) + __popc(peers & ((1u << lane) - 1u));
+    o.cbucket[id] = b;
+    if (o.count[b] > (u32) SEG_CAP) {
+        const u32 q = o.bigoff[b] + off;
+        o.bkx[q] = kxv; o.bky[q] = kyv; o.bkz[q] = kzv; o.bid[q] = id;
+        const u32 mx = __reduce_max_sync(peers, kxv), mn = __reduce_max_sync(peers, ~kxv);
+        if (lane == leader) {
+            atomicMax(&o.xmax[b], mx);
+            atomicMax(&o.xinvmin[b], mn);
+        }
+    } else {
+        const u32 q = o.start[b] + off;
+        o.gkx[q] = kxv; o.gky[q] = kyv; o.gkz[q] = kzv; o.gid[q] = id;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
                                                   const u32 *__restrict__ cand_info, const u32 *__restrict__ bdelta,
-                                                  u32 *__restrict__ kx, u32 *__restrict__ ky, u32 *__restrict__ kz,
-                                                  u32 *__restrict__ cbucket, u32 cand_cap, u32 entry_cap) {
+                                                  CandOut out, u32 cand_cap, u32 entry_cap) {
     const u32 S = counters[C_S];
     if (S > entry_cap || counters[C_VC] > cand_cap) return;   // single-call fast path: the host re-runs with larger buffers
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, nsub = sort_nsub(p);
-    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-        const u32 ci = cand_info[s];
+    const u32 lane = threadIdx.x & 31;
+    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < S; base += gridDim.x * blockDim.x) {   // warp-uniform
+        const u32 s = base + lane;
+        const u32 ci = s < S ? cand_info[s] : 0u;
         const u32 um = ci >> 29;
-        if (!um) continue;
+        if (!__any_sync(0xffffffffu, um != 0u)) continue;
         u32 id = ci & 0x1fffffffu;
-        const uint2 e = entries[s];
-        const u32 r = e.x, z = ent_z(e.y);
-        const u32 x = r / Y, y = r - x * Y;
-        const i64 n = (i64) r * Z + z;
-        const float v0 = __ldg(values + n);
-        const u32 xg = x + (u32) p.g.x_off;
-        const u32 bd = bdelta[s];
-        const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
-        const float py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
-        const float pz0 = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
-        if (um & 1u) {   // +z edge
-            const float t = edge_t(v0, __ldg(values + n + 1), p.level);
-            const float pz1 = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
-            kx[id] = float_key(lerp_ref(t, px0, px0));
-            ky[id] = float_key(lerp_ref(t, py0, py0));
-            kz[id] = float_key(lerp_ref(t, pz0, pz1));
-            cbucket[id] = bucket_of(x, bd, nsub);
-            id++;
+        u32 x = 0, bd = 0;
+        float v0 = 0.f, px0 = 0.f, py0 = 0.f, pz0 = 0.f;
+        i64 n = 0;
+        u32 y = 0, z = 0, xg = 0;
+        if (um) {
+            const uint2 e = entries[s];
+            const u32 r = e.x;
+            z = ent_z(e.y);
+            x = r / Y;
+            y = r - x * Y;
+            n = (i64) r * Z + z;
+            v0 = __ldg(values + n);
+            xg = x + (u32) p.g.x_off;
+            bd = bdelta[s];
+            px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+            py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
+            pz0 = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
         }
-        if (um & 2u) {   // +y edge
-            const float t = edge_t(v0, __ldg(values + n + Z), p.level);
-            const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
-            kx[id] = float_key(lerp_ref(t, px0, px0));
-            ky[id] = float_key(lerp_ref(t, py0, py1));
-            kz[id] = float_key(lerp_ref(t, pz0, pz0));
-            cbucket[id] = bucket_of(x, bd >> 8, nsub);
-            id++;
+        {   // +z edge
+            const bool has = um & 1u;
+            u32 a = 0, b2 = 0, c = 0;
+            if (has) {
+                const float t = edge_t(v0, __ldg(values + n + 1), p.level);
+                const float pz1 = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
+                a = float_key(lerp_ref(t, px0, px0));
+                b2 = float_key(lerp_ref(t, py0, py0));
+                c = float_key(lerp_ref(t, pz0, pz1));
+            }
+            emit_candidate(has, bucket_of(x, bd, nsub), id, a, b2, c, out);
+            if (has) id++;
         }
-        if (um & 4u) {   // +x edge
-            const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
-            const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
-            kx[id] = float_key(lerp_ref(t, px0, px1));
-            ky[id] = float_key(lerp_ref(t, py0, py0));
-            kz[id] = float_key(lerp_ref(t, pz0, pz0));
-            cbucket[id] = bucket_of(x, bd >> 16, nsub);
+        {   // +y edge
+            const bool has = um & 2u;
+            u32 a = 0, b2 = 0, c = 0;
+            if (has) {
+                const float t = edge_t(v0, __ldg(values + n + Z), p.level);
+                const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
+                a = float_key(lerp_ref(t, px0, px0));
+                b2 = float_key(lerp_ref(t, py0, py1));
+                c = float_key(lerp_ref(t, pz0, pz0));
+            }
+            emit_candidate(has, bucket_of(x, bd >> 8, nsub), id, a, b2, c, out);
+            if (has) id++;
+        }
+        {   // +x edge
+            const bool has = um & 4u;
+            u32 a = 0, b2 = 0, c = 0;
+            if (has) {
+                const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
+                const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
+                a = float_key(lerp_ref(t, px0, px1));
+                b2 = float_key(lerp_ref(t, py0, py0));
+                c = float_key(lerp_ref(t, pz0, pz0));
+            }
+            emit_candidate(has, bucket_of(x, bd >> 16, nsub), id, a, b2, c, out);
         }
     }
 }
@@ -542,8 +598,9 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const int sms = device_sms();
     const u32 *n_dev = device_counts ? b.counters + C_VC : nullptr;
     const u32 grid_n = device_counts ? cand_cap : host_nc;
-    ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, s.kx, s.ky, s.kz,
-               s.seg.cbucket, cand_cap, entry_cap);
+    const CandOut co{s.kx, s.ky, s.kz, s.seg.perm0, s.seg.cbucket, b.seg.count, b.seg.start, b.seg.bigoff, b.seg.cursor,
+                     s.seg.bkx, s.seg.bky, s.seg.bkz, s.seg.bid, b.seg.xinvmin, b.seg.xmax};
+    ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg,
                           SegGeom{p.g.amin[0], p.g.asize[0], p.g.amin[1], p.g.asize[1], p.g.amin[2], p.g.asize[2], (u32) p.g.Xg, (u32) p.g.Y,

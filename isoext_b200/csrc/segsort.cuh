@@ -272,8 +272,9 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
         if (n == 1) {
             if (tid == 0) {
                 const u32 id = perm0[s0];
+                const u32 src = LEVEL2 ? id : s0;      // first level: keys are stored grouped, next to their ids
                 perm[o0] = LEVEL2 ? l2.bid[id] : id;
-                skx[o0] = kx[id]; sky[o0] = ky[id]; skz[o0] = kz[id];
+                skx[o0] = kx[src]; sky[o0] = ky[src]; skz[o0] = kz[src];
             }
             continue;
         }
@@ -282,11 +283,12 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
         __syncthreads();
         {
             u32 vz = 0, vy = 0, vx = 0;
-            const u32 id0 = perm0[s0];
+            const u32 id0 = LEVEL2 ? perm0[s0] : s0;
             const u32 z0 = kz[id0], y0 = ky[id0], x0 = kx[id0];
             for (u32 i = tid; i < n; i += THREADS) {
                 const u32 id = perm0[s0 + i];
-                const u32 z = kz[id], y = ky[id], x = kx[id];
+                const u32 src = LEVEL2 ? id : s0 + i;
+                const u32 z = kz[src], y = ky[src], x = kx[src];
                 sk[i] = z; sk[CAP + i] = y; sk[2 * CAP + i] = x;
                 ids[i] = id;
                 ord[i] = (unsigned short) i;
@@ -732,9 +734,9 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         attr_set = true;
     }
     const int blocks = (int) ((grid_n + 255) / 256 > 148 * 8 ? 148 * 8 : (grid_n + 255) / 256);
-    const SegBigOut big{h.count, h.bigoff, kx, ky, kz, b.bkx, b.bky, b.bkz, b.bid, h.xinvmin, h.xmax};
-    ISX_LAUNCH(k_seg_scatter<true>, blocks < 1 ? 1 : blocks, 256, 0, stream, b.cbucket, n, h.start, h.cursor, b.perm0, n_dev, n_cap,
-               nullptr, big);
+    // first level: the producer has already placed keys (kx/ky/kz) and ids (b.perm0) grouped by bucket, and the members
+    // of oversized buckets in the compacted big list (mc_dense.cu emit_candidate)
+    (void) blocks;
     const u32 grid_small = nb < 148u * 32u ? nb : 148u * 32u, grid_large = nb < 148u * 8u ? nb : 148u * 8u;
     ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
                b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
