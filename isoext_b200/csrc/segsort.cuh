@@ -737,9 +737,26 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
     // first level: the producer has already placed keys (kx/ky/kz) and ids (b.perm0) grouped by bucket, and the members
     // of oversized buckets in the compacted big list (mc_dense.cu emit_candidate)
     (void) blocks;
+    // The two instances work on disjoint buckets and each is dominated by its slowest bucket (ncu: 13 % / 32 % SM
+    // throughput), so the small-bucket instance runs on an auxiliary stream next to the large one and the second level.
+    static cudaStream_t aux_of[64];            // one auxiliary stream + event pair per device, created on first use
+    static cudaEvent_t fork_of[64], join_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!aux_of[dev]) {
+        if (cudaStreamCreateWithFlags(&aux_of[dev], cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
+        cudaEventCreateWithFlags(&fork_of[dev], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&join_of[dev], cudaEventDisableTiming);
+    }
+    const cudaStream_t aux = aux_of[dev];
+    const cudaEvent_t ev_fork = fork_of[dev], ev_join = join_of[dev];
+    cudaEventRecord(ev_fork, stream);
+    cudaStreamWaitEvent(aux, ev_fork, 0);
     const u32 grid_small = nb < 148u * 32u ? nb : 148u * 32u, grid_large = nb < 148u * 8u ? nb : 148u * 8u;
-    ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, stream, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
+    ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, aux, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
                b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
+    cudaEventRecord(ev_join, aux);
     ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>), grid_large, SEG_THREADS, smem_big, stream, kx, ky, kz, h.count,
                h.start, b.perm0, b.perm, b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
     const u32 fb_n = nbig_dev ? big_cap : n_big;
@@ -767,12 +784,16 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         // last resort: a second-level bucket is still oversized (info2[4] != 0): global radix sort of the big list.
         // 14 launches that do nothing in the common case, so the single-sync path only enqueues them when the
         // previous extraction of the grid needed them (*radix_needed tells the host)
-        if (!allow_radix) return cudaGetLastError();
+        if (!allow_radix) {
+            cudaStreamWaitEvent(stream, ev_join, 0);
+            return cudaGetLastError();
+        }
         e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, b.info2 + 4);
         if (e != cudaSuccess) return e;
         ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, fb_n, b.info2 + 4, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx,
                    b.bky, b.bkz, b.skx, b.sky, b.skz);
     }
+    cudaStreamWaitEvent(stream, ev_join, 0);
     return cudaGetLastError();
 }
 
