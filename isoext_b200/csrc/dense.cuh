@@ -36,6 +36,7 @@ enum Counter : int {
     C_MAXB = 14,      // largest x-bucket
     C_NHEAVY = 15,    // rows handed to k_rowfill_heavy
     C_RADIX = 16,     // candidates that need the radix last resort of the segmented sort (0 = none)
+    C_ABORT = 17,     // single-call path: the sort was not completed (a capacity or the radix opt-in was missed)
     C_COUNT = 20
 };
 

@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, c
                                                     const u32 *__restrict__ cand_info, const u32 *__restrict__ cand_rank,
                                                     int *__restrict__ F, u32 cand_cap, u32 tri_cap, u32 entry_cap) {
     const u32 S = counters[C_S];
-    if (S > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap) return;
+    if (S > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap || counters[C_ABORT]) return;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const u32 mask = trimask[s];
         if (!mask) continue;
@@ -589,6 +589,16 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
     return enqueue_analysis(values, p, method, b, cap, stream);
 }
 
+// Single-call path: after the sort was enqueued, decide on the device whether its output is complete.  It is not if
+// a capacity was exceeded, if there are candidates in oversized buckets beyond what the second bucket level was
+// sized for (big_cap; 0 = not enqueued), or if the radix last resort was needed but not enqueued.  The weld and
+// face kernels then do nothing and the host falls back to count + emit (same conditions as in isoext_mc_dense_run).
+__global__ void k_phase2_gate(u32 *__restrict__ counters, u32 entry_cap, u32 cand_cap, u32 tri_cap, u32 big_cap, int allow_radix) {
+    const bool bad = counters[C_S] > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap ||
+                     counters[C_NBIG] > big_cap || (counters[C_RADIX] > 0u && !allow_radix);
+    counters[C_ABORT] = bad ? 1u : 0u;
+}
+
 // host_nc: number of candidates if the host knows it (two-phase path), else 0 with device_counts = true:
 // the kernels then read the counts from the counter block and do nothing if a capacity is exceeded.
 static int enqueue_phase2(const float *values, const DenseParams &p, int method, const McBuffers &b, const McScratch &s,
@@ -607,6 +617,8 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
                                   (u32) p.g.Z, p.g.x_off, p.gy, p.gx, p.ystep,
                                   p.ystep + 2 <= (u32) SEG_GROUPS && !getenv("ISX_SORT_NO_GROUPS")},
                           allow_radix, b.counters + C_RADIX, stream));
+    if (device_counts)
+        ISX_LAUNCH(k_phase2_gate, 1, 1, 0, stream, b.counters, entry_cap, cand_cap, tri_cap, big_cap, allow_radix ? 1 : 0);
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
                b.descV, klo, khi, n_dev, cand_cap, true);

@@ -24,7 +24,7 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
     if (n_dev) n = *n_dev;       // single-call fast path: the count lives on the device
-    if (n > n_cap) return;
+    if (n > n_cap || counters[C_ABORT]) return;   // C_ABORT: `perm` is incomplete, the host re-runs
     const u32 ntiles = (n + UQ_TILE - 1) / UQ_TILE;
     while (true) {
         __syncthreads();
@@ -84,7 +84,7 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
                     V[3 * (size_t) rank + 2] = key_float(z[j]);
                     rank++;
                 }
-                cand_rank[c[j]] = rank - 1;
+                if (c[j] < n) cand_rank[c[j]] = rank - 1;   // (never out of range with a complete permutation)
                 if (i == n - 1) counters[C_V] = rank;
             }
         }

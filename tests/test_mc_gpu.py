@@ -225,6 +225,31 @@ def test_repeated_calls_reuse_workspace_and_are_deterministic(iso):
         assert torch.equal(v, v0) and torch.equal(f, f0)
 
 
+@pytest.mark.parametrize("name", ["xface_6x200x200_second_level_by_y", "xface_5x3x9000_radix_last_resort",
+                                  "tilted_7x160x160_second_level_by_x", "box_4x150x150_two_xfaces", "cuboid65_exact_level_hits"])
+def test_fast_path_with_oversized_sort_buckets(iso, name):
+    """Second and later extractions of a grid take the single-sync path (isoext_mc_dense_run), whose second bucket
+    level and radix last resort are only enqueued when the previous call reported them as needed: every call must
+    give the oracle's mesh, also right after the field changed from one with oversized buckets to one without."""
+    vals, level, aabb = CASES[name]()
+    ov, of, _ = oracle.mc_dense(vals.numpy(), level, "nagae", aabb[0], aabb[1])
+    g = iso.UniformGrid(list(vals.shape), aabb[0], aabb[1])
+    g.set_values(vals.cuda())
+    for _ in range(4):
+        v, f = iso.marching_cubes(g, level)
+        assert_same_mesh(v, f, ov, of)
+    other = torch.from_numpy(np.random.default_rng(5).standard_normal(tuple(vals.shape)).astype(np.float32))
+    oov, oof, _ = oracle.mc_dense(other.numpy(), 0.0, "nagae", aabb[0], aabb[1])
+    g.set_values(other.cuda())
+    for _ in range(2):
+        v, f = iso.marching_cubes(g, 0.0)
+        assert_same_mesh(v, f, oov, oof)
+    g.set_values(vals.cuda())
+    for _ in range(2):
+        v, f = iso.marching_cubes(g, level)
+        assert_same_mesh(v, f, ov, of)
+
+
 def test_capacity_retry_path(iso):
     """A noise field has far more active cells than the initial capacity guess."""
     vals = fields.noise((96, 96, 96), 5)
