@@ -125,6 +125,23 @@ def slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
                 halo_above=([p for p in (c_hi, c_hi + 1) if p <= X - 1] if rank < world - 1 else []))
 
 
+def dc_slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
+    """Slab geometry for dual contouring (host logic; the CUDA side is not built yet).
+
+    Rank r emits the quads of the sign-change edges whose lower end point lies in planes ``[c_r, c_{r+1})`` and owns the
+    welded vertices with ``px[c_r] <= x < px[c_{r+1}]``.  A quad joins cells of layers ``p_lo.x - 1`` and ``p_lo.x``, so
+    faces reference dual vertices anywhere inside layer ``c_r - 1``; to number them from the top of the lower
+    neighbour's range the rank must know EVERY global vertex between them and ``px[c_r]`` -- including vertices of
+    layer ``c_r - 2`` that were clipped exactly onto plane ``c_r - 1``.  Hence two halo planes on both sides:
+    point planes ``[c_r - 2, c_{r+1} + 1]``, dual vertices of cell layers ``[c_r - 2, c_{r+1}]``, usage marks from
+    the quads of edges in planes ``[c_r - 2, c_{r+1} + 1]`` (checked on CPU in tests/test_dist_cpu.py)."""
+    c = partition_cells(X, world) if cuts is None else check_cuts(X, world, cuts)
+    c_lo, c_hi = c[rank], c[rank + 1]
+    ext_lo, ext_hi = max(0, c_lo - 2), min(X - 1, c_hi + 1)
+    return dict(c_lo=c_lo, c_hi=c_hi, ext_lo=ext_lo, ext_hi=ext_hi, layer_lo=ext_lo, layer_hi=min(X - 2, c_hi),
+                emit_lo=c_lo, emit_hi=(c_hi if rank < world - 1 else X))
+
+
 def exchange_halos(ext: torch.Tensor, plan: dict, rank: int, world: int, group=None) -> None:
     """Fill the halo planes of the extended slab `ext` ((n_ext, Y, Z), owned planes already in place).
 

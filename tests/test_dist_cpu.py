@@ -151,3 +151,68 @@ def test_vertex_layer_histogram_counts_every_vertex_once():
     v = torch.tensor([[-1.0, 0, 0], [-0.01, 0, 0], [0.0, 0, 0], [0.99, 0, 0], [1.0, 0, 0]])
     h = idist.vertex_layer_histogram(v, 5, -1.0, 1.0)
     assert h.tolist() == [1.0, 1.0, 1.0, 2.0]
+
+
+# ---- dual contouring on slabs: the ownership / numbering design, proved with the oracle ----------------------------
+def _dc_rank_view(vals, its, d, rank, world, halo_below=2):
+    """What rank `rank` would compute for dual contouring (dist.dc_slab_plan), derived from the oracle's global
+    per-cell dual vertices and quads: returns (global ids its faces must get, ids it computes locally, n_own)."""
+    X, Y, Z = vals.shape
+    p = idist.dc_slab_plan(X, rank, world)
+    ext_lo = max(0, p["c_lo"] - halo_below)
+    layer = its.cell_coords[:, 0]                                   # x layer of every active cell
+    edge_x = d["quad_edge"][:, 0] // (Y * Z)                        # plane of the lower end point of every quad's edge
+    edge_x_hi = d["quad_edge"][:, 1] // (Y * Z)
+    # quads the rank can evaluate: both end points inside its point planes
+    can_eval = (edge_x >= ext_lo) & (edge_x_hi <= p["ext_hi"])
+    used = np.zeros(len(layer), bool)
+    used[d["quads"][can_eval].ravel()] = True
+    visible = (layer >= ext_lo) & (layer <= p["layer_hi"]) & used
+    pos = np.ascontiguousarray(d["dual_v"][visible].astype(np.float32))   # the welded vertices are the float32 dual vertices
+    key = np.unique(pos.view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel())   # welded, lexicographic (x, y, z)
+    local_v = np.stack([key["x"], key["y"], key["z"]], axis=1)
+    b_lo = np.float32(px(p["c_lo"], X)) if rank > 0 else np.float32(-np.inf)
+    b_hi = np.float32(px(p["c_hi"], X)) if rank < world - 1 else np.float32(np.inf)
+    n_lo, n_hi = int((local_v[:, 0] < b_lo).sum()), int((local_v[:, 0] < b_hi).sum())
+    # faces of the quads this rank emits, as positions -> local ids
+    mine = (edge_x >= p["emit_lo"]) & (edge_x < p["emit_hi"])
+    tri = np.repeat(mine, 2)
+    want = d["f"][tri]                                               # global ids (ground truth)
+    fpos = np.ascontiguousarray(d["v"][want.ravel()]).view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel()
+    local_ids = np.searchsorted(key, fpos)
+    assert np.array_equal(key[np.minimum(local_ids, len(key) - 1)], fpos), "a referenced vertex is not in the rank's list"
+    return want.ravel(), local_ids, n_lo, n_hi
+
+
+def _dc_numbering_ok(vals, world, halo_below):
+    its = oracle.get_intersection(vals, compute_normals=True)
+    d = oracle.dual_contouring(its, vals.shape)
+    try:
+        views = [_dc_rank_view(vals, its, d, r, world, halo_below) for r in range(world)]
+    except AssertionError:
+        return False
+    owned = [n_hi - n_lo for (_, _, n_lo, n_hi) in views]
+    if sum(owned) != len(d["v"]):
+        return False
+    bases = np.concatenate([[0], np.cumsum(owned)])
+    for r, (want, local_ids, n_lo, n_hi) in enumerate(views):
+        got = idist.relabel_ids_torch(torch.from_numpy(local_ids.astype(np.int64)), n_lo, n_hi, int(bases[r]), int(bases[r + 1])).numpy()
+        if not np.array_equal(got, want):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("name", sorted(FIELDS))
+def test_dc_slab_numbering_design(name, world):
+    """Dual contouring on slabs (host-side design; the CUDA side is the next step): with TWO halo planes
+    on both sides every rank can number the vertices its faces reference exactly as the single-device result does,
+    and the owned ranges tile the global vertex list."""
+    assert _dc_numbering_ok(FIELDS[name]().numpy(), world, halo_below=2)
+
+
+def test_dc_slab_numbering_needs_the_second_halo_plane():
+    """With ONE plane below (the marching-cubes halo) the numbering breaks as soon as dual vertices of layer c_r - 2
+    are clipped onto plane c_r - 1 and interleave with those of layer c_r - 1 (noise does it)."""
+    vals = FIELDS["noise24"]().numpy()
+    assert not _dc_numbering_ok(vals, 2, halo_below=1) and _dc_numbering_ok(vals, 2, halo_below=2)
