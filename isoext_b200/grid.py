@@ -61,6 +61,17 @@ class _Workspace:
         return t
 
 
+def _as_uint32(ids: torch.Tensor) -> torch.Tensor:
+    """The reference hands point ids out as uint32 (NDArray<uint>, src/isoext_ext.cu:90); keep that dtype while the ids
+    fit (and the installed torch can convert on this device), int64 beyond -- the reference overflows there."""
+    if ids.numel() and int(ids.max()) > 0xFFFFFFFF:
+        return ids
+    try:
+        return ids.to(torch.uint32)
+    except (RuntimeError, TypeError):
+        return ids
+
+
 class UniformGrid(Grid):
     """Dense scalar field on a regular lattice.  ``shape`` is the number of POINTS per axis
     (src/grid/uniform.cu:8-20; 64^3 -> 250,047 cells / 262,144 points).
@@ -128,4 +139,4 @@ class UniformGrid(Grid):
         ar = lambda n: torch.arange(n, device=self.device, dtype=torch.int64)
         base = (ar(X - 1)[:, None, None] * Y + ar(Y - 1)[None, :, None]) * Z + ar(Z - 1)[None, None, :]
         offs = torch.tensor([(i >> 2 & 1) * Y * Z + (i >> 1 & 1) * Z + (i & 1) for i in range(8)], device=self.device)
-        return base[..., None] + offs
+        return _as_uint32(base[..., None] + offs)

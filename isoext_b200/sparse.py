@@ -109,7 +109,8 @@ class SparseGrid(Grid):
 
     def get_cells(self) -> torch.Tensor:
         """(N, 8) iota, as the reference (src/grid/sparse.cu:61-69)."""
-        return torch.arange(8 * self.get_num_cells(), device=self.device, dtype=torch.int64).view(-1, 8)
+        from .grid import _as_uint32
+        return _as_uint32(torch.arange(8 * self.get_num_cells(), device=self.device, dtype=torch.int64).view(-1, 8))
 
     def filter_cell_indices(self, cell_indices: torch.Tensor, values: torch.Tensor, level: float = 0.0) -> torch.Tensor:
         """Keep the cells whose 8 values straddle ``level`` (src/grid/sparse.cu:150-179)."""
