@@ -142,6 +142,19 @@ def dc_slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
                 emit_lo=c_lo, emit_hi=(c_hi if rank < world - 1 else X))
 
 
+def sparse_slab_select(cell_idx, shape, rank: int, world: int, cuts=None):
+    """Slab sharding of a SparseGrid (host logic; the sorted cell list is partitioned by x layer):
+    returns boolean masks ``(ext, owned)`` over ``cell_idx``.  Rank r emits the faces of its ``owned`` cells (layers
+    ``[c_r, c_{r+1})``) and welds the vertices of the ``ext`` cells (one ghost layer on either side), so that -- as
+    in the dense path -- it knows every vertex near its two threshold planes and can number by position."""
+    X, Y, Z = (int(v) for v in shape)
+    c = partition_cells(X, world) if cuts is None else check_cuts(X, world, cuts)
+    layer = torch.as_tensor(cell_idx).to(torch.int64) // ((Y - 1) * (Z - 1))
+    owned = (layer >= c[rank]) & (layer < c[rank + 1])
+    ext = (layer >= c[rank] - 1) & (layer <= c[rank + 1])
+    return ext, owned
+
+
 def exchange_halos(ext: torch.Tensor, plan: dict, rank: int, world: int, group=None) -> None:
     """Fill the halo planes of the extended slab `ext` ((n_ext, Y, Z), owned planes already in place).
 

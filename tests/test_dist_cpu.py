@@ -216,3 +216,48 @@ def test_dc_slab_numbering_needs_the_second_halo_plane():
     are clipped onto plane c_r - 1 and interleave with those of layer c_r - 1 (noise does it)."""
     vals = FIELDS["noise24"]().numpy()
     assert not _dc_numbering_ok(vals, 2, halo_below=1) and _dc_numbering_ok(vals, 2, halo_below=2)
+
+
+# ---- SparseGrid on slabs: partition of the sorted cell list, proved with the oracle -----------------------------------
+def _sparse_band(vals):
+    """Crossing cells of a dense field as a sparse grid: sorted cell ids + (N, 8) corner values (Morton corner order)."""
+    X, Y, Z = vals.shape
+    neg = vals < 0
+    cnt = sum(neg[dx:dx + X - 1, dy:dy + Y - 1, dz:dz + Z - 1].astype(np.int8) for dx in (0, 1) for dy in (0, 1) for dz in (0, 1))
+    x, y, z = np.nonzero((cnt > 0) & (cnt < 8))
+    cells = (x * (Y - 1) + y) * (Z - 1) + z
+    order = np.argsort(cells)
+    x, y, z, cells = x[order], y[order], z[order], cells[order]
+    v8 = np.stack([vals[x + (i >> 2 & 1), y + (i >> 1 & 1), z + (i & 1)] for i in range(8)], axis=1).astype(np.float32)
+    return cells.astype(np.int64), v8
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["cuboid33_faces_on_slab_planes", "sphere40", "csg36", "noise24", "planes_exactly_at_level"])
+def test_sparse_slabs_concatenate_to_the_single_device_mesh(name, world):
+    """SparseGrid marching cubes on slabs (host-side design, dist.sparse_slab_select): every rank runs the ordinary
+    sparse extraction on its owned cells plus one ghost layer on either side, keeps the faces of its owned cells,
+    owns the vertices between its two threshold planes and relabels exactly like the dense path."""
+    vals = FIELDS[name]().numpy()
+    shape = vals.shape
+    cells, v8 = _sparse_band(vals)
+    gv, gf, _ = oracle.mc_sparse(v8, cells, shape)
+    parts = []
+    for r in range(world):
+        ext, owned = (m.numpy() for m in idist.sparse_slab_select(cells, shape, r, world))
+        c = idist.partition_cells(shape[0], world)
+        below = ext & ~owned & (cells // ((shape[1] - 1) * (shape[2] - 1)) < c[r])
+        v_ext, f_ext, _ = oracle.mc_sparse(v8[ext], cells[ext], shape)
+        n_below = len(oracle.mc_sparse(v8[below], cells[below], shape)[1]) if below.any() else 0
+        n_own = len(oracle.mc_sparse(v8[owned], cells[owned], shape)[1]) if owned.any() else 0
+        b_lo = np.float32(px(c[r], shape[0])) if r > 0 else np.float32(-np.inf)
+        b_hi = np.float32(px(c[r + 1], shape[0])) if r < world - 1 else np.float32(np.inf)
+        n_lo = int((v_ext[:, 0] < b_lo).sum()) if len(v_ext) else 0
+        n_hi = int((v_ext[:, 0] < b_hi).sum()) if len(v_ext) else 0
+        parts.append((v_ext[n_lo:n_hi], f_ext[n_below:n_below + n_own], n_lo, n_hi))
+    bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])])
+    vs = [p[0] for p in parts]
+    fs = [idist.relabel_ids_torch(torch.from_numpy(p[1]), p[2], p[3], int(bases[r]), int(bases[r + 1])).numpy() for r, p in enumerate(parts)]
+    v, f = np.concatenate(vs), np.concatenate(fs)
+    assert v.shape == gv.shape and np.array_equal(v.view(np.uint32), gv.view(np.uint32))
+    assert np.array_equal(f, gf)
