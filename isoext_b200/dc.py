@@ -121,8 +121,11 @@ def _normals_dense(grid: UniformGrid, its: Intersection) -> None:
     its._has_normals = True
 
 
-def dc_dense_raw(grid: UniformGrid, its: Intersection, reg: float, svd_tol: float, want_quads: bool = False):
-    """Returns (v, f, dual_v, quads): welded mesh + per-active-cell dual vertices (+ oriented quads)."""
+def dc_dense_raw(grid: UniformGrid, its: Intersection, reg: float, svd_tol: float, want_quads: bool = False,
+                 dual_v_in: torch.Tensor | None = None):
+    """Returns (v, f, dual_v, quads): welded mesh + per-active-cell dual vertices (+ oriented quads).
+    ``dual_v_in`` (n_cells, 3) replaces the solved dual vertices before the quad/split/weld stage (parity tests
+    feed the reference's own dual vertices through it to compare everything downstream of the solve)."""
     lib = _lib.lib()
     X, Y, Z = grid.shape
     dev = grid.device
@@ -141,6 +144,8 @@ def dc_dense_raw(grid: UniformGrid, its: Intersection, reg: float, svd_tol: floa
     Q, Vc = int(counts[0]), int(counts[1])
     if Q == 0:
         return None, None, dual_v, None
+    if dual_v_in is not None:
+        dual_v.copy_(dual_v_in)
     scratch = grid._ws.get("dc_scratch", lib.isoext_dc_dense_scratch_bytes(Vc), dev)
     V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
     F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)

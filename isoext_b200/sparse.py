@@ -184,7 +184,8 @@ def its_sparse(grid: SparseGrid, level: float, compute_normals: bool):
                               _has_normals=bool(compute_normals))
 
 
-def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads: bool = False):
+def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads: bool = False, dual_v_in=None):
+    """(v, f, dual_v, quads) like dc.dc_dense_raw; ``dual_v_in`` replaces the solved dual vertices (parity tests)."""
     lib = _lib.lib()
     n = grid.get_num_cells()
     X, Y, Z, amin, amax = grid._geom()
@@ -203,6 +204,8 @@ def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads:
         Q, Vc = int(counts[0]), int(counts[1])
         if Q == 0:
             return None, None, dual_v, None
+        if dual_v_in is not None:
+            dual_v.copy_(dual_v_in)
         scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc), dev)
         V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
         F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)

@@ -209,5 +209,23 @@ def dual_contouring(grid, level=0.0, intersection=None, reg=1e-2, svd_tol=1e-6):
     return _adopt(v.value, (nv.value, 3), torch.float32), _adopt(f.value, (nf.value, 3), torch.int32)
 
 
+def dc_dual_vertices(grid, intersection, reg=1e-2, svd_tol=1e-6):
+    """Per ACTIVE CELL (order of ``intersection.get_cell_indices()``), from the reference's own compiled code
+    (oracle/ref_shim_dc.cu -> src/dc.cu:166-182): dict(dual_v (S,3) clipped, raw (S,3) before the clip, ATA (S,3,3),
+    ATb (S,3) float32 QEF, info (S,) cuSOLVER gesvdj status).  ``intersection`` must carry normals."""
+    h = lib()
+    h.ref_dc_last_error.restype = C.c_char_p
+    p = [C.c_void_p() for _ in range(5)]
+    n = C.c_size_t()
+    rc = h.ref_dc_dual_vertices(grid.h, intersection.h, C.c_float(reg), C.c_float(svd_tol),
+                                *[C.byref(x) for x in p], C.byref(n))
+    if rc != 0:
+        raise RuntimeError(h.ref_dc_last_error().decode())
+    S = n.value
+    return dict(dual_v=_adopt(p[0].value, (S, 3), torch.float32), raw=_adopt(p[1].value, (S, 3), torch.float32),
+                ATA=_adopt(p[2].value, (S, 3, 3), torch.float32), ATb=_adopt(p[3].value, (S, 3), torch.float32),
+                info=_adopt(p[4].value, (S,), torch.int32))
+
+
 def free(ptr):
     lib().ref_free(ptr)
