@@ -4,26 +4,38 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 One "step" = one pass of the hot path (marching_cubes, default LUT method "nagae", level 0) over one
-synthetic analytic field:
-  N = 1  : BASELINE.json configs[1], 512^3 dense torus SDF (R=.5, r=.2) on [-1,1]^3      ("c2")
-  N > 1  : BASELINE.json configs[2], 2048^3 CSG box-minus-sphere, slab-sharded on dim 0      ("c3")
-           one process per GPU (torchrun), halo pull + vertex-id bases as kernels over NVLink peer memory, slab cuts
-           balanced by measured load; strong scaling.  The N = 1 line also carries "scaling_base": the same c3
-           workload timed on the single GPU, so that 1 -> N comparisons have a same-workload base.
-Metric: Gvoxels/s = X*Y*Z / t / 1e9 (whole job).  `value` is timed with the field resident in HBM
-(CUDA events, max over ranks); `e2e` goes through the public API from pinned HOST memory, H2D copy of
-the field and D2H read of the mesh inside the timed region.  Inputs (537 MB / 34 GB) are larger than
-the 126 MB L2, so no explicit L2 flush is needed between iterations.
+synthetic analytic field resident in HBM.  The SAME workload at every N, so the driver's 1 -> N arithmetic
+is meaningful:
+
+  headline (every N): BASELINE.json configs[2], 2048^3 dense CSG box-minus-sphere ("c3", 34.4 GB: the largest
+           configuration that fits one B200).  N = 1: one UniformGrid.  N > 1: dim-0 slabs, one process per
+           GPU (torchrun), halo pull + vertex-id bases as kernels over NVLink peer memory; strong scaling.
+           The headline value at N > 1 uses EVEN slabs (no foreknowledge of the surface); the same loop with
+           slab cuts balanced by the measured load of a previous extraction is reported beside it
+           ("balanced_cuts"), as is the first (cold: count + emit, capacity discovery) call ("first_call_ms").
+  sub_records (N = 1): configs[1] 512^3 torus ("c2", the reference-representable single-GPU case) and the
+           north-star target 1024^3 torus ("t1024"), each timed with the same protocol and with its own
+           whole_path_frac.
+Every line carries the global vertex / triangle totals and a 64-bit order-sensitive checksum of the mesh
+(V bits and F ids weighted by their global index); they are checked against the values the single-GPU
+path produced (EXPECTED below), so a wrong mesh at any N fails loudly instead of printing a number.
+
+Metric: Gvoxels/s = X*Y*Z / t / 1e9 (whole job).  `value` is timed with the field resident in HBM (CUDA
+events, max over ranks); `e2e` goes through the public API from pinned HOST memory, H2D copy of the field
+and D2H read of the mesh inside the timed region.  Inputs (>= 537 MB) are larger than the 126 MB L2, so no
+explicit L2 flush is needed between iterations.
 `--impl reference` times the reference's own implementation of the path: GuangyanCai/isoext has NO CPU
 extraction path, so that arm runs the UNMODIFIED reference CUDA sources (oracle/_ref, built from
-/root/reference by oracle/Makefile) on the same GPU and config -- the baseline BASELINE.json names.
+/root/reference by oracle/Makefile) on one GPU.  The reference cannot represent 2048^3 (it refuses more than
+INT_MAX points and is wrong above 2^29 cells), so each step is a bounded sample of the workload -- the same
+field sampled at 512^3 over the same AABB -- and the line says so (`same_workload`); it also carries a
+full-size, identical-workload record for c2 (512^3 torus).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
-import math
 import os
 import statistics
 import subprocess
@@ -38,6 +50,29 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "Gvoxels/s and % HBM roofline for MC/DC at 1/2/4/8 B200 vs reference CUDA"
 
+WORKLOADS = {
+    "c1": dict(n=64, field="sphere", desc="64^3 sphere SDF UniformGrid marching_cubes (nagae)"),
+    "c2": dict(n=512, field="torus", desc="512^3 dense torus SDF marching_cubes (nagae), 1 GPU"),
+    "t1024": dict(n=1024, field="torus", desc="1024^3 dense torus SDF marching_cubes (nagae), 1 GPU (north-star target size)"),
+    "c3": dict(n=2048, field="csg", desc="2048^3 dense CSG box-minus-sphere marching_cubes (nagae)"),
+}
+# Mesh of each workload as produced by the single-GPU path (bit-identical to the reference build where the
+# reference can represent the grid: c2; closed-manifold / slab-equality tested for the others).  Every run,
+# at every N, must reproduce counts and checksum.
+EXPECTED = {
+    "c2": {"vertices": 372576, "triangles": 745152, "checksum": 0x1264ae17dfaf9555},
+    "t1024": {"vertices": 1492552, "triangles": 2985104, "checksum": 0x305beda00021f936},
+    "c3": {"vertices": 9047904, "triangles": 18095804, "checksum": 0xd3e1e9356034ecb5},
+}
+
+
+def workload_config(wl_name):
+    """The workload-defining part of the JSON line: identical in the `ours` and `reference` arms."""
+    wl = WORKLOADS[wl_name]
+    n = wl["n"]
+    return {"workload": f"{wl_name}: {wl['desc']}", "shape": [n, n, n], "field": wl["field"], "aabb": [-1.0, 1.0], "level": 0.0,
+            "method": "nagae", "l2_policy": "inputs larger than L2 (no flush needed)"}
+
 
 # ------------------------------------------------------------------------------------------------
 def load_peaks():
@@ -50,8 +85,8 @@ def load_peaks():
 
 class ClockSampler:
     """Samples SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled from a
-    thread every few ms (the timed region of the headline workload is only tens of ms long, far below what an
-    `nvidia-smi -lms` loop resolves); nvidia-smi is the fallback when the NVML binding is missing."""
+    thread every ms (the timed regions here are tens to hundreds of ms, below what an `nvidia-smi -lms` loop
+    resolves); nvidia-smi is the fallback when the NVML binding is missing."""
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
@@ -108,20 +143,13 @@ def field_fn(name):
     return {"torus": fields.torus(), "csg": fields.csg_box_minus_sphere(), "sphere": fields.sphere(0.5)}[name]
 
 
-WORKLOADS = {
-    "c1": dict(n=64, field="sphere", desc="64^3 sphere SDF UniformGrid marching_cubes (nagae)"),
-    "c2": dict(n=512, field="torus", desc="512^3 dense torus SDF marching_cubes (nagae), 1 GPU"),
-    "t1024": dict(n=1024, field="torus", desc="1024^3 dense torus SDF marching_cubes (nagae), 1 GPU"),
-    "c3": dict(n=2048, field="csg", desc="2048^3 dense CSG box-minus-sphere marching_cubes, dim-0 slabs"),
-}
-
-
-def build_field_gpu(fn, n, x0, x1, device, slab=16):
+def build_field_gpu(fn, n, x0, x1, device, slab=16, out=None):
     """(x1-x0, n, n) f32 field on the GPU from global indices (same formula as tests/fields.py)."""
     import torch
     import fields
     ax = fields.axis(n).to(device)
-    out = torch.empty((x1 - x0, n, n), dtype=torch.float32, device=device)
+    if out is None:
+        out = torch.empty((x1 - x0, n, n), dtype=torch.float32, device=device)
     for a in range(x0, x1, slab):
         b = min(x1, a + slab)
         P = torch.stack(torch.meshgrid(ax[a:b], ax, ax, indexing="ij"), dim=-1)
@@ -134,13 +162,42 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+_GOLD = -7046029254386353131     # 0x9E3779B97F4A7C15 as a signed 64-bit integer
+
+
+def mesh_checksum(v, f, v_base=0, t_base=0):
+    """Order-sensitive 64-bit checksum (wrap-around int64 arithmetic on the device): sum over the float BITS of V and
+    the ids of F, each multiplied by an odd weight derived from its GLOBAL flat index.  Per-rank parts add up to the
+    checksum of the concatenated mesh, so it is comparable across N."""
+    import torch
+    tot = 0
+    for t, base, salt in ((v, 3 * v_base, 1), (f, 3 * t_base, 2)):
+        if t is None or t.numel() == 0:
+            continue
+        bits = (t.contiguous().view(torch.int32) if t.dtype == torch.float32 else t.contiguous()).reshape(-1).to(torch.int64)
+        idx = torch.arange(bits.numel(), dtype=torch.int64, device=t.device) + int(base)
+        w = ((idx + salt) * _GOLD) | 1
+        tot = (tot + int((bits * w).sum().item())) & 0xFFFFFFFFFFFFFFFF
+    return tot
+
+
+def verify_mesh(wl_name, nV, nT, checksum):
+    exp = EXPECTED.get(wl_name)
+    if not exp:
+        return None
+    ok = nV == exp["vertices"] and nT == exp["triangles"] and ("checksum" not in exp or checksum == exp["checksum"])
+    if not ok:
+        raise SystemExit(f"bench.py: WRONG MESH for {wl_name}: got {nV} V / {nT} T / checksum {checksum:016x}, expected {exp}")
+    return True
+
+
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_port(n_sample=256):
-    """The oracle C port (single thread) on a bounded sample of the same field: the n_sample^3 grid of
-    the torus SDF.  A reported baseline, not the target."""
+def cpu_baseline_port(field="csg", n_sample=256):
+    """The oracle C port (single thread) on a bounded sample of the headline field: the n_sample^3 grid of
+    the same SDF over the same AABB.  A reported baseline, not the target."""
     import fields
     import oracle
-    vals = fields.eval_field(fields.torus(), (n_sample,) * 3).numpy()
+    vals = fields.eval_field(field_fn(field), (n_sample,) * 3).numpy()
     t0 = time.perf_counter()
     reps = 0
     while True:
@@ -150,8 +207,72 @@ def cpu_baseline_port(n_sample=256):
             break
     dt = (time.perf_counter() - t0) / reps
     return {"value": n_sample ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
-            "sample": f"{n_sample}^3 torus SDF (same field family as the workload), oracle/oracle_c.c, "
+            "sample": f"{n_sample}^3 sampling of the workload's field ({field}) over the same AABB, oracle/oracle_c.c, "
                       f"{reps} repetitions in {dt * reps:.1f} s"}
+
+
+def timed_loop(step, steps, warmup, barrier, sampler=None, lib=None):
+    """W untimed steps, then exactly K steps between barriers + synchronize, CUDA events on the current stream."""
+    import torch
+    for _ in range(warmup):
+        out = step()
+    barrier()
+    if sampler:
+        sampler.start()
+    if lib:
+        lib.isoext_profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    prof = None
+    if lib:
+        sm_ms, sm_n, launches = C.c_double(), C.c_int64(), C.c_int64()
+        lib.isoext_profile_end(C.byref(sm_ms), C.byref(sm_n), C.byref(launches))
+        prof = (sm_ms.value, sm_n.value, launches.value)
+    clocks = sampler.stop() if sampler else None
+    return ms_total, out, prof, clocks
+
+
+def single_gpu_record(iso, lib, wl_name, dev, steps, warmup, peak, keep=False):
+    """Build the workload on this GPU, time the first (cold) call and the steady-state loop."""
+    import torch
+    wl = WORKLOADS[wl_name]
+    n = wl["n"]
+    grid = iso.UniformGrid([n, n, n])
+    view = grid.values_view()
+    fn = field_fn(wl["field"])
+    for a in range(0, n, 64):
+        build_field_gpu(fn, n, a, min(n, a + 64), dev, out=view[a:a + 64])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    iso.marching_cubes(grid)          # first call: count + emit (two syncs), workspace allocation, capacity discovery
+    torch.cuda.synchronize()
+    first_ms = (time.perf_counter() - t0) * 1e3
+    sampler = ClockSampler(dev.index or 0)
+    ms_total, (v, f), prof, clocks = timed_loop(lambda: iso.marching_cubes(grid), steps, warmup, torch.cuda.synchronize, sampler, lib)
+    ms_step = ms_total / steps
+    nV, nT = int(v.shape[0]), int(f.shape[0])
+    csum = mesh_checksum(v, f)
+    voxels = float(n) ** 3
+    rec = {"workload": f"{wl_name}: {wl['desc']}", "shape": [n, n, n], "value": voxels / (ms_step * 1e-3) / 1e9, "unit": "Gvoxels/s",
+           "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "first_call_ms": first_ms,
+           "vertices": nV, "triangles": nT, "mesh_checksum": f"{csum:016x}", "mesh_verified": verify_mesh(wl_name, nV, nT, csum),
+           "whole_path_frac": (4.0 * voxels + 12.0 * nV + 12.0 * nT) / (ms_step * 1e-3) / 1e9 / peak,
+           "whole_path_algorithmic_bytes": 4.0 * voxels + 12.0 * nV + 12.0 * nT, "clocks": clocks}
+    if prof and prof[1]:
+        k_ms = prof[0] / prof[1]
+        rec["k_signbits_ms"] = k_ms
+        rec["k_signbits_frac_of_peak"] = 4.0 * voxels / (prof[1] / steps) / (k_ms * 1e-3) / 1e9 / peak
+    if keep:
+        return rec, grid, prof
+    del grid, view, v, f
+    torch.cuda.empty_cache()
+    return rec, None, prof
 
 
 def run_ours(args):
@@ -166,101 +287,92 @@ def run_ours(args):
     import isoext_b200 as iso
     from isoext_b200 import _lib
 
-    wl_name = args.workload or ("c2" if world == 1 else "c3")
+    wl_name = args.workload or "c3"
     wl = WORKLOADS[wl_name]
     n = wl["n"]
     fn = field_fn(wl["field"])
     lib = _lib.lib()
-    sampler = ClockSampler(local_rank)
     peak, peak_src = load_peaks()
-
-    cuts = None
-    if world == 1:
-        vals = build_field_gpu(fn, n, 0, n, dev)
-        grid = iso.UniformGrid([n, n, n])
-        grid.set_values(vals)
-
-        def step():
-            return iso.marching_cubes(grid)
-    else:
-        from isoext_b200 import dist as idist
-        sg = idist.SlabGrid([n, n, n], group=dist.group.WORLD)
-        x0, x1 = sg.owned_point_range()
-        sg.set_owned_values(build_field_gpu(fn, n, x0, x1, dev))
-        cuts = None
-        if not args.even_slabs:
-            # cut the slabs by measured load (setup, untimed): one extraction on even slabs gives the vertices per
-            # cell layer; cost(layer) = time to stream one plane + surface-stage time per vertex
-            v0, _ = idist.marching_cubes(sg)
-            hist = idist.vertex_layer_histogram(v0, n, -1.0, 1.0, dist.group.WORLD)
-            plane_s, vertex_s = 4.0 * n * n / (peak * 1e9), 0.43e-9
-            cuts = idist.balanced_cuts((plane_s + vertex_s * hist).tolist(), world, ghost_cost=(vertex_s * hist).tolist())
-            del v0
-            sg.close()
-            sg = idist.SlabGrid([n, n, n], group=dist.group.WORLD, cuts=cuts)
-            x0, x1 = sg.owned_point_range()
-            sg.set_owned_values(build_field_gpu(fn, n, x0, x1, dev))
-
-        def step():
-            return idist.marching_cubes(sg)
+    voxels = float(n) ** 3
+    extra = {}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        v, f = step()
-    barrier()
-    sampler.start()
-    lib.isoext_profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        v, f = step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    sm_ms, sm_n, launches = C.c_double(), C.c_int64(), C.c_int64()
-    lib.isoext_profile_end(C.byref(sm_ms), C.byref(sm_n), C.byref(launches))
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    voxels = float(n) ** 3
-    value = voxels / (ms_step * 1e-3) / 1e9
-    nV = 0 if v is None else int(v.shape[0])
-    nT = 0 if f is None else int(f.shape[0])
-
-    # ---- end to end through the public API with HOST buffers (N = 1: full field from pinned memory)
-    e2e = None
     if world == 1:
-        host = vals.cpu().pin_memory()
-        grid2 = iso.UniformGrid([n, n, n])
-        dbuf = torch.empty_like(vals)
+        rec, grid, prof = single_gpu_record(iso, lib, wl_name, dev, args.steps, args.warmup, peak, keep=True)
+        ms_step, clocks, first_ms = rec["ms_per_step"], rec["clocks"], rec["first_call_ms"]
+        nV, nT, csum = rec["vertices"], rec["triangles"], int(rec["mesh_checksum"], 16)
+        local_vox = voxels
+        parallelism = "single GPU"
+
+        # ---- end to end through the public API with HOST buffers: full field from pinned memory every step
+        host = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
+        view = grid.values_view()
+        for a in range(0, n, 64):
+            host[a:a + 64].copy_(view[a:a + 64])
+        dbuf = torch.empty((n, n, n), dtype=torch.float32, device=dev)
 
         def e2e_step():
             dbuf.copy_(host, non_blocking=True)           # H2D of this step's input
-            grid2.set_values(dbuf)
-            vv, ff = iso.marching_cubes(grid2)
+            grid.set_values(dbuf)
+            vv, ff = iso.marching_cubes(grid)
             return vv.cpu(), ff.cpu()                     # D2H of the step's result
 
-        for _ in range(2):
-            e2e_step()
+        e2e_step()
         torch.cuda.synchronize()
-        k = max(3, min(args.steps, 10))
+        k = 3 if n >= 2048 else max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(k):
             hv, hf = e2e_step()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / k
-        e2e = {"value": voxels / dt / 1e9, "unit": "Gvoxels/s", "ms_per_step": dt * 1e3,
+        e2e = {"value": voxels / dt / 1e9, "unit": "Gvoxels/s", "ms_per_step": dt * 1e3, "steps": k,
                "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(hv.numel() * 4 + hf.numel() * 4)}
+        del host, dbuf, grid, view, hv, hf
+        torch.cuda.empty_cache()
     else:
-        # multi-GPU: each rank uploads its own slab from pinned host memory and reads its mesh part back
+        from isoext_b200 import dist as idist
+
+        def make_slabs(cuts=None):
+            sg = idist.SlabGrid([n, n, n], group=dist.group.WORLD, cuts=cuts)
+            x0, x1 = sg.owned_point_range()
+            build_field_gpu(fn, n, x0, x1, dev, out=sg.owned_values())
+            return sg
+
+        def totals(v, f):
+            """Global V / T totals and the checksum of the concatenated mesh (all_reduce of per-rank parts)."""
+            mine = torch.tensor([v.shape[0], f.shape[0]], dtype=torch.int64, device=dev)
+            allc = torch.empty(world * 2, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, mine)
+            allc = allc.view(world, 2).cpu()
+            c = mesh_checksum(v, f, int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum()))
+            ct = torch.tensor([c - (1 << 64) if c >= (1 << 63) else c], dtype=torch.int64, device=dev)
+            dist.all_reduce(ct)
+            return int(allc[:, 0].sum()), int(allc[:, 1].sum()), int(ct.item()) & 0xFFFFFFFFFFFFFFFF
+
+        def max_over_ranks(x):
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        # ---- headline: EVEN slabs (no foreknowledge)
+        sg = make_slabs()
+        barrier()
+        t0 = time.perf_counter()
+        v0, f0 = idist.marching_cubes(sg)
+        barrier()
+        first_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        sampler = ClockSampler(local_rank)
+        ms_total, (v, f), prof, clocks = timed_loop(lambda: idist.marching_cubes(sg), args.steps, args.warmup, barrier, sampler, lib)
+        ms_step = max_over_ranks(ms_total) / args.steps
+        nV, nT, csum = totals(v, f)
+        local_vox = float(sg.local_points())
+        parallelism = f"dim-0 slabs x{world}, even cuts; halo pull + vertex-id bases as kernels over NVLink peer memory"
+
+        # ---- end to end: each rank uploads its own slab from pinned host memory and reads its mesh part back
         host = sg.owned_values().cpu().pin_memory()
         dbuf = torch.empty_like(sg.owned_values())
 
@@ -268,7 +380,7 @@ def run_ours(args):
             dbuf.copy_(host, non_blocking=True)
             sg.set_owned_values(dbuf)
             vv, ff = idist.marching_cubes(sg)
-            return (vv.cpu() if vv is not None else None), (ff.cpu() if ff is not None else None)
+            return vv.cpu(), ff.cpu()
 
         e2e_step()
         barrier()
@@ -277,79 +389,79 @@ def run_ours(args):
         for _ in range(k):
             hv, hf = e2e_step()
         barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / k], device=dev)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        nb = torch.tensor([host.numel() * 4, (0 if hv is None else hv.numel() * 4) + (0 if hf is None else hf.numel() * 4)],
-                          device=dev, dtype=torch.int64)
+        dt = max_over_ranks((time.perf_counter() - t0) / k)
+        nb = torch.tensor([host.numel() * 4, hv.numel() * 4 + hf.numel() * 4], device=dev, dtype=torch.int64)
         dist.all_reduce(nb)
-        e2e = {"value": voxels / float(dt.item()) / 1e9, "unit": "Gvoxels/s", "ms_per_step": float(dt.item()) * 1e3,
+        e2e = {"value": voxels / dt / 1e9, "unit": "Gvoxels/s", "ms_per_step": dt * 1e3, "steps": k,
                "h2d_bytes_per_step": int(nb[0].item()), "d2h_bytes_per_step": int(nb[1].item())}
+        del host, dbuf
 
+        # ---- beside it: slab cuts balanced by the measured load of the previous extraction (time-series use)
+        if not args.no_balanced:
+            hist = idist.vertex_layer_histogram(v0, n, -1.0, 1.0, dist.group.WORLD)
+            plane_s, vertex_s = 4.0 * n * n / (peak * 1e9), 0.43e-9
+            cuts = idist.balanced_cuts((plane_s + vertex_s * hist).tolist(), world, ghost_cost=(vertex_s * hist).tolist())
+            del v0, f0, v, f
+            sg.close()
+            sg = make_slabs(cuts)
+            idist.marching_cubes(sg)
+            ms_b, (vb, fb), _, _ = timed_loop(lambda: idist.marching_cubes(sg), args.steps, args.warmup, barrier)
+            ms_b = max_over_ranks(ms_b) / args.steps
+            bV, bT, bsum = totals(vb, fb)
+            extra["balanced_cuts"] = {"ms_per_step": ms_b, "value": voxels / (ms_b * 1e-3) / 1e9, "unit": "Gvoxels/s", "cuts": cuts,
+                                      "cost_model": {"plane_s": plane_s, "vertex_s": vertex_s},
+                                      "vertices": bV, "triangles": bT, "mesh_checksum": f"{bsum:016x}",
+                                      "mesh_verified": verify_mesh(wl_name, bV, bT, bsum),
+                                      "note": "cuts from the per-layer vertex histogram of a PREVIOUS extraction of the same field"}
+        sg.close()
+
+    value = voxels / (ms_step * 1e-3) / 1e9
     if rank == 0:
+        verified = verify_mesh(wl_name, nV, nT, csum)
         # roofline of the dominant kernel (k_signbits: the one volume-sized HBM stream); 4 B/voxel algorithmic
-        # large grids are streamed as several x-chunks per step: bytes per launch = 4 B x voxels of that launch
-        local_vox = voxels if world == 1 else float(sg.local_points())
-        launches_per_step = max(1.0, sm_n.value / float(args.steps))
-        local_vox = local_vox / launches_per_step
-        k_ms = sm_ms.value / max(1, sm_n.value)
-        achieved = 4.0 * local_vox / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        sm_ms, sm_n, launches = prof
+        launches_per_step = max(1.0, sm_n / float(args.steps))
+        vox_per_launch = local_vox / launches_per_step
+        k_ms = sm_ms / max(1, sm_n)
+        achieved = 4.0 * vox_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         traffic = None
-        prof = ROOT / "profiles" / "k_signbits_traffic.json"
-        if prof.exists():
+        tprof = ROOT / "profiles" / "k_signbits_traffic.json"
+        if tprof.exists():
             try:
-                traffic = json.loads(prof.read_text()).get(wl_name)
+                traffic = json.loads(tprof.read_text()).get(wl_name)
             except Exception:
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if world > 1 or wl_name == "c3" else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "ours",
-            "config": {"workload": f"{wl_name}: {wl['desc']}", "shape": [n, n, n], "level": 0.0, "method": "nagae",
-                       "vertices": nV, "triangles": nT, "l2_policy": "inputs larger than L2 (no flush needed)",
-                       "parallelism": "single GPU" if world == 1 else
-                       f"dim-0 slabs x{world}; halo pull + vertex-id bases as kernels over NVLink peer memory"
-                       + (f"; slab cuts balanced by measured load {cuts}" if cuts else "; even slabs")},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+            "config": workload_config(wl_name),
+            "parallelism": parallelism,
+            "mesh": {"vertices": nV, "triangles": nT, "checksum": f"{csum:016x}", "verified": verified},
+            "first_call_ms": first_ms,
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(launches.value),
+            "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_signbits", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": k_ms, "kernel_launches_timed": int(sm_n.value), "kernel_launches_per_step": launches_per_step,
-                         "algorithmic_bytes_per_launch": 4.0 * local_vox,
+                         "kernel_ms": k_ms, "kernel_launches_timed": int(sm_n), "kernel_launches_per_step": launches_per_step,
+                         "algorithmic_bytes_per_launch": 4.0 * vox_per_launch,
                          "whole_path_frac": (4.0 * voxels + 12.0 * nV + 12.0 * nT) / (ms_step * 1e-3) / 1e9 / peak / world},
         }
+        line.update(extra)
+        if world == 1 and not args.no_sub_records and wl_name == "c3":
+            subs = []
+            for name in ("c2", "t1024"):
+                try:
+                    r, _, _ = single_gpu_record(iso, lib, name, dev, args.steps, args.warmup, peak)
+                    subs.append(r)
+                except Exception as exc:    # the headline line must still be printed
+                    subs.append({"workload": name, "unavailable": repr(exc)[:200]})
+            line["sub_records"] = subs
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_port()
-        if world == 1 and wl_name == "c2" and not args.no_scaling_base:
-            # The N > 1 lines run c3 (2048^3 CSG, BASELINE.json configs[2], "sharded at 1/2/4/8 B200"): time the same
-            # workload on this single GPU as well, so that a 1 -> N comparison has a same-workload base.
-            try:
-                del vals, grid, grid2, dbuf, host
-                torch.cuda.empty_cache()
-                n3 = WORKLOADS["c3"]["n"]
-                g3 = iso.UniformGrid([n3] * 3)
-                view = g3.values_view()
-                fn3 = field_fn(WORKLOADS["c3"]["field"])
-                for a in range(0, n3, 64):
-                    view[a:a + 64] = build_field_gpu(fn3, n3, a, min(n3, a + 64), dev)
-                for _ in range(3):
-                    iso.marching_cubes(g3)
-                torch.cuda.synchronize()
-                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s0.record()
-                for _ in range(5):
-                    iso.marching_cubes(g3)
-                s1.record()
-                torch.cuda.synchronize()
-                ms3 = s0.elapsed_time(s1) / 5
-                line["scaling_base"] = {"workload": "c3: " + WORKLOADS["c3"]["desc"] + " on this single GPU (the N > 1 lines run c3)",
-                                        "value": float(n3) ** 3 / (ms3 * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms3, "steps": 5}
-            except Exception as exc:   # e.g. a GPU with less memory: the headline line must still be printed
-                line["scaling_base"] = {"unavailable": repr(exc)[:200]}
+            line["cpu_baseline"] = cpu_baseline_port(wl["field"])
         print(json.dumps(line), flush=True)
     if world > 1:
-        sg.close()
         dist.destroy_process_group()
 
 
@@ -368,51 +480,58 @@ def run_reference(args):
         return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    wl_name = args.workload or ("c2" if world == 1 else "c3")
-    wl = WORKLOADS[wl_name]
-    n_full = wl["n"]
+    wl_name = args.workload or "c3"
+
+    def time_ref(name, n, steps, warmup, sampler=None):
+        fn = field_fn(WORKLOADS[name]["field"])
+        vals = build_field_gpu(fn, n, 0, n, dev)
+        grid = ref.UniformGrid([n, n, n])
+        grid.set_values(vals)
+
+        def step():
+            v, f, nv, nf = ref.marching_cubes_timed_raw(grid, 0.0, "nagae")
+            ref.free(v); ref.free(f)
+            return nv, nf
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            nv, nf = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        clocks = sampler.stop() if sampler else None
+        del grid, vals
+        torch.cuda.empty_cache()
+        return ms, nv, nf, clocks
+
+    n_full = WORKLOADS[wl_name]["n"]
     n = min(n_full, 512)     # bounded sample: the reference is invalid above 813 points/axis (uint overflow)
-    fn = field_fn(wl["field"])
-    if n == n_full:
-        vals = build_field_gpu(fn, n, 0, n, dev)
-        sample = f"full workload ({n}^3)"
-    else:
-        # central n^3 block of the n_full^3 field is not expressible in the reference (positions are tied to
-        # the grid shape), so sample the same analytic field at n^3 over the same AABB.
-        vals = build_field_gpu(fn, n, 0, n, dev)
-        sample = f"{n}^3 sampling of the same field over the same AABB (reference cannot represent {n_full}^3)"
-    grid = ref.UniformGrid([n, n, n])
-    grid.set_values(vals)
-    sampler = ClockSampler(local_rank)
-
-    def step():
-        v, f, nv, nf = ref.marching_cubes_timed_raw(grid, 0.0, "nagae")
-        ref.free(v); ref.free(f)
-        return nv, nf
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        nv, nf = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_step = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop()
+    sample = (f"full workload ({n}^3)" if n == n_full else
+              f"{n}^3 sampling of the same field over the same AABB (the reference cannot represent {n_full}^3)")
+    ms_step, nv, nf, clocks = time_ref(wl_name, n, args.steps, args.warmup, ClockSampler(local_rank))
     value = float(n) ** 3 / (ms_step * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{wl_name}: {wl['desc']}", "shape": [n, n, n], "level": 0.0, "method": "nagae",
-                       "vertices": nv, "triangles": nf, "sample": sample,
-                       "note": "reference = its own CUDA extension (thrust pipeline) on 1 GPU; it has no CPU path and no multi-GPU path"},
+            "config": workload_config(wl_name),
+            "same_workload": bool(n == n_full and world == 1),
+            "sample": {"shape": [n, n, n], "vertices": nv, "triangles": nf, "what": sample,
+                       "note": "reference = its own CUDA extension (thrust pipeline) on ONE GPU; it has no CPU path and no multi-GPU path"},
             "clocks": clocks,
             "cpu_baseline": {"value": value, "unit": "Gvoxels/s", "cores": 0, "kind": "reference",
                              "sample": sample + "; runs on the GPU: the reference has no CPU implementation of this path"},
             "e2e": {"value": value, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if wl_name == "c3" and not args.no_sub_records:
+        ms2, nv2, nf2, _ = time_ref("c2", 512, max(3, min(args.steps, 10)), 1)
+        line["sub_records"] = [{"workload": f"c2: {WORKLOADS['c2']['desc']}", "shape": [512] * 3, "same_workload": True,
+                                "value": 512.0 ** 3 / (ms2 * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms2,
+                                "vertices": nv2, "triangles": nf2}]
     print(json.dumps(line), flush=True)
 
 
@@ -423,9 +542,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--even-slabs", action="store_true", help="N > 1: keep the even dim-0 split (default: cuts balanced by measured load)")
+    ap.add_argument("--no-balanced", action="store_true", help="N > 1: skip the extra timing with load-balanced slab cuts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-scaling-base", action="store_true", help="N = 1: skip the extra c3 timing on one GPU")
+    ap.add_argument("--no-sub-records", action="store_true", help="N = 1: skip the c2 / 1024^3 sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

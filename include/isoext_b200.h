@@ -203,24 +203,6 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
                         float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
                         int64_t *counts_out);
 
-/* Chunked, overlapped single-call path for large grids: the slab is cut into n_chunks (<= 8) sub-slabs along
- * x -- the same extended-slab / ownership-by-position logic as the multi-GPU path -- that are enqueued
- * alternately on two internal streams, so the latency-bound surface stage of chunk k overlaps the HBM-bound
- * stream of chunk k+1; two final kernels concatenate the owned vertices and relabel the faces.  One sync.
- * workspace / scratch: TWO consecutive sets (workspace_bytes_each / scratch_bytes_each) sized for the largest
- * chunk.  Vtmp / Ftmp: per-chunk staging at row offsets vtmp_off[k] / ftmp_off[k] with capacities cand_cap[k] /
- * tri_cap[k]; V (v_cap rows) receives only the vertices OWNED by the slab, F (f_cap rows) ids in the slab's
- * extended id space [0,n_lo) below | [n_lo,n_hi) owned | above.  chunk_dev: 10*n_chunks + 8 u32 (device).
- * counts_out: {owned vertices, triangles, n_lo, n_hi, then per chunk S, T, Vc, n_big}.
- * Returns 0, or 1 = not completed (a capacity was too small; counts_out tells what is needed). */
-int isoext_mc_dense_run_chunked(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
-                                const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
-                                int64_t emit_x_hi, float x_lo_threshold, float x_hi_threshold, int n_chunks, void *workspace,
-                                size_t workspace_bytes_each, int64_t cap_entries, void *scratch, size_t scratch_bytes_each,
-                                const int64_t *cand_cap, const int64_t *tri_cap, const int64_t *big_cap, float *Vtmp,
-                                const int64_t *vtmp_off, int32_t *Ftmp, const int64_t *ftmp_off, float *V, int64_t v_cap,
-                                int32_t *F, int64_t f_cap, uint32_t *chunk_dev, void *stream, int64_t *counts_out);
-
 /* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
  * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->
  * base_mine + (id - n_lo); id >= n_hi -> base_next + (id - n_hi). */

@@ -66,9 +66,6 @@ SIGNATURES = {
                                      _vp, _pi64]),
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _vp, _vp, _vp, _pi64]),
-    "isoext_mc_dense_run_chunked": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64, _f32, _f32, _int,
-                                           _vp, _sz, _i64, _vp, _sz, _pi64, _pi64, _pi64, _vp, _pi64, _vp, _pi64, _vp, _i64, _vp,
-                                           _i64, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "isoext_peer_sync_words": (_int, []),
     "isoext_peer_alloc": (_int, [_sz, C.POINTER(_vp), C.POINTER(C.c_ubyte)]),

@@ -19,6 +19,7 @@
 //   k_dc_keys      sortable position keys of the used dual vertices
 //   radix_sort96 + k_unique (weld.cuh): reference order = lexicographic positions
 //   k_dc_faces     orientation flip, shorter-diagonal split, final ids
+#include "../../include/isoext_b200.h"   // the C-ABI prototypes are compiler-checked against the definitions
 #include "dense.cuh"
 #include "radix.cuh"
 #include "weld.cuh"

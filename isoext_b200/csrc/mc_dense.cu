@@ -14,6 +14,7 @@
 // Every arithmetic step that decides a bit of the output uses explicit _rn intrinsics.
 #include <cmath>
 #include <cstdlib>
+#include "../../include/isoext_b200.h"   // the C-ABI prototypes are compiler-checked against the definitions
 #include "dense.cuh"
 #include "radix.cuh"
 #include "weld.cuh"
@@ -530,10 +531,11 @@ int make_dense_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin,
 }
 
 int device_sms() {
-    static int n = 0;
+    static thread_local int n_of[64];   // per device (and per host thread: no lock needed)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &n = n_of[dev & 63];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
@@ -744,200 +746,6 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
     return OK;
 }
 
-// ---- chunked, overlapped single-call path ---------------------------------------------------------
-// EXPERIMENT (kept, tested, off by default in the host layer): cut the slab into n_chunks sub-slabs along x
-// (exactly the multi-GPU slab logic: extended planes, ghost cell layers, ownership by x position), stream
-// them back to back on a low-priority stream and run their surface-sized stages on two high-priority
-// streams, so that the tail of chunk k overlaps the HBM stream of chunk k+1.  Measured on B200 at 1024^3:
-// no gain (1.41 ms vs 1.28 ms unchunked): the surface kernels are bound by memory LATENCY, and with HBM
-// saturated by k_signbits their latencies inflate 3-4x (chunk surface stage 150 -> 560 us, see
-// profiles/r1_chunked_overlap_timeline.txt).  Results are bit-identical to the unchunked path.
-struct ChunkPlan { i64 ext_lo, n_ext, emit_lo, emit_hi; float thr_lo, thr_hi; };
-
-static float host_axis_pos(i64 i, i64 res, float amin, float amax) {
-    float q = (float) (uint32_t) i / (float) (uint32_t) (res - 1);
-    return fmaf(q, amax - amin, amin);
-}
-
-// per-chunk result block (u32 x 8): S, T, VC, NBIG, V, NLO, NHI, ok-so-far
-__global__ void k_chunk_save(const u32 *__restrict__ counters, u32 *__restrict__ out, u32 cap, u32 cand_cap, u32 tri_cap, u32 big_cap) {
-    if (threadIdx.x == 0) {
-        out[0] = counters[C_S]; out[1] = counters[C_T]; out[2] = counters[C_VC]; out[3] = counters[C_NBIG];
-        out[4] = counters[C_V]; out[5] = counters[C_NLO]; out[6] = counters[C_NHI];
-        out[7] = (counters[C_S] <= cap && counters[C_VC] <= cand_cap && counters[C_T] <= tri_cap && counters[C_NBIG] <= big_cap) ? 1u : 0u;
-    }
-}
-// bases[k] = first extended id of chunk k's owned vertices, fbase[k] = first triangle; totals + ok flag
-__global__ void k_chunk_bases(const u32 *__restrict__ cc, int n_chunks, u32 *__restrict__ bases /* 2*(n+1)+4 */, u32 v_cap, u32 f_cap) {
-    if (threadIdx.x == 0) {
-        u32 vb = cc[5], fb = 0, ok = 1;   // ids below chunk 0's lower threshold keep their place: [0, n_lo_0)
-        for (int k = 0; k < n_chunks; k++) {
-            bases[k] = vb;
-            bases[n_chunks + 1 + k] = fb;
-            vb += cc[8 * k + 6] - cc[8 * k + 5];
-            fb += cc[8 * k + 1];
-            ok &= cc[8 * k + 7];
-        }
-        bases[n_chunks] = vb;
-        bases[2 * n_chunks + 1] = fb;
-        const u32 n_own = vb - cc[5];
-        if (n_own > v_cap || fb > f_cap) ok = 0;
-        bases[2 * n_chunks + 2] = ok;
-        bases[2 * n_chunks + 3] = n_own;
-    }
-}
-struct ChunkPtrs { const float *v[8]; const int *f[8]; };
-__global__ void __launch_bounds__(256) k_chunk_gather_v(ChunkPtrs cp, const u32 *__restrict__ cc, const u32 *__restrict__ bases, int n_chunks,
-                                                        float *__restrict__ V) {
-    if (!bases[2 * n_chunks + 2]) return;
-    const int k = blockIdx.y;
-    const u32 n_lo = cc[8 * k + 5], n_hi = cc[8 * k + 6], n_lo0 = cc[5];
-    const u32 n = 3 * (n_hi - n_lo);
-    const float *src = cp.v[k] + 3 * (size_t) n_lo;
-    float *dst = V + 3 * (size_t) (bases[k] - n_lo0);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-__global__ void __launch_bounds__(256) k_chunk_gather_f(ChunkPtrs cp, const u32 *__restrict__ cc, const u32 *__restrict__ bases, int n_chunks,
-                                                        int *__restrict__ F) {
-    if (!bases[2 * n_chunks + 2]) return;
-    const int k = blockIdx.y;
-    const u32 n_lo = cc[8 * k + 5], n_hi = cc[8 * k + 6];
-    const u32 vb = bases[k], vnext = bases[k + 1];
-    const u32 n = 3 * cc[8 * k + 1];
-    const int *src = cp.f[k];
-    int *dst = F + 3 * (size_t) bases[n_chunks + 1 + k];
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const u32 id = (u32) src[i];
-        dst[i] = (int) (id < n_lo ? vb - (n_lo - id) : (id < n_hi ? vb + (id - n_lo) : vnext + (id - n_hi)));
-    }
-}
-
-// Chunked single-call path (see the comment above k_chunk_save).  Geometry arguments as isoext_mc_dense_run.
-//   workspace / scratch: TWO consecutive sets of workspace_bytes_each / scratch_bytes_each bytes, sized for
-//     the largest chunk: isoext_mc_dense_workspace_bytes(max planes, Y, Z, cap_entries) and
-//     isoext_mc_dense_scratch_bytes(max cand_cap[k]).
-//   cand_cap / tri_cap / big_cap [n_chunks]: per-chunk capacities; Vtmp / Ftmp: per-chunk staging outputs, chunk k
-//     at row offset vtmp_off[k] / ftmp_off[k]; V (v_cap rows) receives ONLY the vertices owned by this slab,
-//     F (f_cap rows) ids in the slab's extended id space (see counts_out);  chunk_dev: 8*n_chunks + 2*n_chunks + 8 u32.
-//   counts_out: [0] owned vertices, [1] triangles, [2] n_lo, [3] n_hi, then per chunk {S, T, Vc, n_big}.
-// Returns 0, or 1 ("not completed": some capacity was too small; counts_out holds what is needed).
-int isoext_mc_dense_run_chunked(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
-                                const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
-                                int64_t emit_x_hi, float x_lo_threshold, float x_hi_threshold, int n_chunks, void *workspace,
-                                size_t workspace_bytes_each, int64_t cap_entries, void *scratch, size_t scratch_bytes_each,
-                                const int64_t *cand_cap, const int64_t *tri_cap, const int64_t *big_cap, float *Vtmp,
-                                const int64_t *vtmp_off, int32_t *Ftmp, const int64_t *ftmp_off, float *V, int64_t v_cap, int32_t *F,
-                                int64_t f_cap, uint32_t *chunk_dev, void *stream_, int64_t *counts_out) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
-    if (n_chunks < 1 || n_chunks > 8) return fail(E_INVALID, "n_chunks must be 1..8");
-    if ((Y * Z) % 8 != 0) return fail(E_INVALID, "chunking needs Y*Z to be a multiple of 8 (32-byte aligned planes)");
-    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
-    if (emit_x_hi - emit_x_lo < 2 * n_chunks) return fail(E_INVALID, "too few cell layers for this many chunks");
-    // one low-priority stream for the volume streams, two high-priority streams for the surface stages
-    static cudaStream_t s_lo = nullptr, cs[2] = {nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_sb[8], ev_comp[8];
-    if (!s_lo) {
-        int lo_p = 0, hi_p = 0;
-        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
-        ISX_CUDA(cudaStreamCreateWithPriority(&s_lo, cudaStreamNonBlocking, lo_p));
-        for (int i = 0; i < 2; i++) {
-            ISX_CUDA(cudaStreamCreateWithPriority(&cs[i], cudaStreamNonBlocking, hi_p));
-            ISX_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
-        }
-        for (int i = 0; i < 8; i++) {
-            ISX_CUDA(cudaEventCreateWithFlags(&ev_sb[i], cudaEventDisableTiming));
-            ISX_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-        }
-        ISX_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    }
-    ChunkPlan plan[8];
-    i64 max_planes = 0, max_cand = 0;
-    for (int k = 0; k < n_chunks; k++) {
-        const i64 c_lo = emit_x_lo + (emit_x_hi - emit_x_lo) * k / n_chunks, c_hi = emit_x_lo + (emit_x_hi - emit_x_lo) * (k + 1) / n_chunks;
-        ChunkPlan &q = plan[k];
-        q.ext_lo = c_lo - 1 < 0 ? 0 : c_lo - 1;
-        const i64 ext_hi = c_hi + 1 > X - 1 ? X - 1 : c_hi + 1;
-        q.n_ext = ext_hi - q.ext_lo + 1;
-        q.emit_lo = c_lo - q.ext_lo;
-        q.emit_hi = c_hi - q.ext_lo;
-        q.thr_lo = k == 0 ? x_lo_threshold : host_axis_pos(c_lo + x_offset, X_global, aabb_min[0], aabb_max[0]);
-        q.thr_hi = k == n_chunks - 1 ? x_hi_threshold : host_axis_pos(c_hi + x_offset, X_global, aabb_min[0], aabb_max[0]);
-        if (q.n_ext > max_planes) max_planes = q.n_ext;
-        if (cand_cap[k] > max_cand) max_cand = cand_cap[k];
-        if (cand_cap[k] < 1 || cand_cap[k] >= ((i64) 1 << 29) || tri_cap[k] < 1 || big_cap[k] < 0 || big_cap[k] > cand_cap[k])
-            return fail(E_INVALID, "chunk capacities out of range");
-    }
-    if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
-    u32 *cc = chunk_dev, *bases = chunk_dev + 8 * n_chunks;
-    ISX_CUDA(cudaEventRecord(ev_fork, stream));
-    ISX_CUDA(cudaStreamWaitEvent(s_lo, ev_fork, 0));
-    ISX_CUDA(cudaStreamWaitEvent(cs[0], ev_fork, 0));
-    ISX_CUDA(cudaStreamWaitEvent(cs[1], ev_fork, 0));
-    ChunkPtrs cp;
-    for (int k = 0; k < 8; k++) { cp.v[k] = nullptr; cp.f[k] = nullptr; }
-    for (int k = 0; k < n_chunks; k++) {
-        const ChunkPlan &q = plan[k];
-        cudaStream_t s_k = cs[k & 1];
-        DenseParams p;
-        int rc = make_dense_params(q.n_ext, Y, Z, x_offset + q.ext_lo, X_global, aabb_min, aabb_max, level, q.emit_lo, q.emit_hi, &p);
-        if (rc != OK) return rc;
-        Carver c(static_cast<char *>(workspace) + (size_t) (k & 1) * workspace_bytes_each);
-        McBuffers b;
-        if (carve_mc(c, p, (size_t) cap_entries, &b) > workspace_bytes_each) return fail(E_WORKSPACE, "workspace too small");
-        Carver csx(static_cast<char *>(scratch) + (size_t) (k & 1) * scratch_bytes_each);
-        McScratch s;
-        if (carve_mc_scratch(csx, (size_t) max_cand, &s) > scratch_bytes_each) return fail(E_WORKSPACE, "scratch too small");
-        const float *vals_k = values + (size_t) q.ext_lo * (size_t) (Y * Z);
-        float *Vk = Vtmp + 3 * (size_t) vtmp_off[k];
-        int32_t *Fk = Ftmp + 3 * (size_t) ftmp_off[k];
-        cp.v[k] = Vk;
-        cp.f[k] = Fk;
-        const u32 tcap = (u32) (tri_cap[k] > 0xffffffffLL ? 0xffffffffLL : tri_cap[k]);
-        // s_k: zero-fill (ordered after chunk k-2, which used the same workspace set on the same stream)
-        rc = enqueue_zero(b, s_k);
-        if (rc != OK) return rc;
-        // s_lo: the volume stream of this chunk.  It reuses the workspace set of chunk k-2, whose layout may
-        // differ (it depends on the chunk's plane count), so it has to wait for that chunk to finish completely.
-        if (k >= 2) ISX_CUDA(cudaStreamWaitEvent(s_lo, ev_comp[k - 2], 0));
-        enqueue_signbits(vals_k, p, b, s_lo);
-        ISX_CUDA(cudaEventRecord(ev_sb[k], s_lo));
-        // s_k: everything surface-sized
-        ISX_CUDA(cudaStreamWaitEvent(s_k, ev_sb[k], 0));
-        enqueue_compact(p, b, (u32) cap_entries, s_k);
-        rc = enqueue_analysis(vals_k, p, method, b, (u32) cap_entries, s_k);
-        if (rc != OK) return rc;
-        rc = enqueue_phase2(vals_k, p, method, b, s, (u32) cap_entries, 0, 0, true, (u32) cand_cap[k], tcap, (u32) big_cap[k], true, q.thr_lo,
-                            q.thr_hi, Vk, Fk, s_k);
-        if (rc != OK) return rc;
-        ISX_LAUNCH(k_chunk_save, 1, 32, 0, s_k, b.counters, cc + 8 * k, (u32) cap_entries, (u32) cand_cap[k], tcap, (u32) big_cap[k]);
-        ISX_CUDA(cudaEventRecord(ev_comp[k], s_k));   // chunk k done: its workspace set may be reused
-    }
-    for (int i = 0; i < 2; i++) {
-        ISX_CUDA(cudaEventRecord(ev_join[i], cs[i]));
-        ISX_CUDA(cudaStreamWaitEvent(stream, ev_join[i], 0));
-    }
-    ISX_LAUNCH(k_chunk_bases, 1, 32, 0, stream, cc, n_chunks, bases, (u32) (v_cap > 0xffffffffLL ? 0xffffffffLL : v_cap),
-               (u32) (f_cap > 0xffffffffLL ? 0xffffffffLL : f_cap));
-    dim3 grid(148 * 4, n_chunks);
-    ISX_LAUNCH(k_chunk_gather_v, grid, 256, 0, stream, cp, cc, bases, n_chunks, V);
-    ISX_LAUNCH(k_chunk_gather_f, grid, 256, 0, stream, cp, cc, bases, n_chunks, F);
-    ISX_CUDA(cudaGetLastError());
-    u32 h[8 * 8 + 2 * 9 + 8];
-    const size_t nwords = (size_t) 8 * n_chunks + 2 * n_chunks + 4;
-    ISX_CUDA(cudaMemcpyAsync(h, chunk_dev, nwords * sizeof(u32), cudaMemcpyDeviceToHost, stream));
-    ISX_CUDA(cudaStreamSynchronize(stream));
-    const u32 *hb = h + 8 * n_chunks;
-    counts_out[0] = hb[2 * n_chunks + 3];              // owned vertices
-    counts_out[1] = hb[2 * n_chunks + 1];              // triangles
-    counts_out[2] = h[5];                              // n_lo of the slab (chunk 0)
-    counts_out[3] = (i64) h[5] + hb[2 * n_chunks + 3]; // n_hi
-    for (int k = 0; k < n_chunks; k++)
-        for (int j = 0; j < 4; j++) counts_out[4 + 4 * k + j] = h[8 * k + j];
-    return hb[2 * n_chunks + 2] ? OK : 1;
-}
-
-// (X,Y,Z,3) grid point positions.
 int isoext_grid_points_dense(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
                              const float *aabb_max, float *out, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -15,6 +15,7 @@
 // Ranks may drift apart by at most world-1 epochs (a pull needs the neighbour's READY of the same epoch),
 // so a ring of 32 slots serves any single-node world size.  Every spin is bounded by a wall-clock timeout;
 // on expiry the kernel raises *err (host-mapped memory) and stops waiting, and the host layer throws.
+#include "../../include/isoext_b200.h"   // the C-ABI prototypes are compiler-checked against the definitions
 #include "common.cuh"
 
 namespace isx {

@@ -725,7 +725,13 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
                                        u32 nb, u32 n_big, const u32 *nbig_dev, u32 big_cap, const SegHead &h, const SegScratch &b,
                                        const SegGeom &geom, bool allow_radix, u32 *radix_needed, cudaStream_t stream) {
     constexpr size_t smem_big = SegCfg<SEG_CAP, SEG_THREADS>::SMEM, smem_small = SegCfg<SEG_SMALL, 128>::SMEM;
-    static bool attr_set = false;
+    // per device: the attribute belongs to the device's context; per host thread: the auxiliary stream / event pair
+    // below must not be shared by concurrent callers (thread_local, so no lock is needed)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    static thread_local bool attr_set_of[64];
+    bool &attr_set = attr_set_of[dev];
     if (!attr_set) {
         cudaFuncSetAttribute(k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_big);
         cudaFuncSetAttribute(k_seg_sort<SEG_SMALL, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_small);
@@ -739,24 +745,23 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
     (void) blocks;
     // The two instances work on disjoint buckets and each is dominated by its slowest bucket (ncu: 13 % / 32 % SM
     // throughput), so the small-bucket instance runs on an auxiliary stream next to the large one and the second level.
-    static cudaStream_t aux_of[64];            // one auxiliary stream + event pair per device, created on first use
-    static cudaEvent_t fork_of[64], join_of[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
+    static thread_local cudaStream_t aux_of[64];   // one auxiliary stream + event pair per device and host thread, created on first use
+    static thread_local cudaEvent_t fork_of[64], join_of[64];
     if (!aux_of[dev]) {
-        if (cudaStreamCreateWithFlags(&aux_of[dev], cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
-        cudaEventCreateWithFlags(&fork_of[dev], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&join_of[dev], cudaEventDisableTiming);
+        cudaError_t e0 = cudaStreamCreateWithFlags(&aux_of[dev], cudaStreamNonBlocking);
+        if (e0 == cudaSuccess) e0 = cudaEventCreateWithFlags(&fork_of[dev], cudaEventDisableTiming);
+        if (e0 == cudaSuccess) e0 = cudaEventCreateWithFlags(&join_of[dev], cudaEventDisableTiming);
+        if (e0 != cudaSuccess) { aux_of[dev] = nullptr; return e0; }
     }
     const cudaStream_t aux = aux_of[dev];
     const cudaEvent_t ev_fork = fork_of[dev], ev_join = join_of[dev];
-    cudaEventRecord(ev_fork, stream);
-    cudaStreamWaitEvent(aux, ev_fork, 0);
+    cudaError_t ef = cudaEventRecord(ev_fork, stream);
+    if (ef == cudaSuccess) ef = cudaStreamWaitEvent(aux, ev_fork, 0);
+    if (ef != cudaSuccess) return ef;
     const u32 grid_small = nb < 148u * 32u ? nb : 148u * 32u, grid_large = nb < 148u * 8u ? nb : 148u * 8u;
     ISX_LAUNCH((k_seg_sort<SEG_SMALL, 128, 1>), grid_small, 128, smem_small, aux, kx, ky, kz, h.count, h.start, b.perm0, b.perm,
                b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
-    cudaEventRecord(ev_join, aux);
+    if ((ef = cudaEventRecord(ev_join, aux)) != cudaSuccess) return ef;
     ISX_LAUNCH((k_seg_sort<SEG_CAP, SEG_THREADS, SEG_SMALL + 1>), grid_large, SEG_THREADS, smem_big, stream, kx, ky, kz, h.count,
                h.start, b.perm0, b.perm, b.skx, b.sky, b.skz, n_dev, n_cap, nb, geom);
     const u32 fb_n = nbig_dev ? big_cap : n_big;
@@ -785,7 +790,7 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         // 14 launches that do nothing in the common case, so the single-sync path only enqueues them when the
         // previous extraction of the grid needed them (*radix_needed tells the host)
         if (!allow_radix) {
-            cudaStreamWaitEvent(stream, ev_join, 0);
+            if ((ef = cudaStreamWaitEvent(stream, ev_join, 0)) != cudaSuccess) return ef;
             return cudaGetLastError();
         }
         e = radix_sort96(b.bkx, b.bky, b.bkz, fb_n, b.radix, stream, b.info2 + 4);
@@ -793,7 +798,7 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
         ISX_LAUNCH(k_seg_big_scatter, bb, 256, 0, stream, fb_n, b.info2 + 4, b.radix.perm[0], b.bid, b.cbucket, h.start, h.bigoff, b.perm, b.bkx,
                    b.bky, b.bkz, b.skx, b.sky, b.skz);
     }
-    cudaStreamWaitEvent(stream, ev_join, 0);
+    if ((ef = cudaStreamWaitEvent(stream, ev_join, 0)) != cudaSuccess) return ef;
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@
 // A sparse cell carries its own 8 corner values, which need not agree with its neighbours', so
 // vertices are welded by position only (exactly the reference's semantics): every (cell, edge) vertex
 // that a kept triangle references becomes a sort candidate.
+#include "../../include/isoext_b200.h"   // the C-ABI prototypes are compiler-checked against the definitions
 #include "dense.cuh"
 #include "radix.cuh"
 #include "weld.cuh"

@@ -50,10 +50,6 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     thr_lo, thr_hi = float(x_thresholds[0]), float(x_thresholds[1])
 
     if hints is not None and hints.get("Vc", 0) > 0 and hints.get("T", 0) > 0:
-        out = _try_chunked(lib, values, (X, Y, Z), x_offset, xg, amin, amax, level, method_id, lo, hi, thr_lo, thr_hi, ws, cap,
-                           hints, stream)
-        if out is not None:
-            return out
         cand_cap = hints["Vc"] + (hints["Vc"] >> 6) + 16
         tri_cap = hints["T"] + (hints["T"] >> 6) + 16
         nb_hint = hints.get("n_big", 0)
@@ -106,72 +102,6 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
                                         stream, out))
     n_lo, n_hi = int(out[1]), int(out[2])
     return V[n_lo:n_hi], F, n_lo, n_hi, max(cap, S)
-
-
-CHUNK_MIN_POINTS = 1 << 62     # chunked/overlapped path is opt-in: measured slower than the plain path (see mc_dense.cu)
-
-
-def _chunk_count(P: int) -> int:
-    return min(8, P >> 28)
-
-
-def _try_chunked(lib, values, shape, x_offset, xg, amin, amax, level, method_id, lo, hi, thr_lo, thr_hi, ws, cap, hints, stream):
-    """Chunked, two-stream overlapped path (isoext_mc_dense_run_chunked).  Returns the result tuple, or None if
-    the grid is too small / not eligible / a capacity guess was too small (the caller then continues with
-    the unchunked paths, which also refresh the hints)."""
-    X, Y, Z = shape
-    P = X * Y * Z
-    K = _chunk_count(P)
-    if P < CHUNK_MIN_POINTS or K < 2 or (Y * Z) % 8 != 0 or hi - lo < 2 * K:
-        return None
-    dev = values.device
-    slack = lambda n: n + (n >> 6) + 16
-    per = hints.get("chunks")
-    if per is not None and len(per) == K:
-        cand = [slack(c[2]) for c in per]
-        tri = [slack(c[1]) for c in per]
-        big = [min(slack(c[3]), cd) if c[3] > 0 else 0 for c, cd in zip(per, cand)]
-        ecap = max(cap, max(c[0] for c in per) + 1024)
-    else:   # bootstrap from the totals of the previous (unchunked) extraction: every chunk could hold everything
-        cand = [slack(hints["Vc"])] * K
-        tri = [slack(hints["T"])] * K
-        nb = hints.get("n_big", 0)
-        big = [min(slack(nb), cand[0]) if nb > 0 else 0] * K
-        ecap = cap
-    v_cap, f_cap = slack(hints["Vc"]), slack(hints["T"])
-    max_planes = -(-(hi - lo) // K) + 3
-    ws_each = lib.isoext_mc_dense_workspace_bytes(min(max_planes, X), Y, Z, ecap)
-    sc_each = lib.isoext_mc_dense_scratch_bytes(max(cand))
-    wsbuf = ws.get("mc_ws2", 2 * ws_each, dev)
-    scratch = ws.get("mc_scratch2", 2 * sc_each, dev)
-    voff = [0] * K
-    foff = [0] * K
-    for k in range(1, K):
-        voff[k] = voff[k - 1] + cand[k - 1]
-        foff[k] = foff[k - 1] + tri[k - 1]
-    vtmp = ws.get("mc_vtmp", 12 * (voff[-1] + cand[-1]), dev)
-    ftmp = ws.get("mc_ftmp", 12 * (foff[-1] + tri[-1]), dev)
-    cdev = ws.get("mc_chunkdev", 4 * (10 * K + 16), dev)
-    V = torch.empty((v_cap, 3), dtype=torch.float32, device=dev)
-    F = torch.empty((f_cap, 3), dtype=torch.int32, device=dev)
-    arr = lambda xs: (C.c_int64 * K)(*xs)
-    counts = (C.c_int64 * (4 + 4 * K))()
-    rc = lib.isoext_mc_dense_run_chunked(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
-                                         thr_lo, thr_hi, K, wsbuf.data_ptr(), ws_each, ecap, scratch.data_ptr(), sc_each, arr(cand),
-                                         arr(tri), arr(big), vtmp.data_ptr(), arr(voff), ftmp.data_ptr(), arr(foff), V.data_ptr(), v_cap,
-                                         F.data_ptr(), f_cap, cdev.data_ptr(), stream, counts)
-    if rc not in (0, 1):
-        _lib.check(rc)
-    per = [tuple(int(counts[4 + 4 * k + j]) for j in range(4)) for k in range(K)]
-    hints["chunks"] = per
-    if rc == 1:
-        if max(c[0] for c in per) > ecap:
-            hints["chunks"] = None   # entry capacity: let the unchunked path re-measure
-        return None
-    n_own, T, n_lo, n_hi = int(counts[0]), int(counts[1]), int(counts[2]), int(counts[3])
-    if n_own == 0 and T == 0:
-        return None, None, 0, 0, cap
-    return V[:n_own], F[:T], n_lo, n_hi, cap
 
 
 def marching_cubes(grid, level: float = 0.0, method: str = "nagae"):

@@ -8,7 +8,7 @@
  * Parity status: PINNED.  tests/test_oracle_golden.py checks this file against every known-answer
  * count the reference records in its executed notebooks (doc/marching_cubes.ipynb:60-61,113-114,
  * 144-146; doc/grids.ipynb:172; doc/occupancy_grids.ipynb:88; doc/quickstart.ipynb:21;
- * doc/dual_contouring.ipynb:51-52,104) and tests/test_ref_parity.py (GPU) checks it bit-for-bit
+ * doc/dual_contouring.ipynb:51-52,104) and tests/test_mc_gpu.py / tests/test_dc_parity3_gpu.py (GPU) checks it bit-for-bit
  * against the reference's own CUDA build (oracle/_ref/libisoext_ref.so).
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math  (no FMA contraction: every fused
@@ -549,8 +549,13 @@ int orc_dual_contouring(const orc_its *its, int64_t X, int64_t Y, int64_t Z, con
         Q++;
         /* src/dc.cu:129-155 */
         f3 v0 = dvf[q[0]], v1 = dvf[q[1]], v2 = dvf[q[2]], v3 = dvf[q[3]];
-        float d02 = sqrtf((v0.x - v2.x) * (v0.x - v2.x) + (v0.y - v2.y) * (v0.y - v2.y) + (v0.z - v2.z) * (v0.z - v2.z));
-        float d13 = sqrtf((v1.x - v3.x) * (v1.x - v3.x) + (v1.y - v3.y) * (v1.y - v3.y) + (v1.z - v3.z) * (v1.z - v3.z));
+        /* norm() of include/math.cuh as nvcc contracts it (SASS of get_triangles_op): sqrt(fma(dz,dz, fma(dx,dx, dy*dy))).
+         * Pinned on the GPU: tests/test_dc_parity3_gpu.py feeds the reference's own dual vertices through the product's
+         * split and obtains the reference's F bit for bit, and the product's split equals this one. */
+        float dx02 = v0.x - v2.x, dy02 = v0.y - v2.y, dz02 = v0.z - v2.z;
+        float dx13 = v1.x - v3.x, dy13 = v1.y - v3.y, dz13 = v1.z - v3.z;
+        float d02 = sqrtf(fmaf(dz02, dz02, fmaf(dx02, dx02, dy02 * dy02)));
+        float d13 = sqrtf(fmaf(dz13, dz13, fmaf(dx13, dx13, dy13 * dy13)));
         if (d02 > d13) {
             f3vec_push(&corners, v1); f3vec_push(&corners, v3); f3vec_push(&corners, v0);
             f3vec_push(&corners, v3); f3vec_push(&corners, v1); f3vec_push(&corners, v2);

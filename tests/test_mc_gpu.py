@@ -256,24 +256,3 @@ def test_capacity_retry_path(iso):
     v, f = run_ours(iso, vals)
     ov, of, _ = oracle.mc_dense(vals.numpy())
     assert_same_mesh(v, f, ov, of)
-
-
-def test_chunked_overlapped_path_equals_unchunked(iso, monkeypatch):
-    """isoext_mc_dense_run_chunked (x-chunks on three streams; opt-in, see mc_dense.cu).  Force it on small
-    grids and compare with the plain path bit for bit: a curved field, a box with faces on chunk boundaries
-    (exact-level hits, oversized x-buckets -> radix fallback) and noise."""
-    from isoext_b200 import mc as mcmod
-    for vals in (fields.eval_field(fields.torus(), (96, 64, 128)), fields.eval_field(S.CuboidSDF([1, 1, 1]), (65, 64, 64)),
-                 fields.eval_field(fields.csg_box_minus_sphere(), (80, 160, 128)), fields.noise((48, 16, 24), 6)):
-        g = iso.UniformGrid(list(vals.shape))
-        g.set_values(vals.cuda())
-        monkeypatch.setattr(mcmod, "CHUNK_MIN_POINTS", 1 << 62)
-        v0, f0 = iso.marching_cubes(g)
-        monkeypatch.setattr(mcmod, "CHUNK_MIN_POINTS", 0)
-        monkeypatch.setattr(mcmod, "_chunk_count", lambda P: 4, raising=False)
-        g2 = iso.UniformGrid(list(vals.shape))
-        g2.set_values(vals.cuda())
-        for _ in range(4):   # 1st: two-phase, 2nd: chunked bootstrap, 3rd+: chunked with per-chunk hints
-            v, f = iso.marching_cubes(g2)
-            assert torch.equal(v.view(torch.int32), v0.view(torch.int32)) and torch.equal(f, f0)
-        assert g2._hints.get("chunks") is not None
