@@ -155,6 +155,26 @@ int isoext_sparse_points(int64_t X, int64_t Y, int64_t Z, const float *aabb_min,
                          const int64_t *cell_idx, int64_t n, float *d_out, void *stream);
 /* filter_cell_indices (src/grid/sparse.cu:150-179): keep[i] = 1 iff cell i's case is not 0/255 */
 int isoext_sparse_crossing(const float *values8, int64_t n, float level, unsigned char *keep, void *stream);
+/* ---- cell-list maintenance and index utilities (csrc/setops.cu) ---------------------------------
+ * workspace: isoext_setops_workspace_bytes(max number of ids of the call).  Each call synchronises the
+ * stream once to return its count.
+ * add_cells (src/grid/sparse.cu:71-97: thrust sort + unique + set_union): out = sorted unique ids of `ids`
+ * (the host layer passes old list ++ new ids); out has room for n. */
+size_t isoext_setops_workspace_bytes(int64_t n);
+int isoext_ids_sort_unique(const int64_t *ids, int64_t n, int64_t *d_out, void *workspace, size_t workspace_bytes,
+                           void *stream, int64_t *n_out);
+/* remove_cells (src/grid/sparse.cu:99-126: thrust set_difference): out = a (sorted unique) minus b (any order). */
+int isoext_ids_difference(const int64_t *a, int64_t na, const int64_t *b, int64_t nb, int64_t *d_out, void *workspace,
+                          size_t workspace_bytes, void *stream, int64_t *n_out);
+/* the copy_if of filter_cell_indices (src/grid/sparse.cu:170-178): stable compaction of 4- or 8-byte items. */
+int isoext_compact_flagged(const void *src, int elem_bytes, const unsigned char *keep, int64_t n, void *d_out,
+                           void *workspace, size_t workspace_bytes, void *stream, int64_t *n_out);
+/* UniformGrid::get_cells (src/grid/uniform.cu:42-51, include/utils.cuh:32-60): (X-1,Y-1,Z-1,8) corner point ids,
+ * uint32 (wide = 0, the reference's type) or int64 (wide = 1, needed above 2^32 points). */
+int isoext_grid_cells_dense(int64_t X, int64_t Y, int64_t Z, int wide, void *d_out, void *stream);
+/* welded vertices per cell layer along x (no reference counterpart: input of the slab balancer, dist.py). */
+int isoext_vertex_layer_histogram(const float *V, int64_t n, float aabb_min_x, float aabb_max_x, int64_t layers,
+                                  uint32_t *d_hist, void *stream);
 /* marching_cubes on a SparseGrid: phase 1 counts_out[0..1] = T, Vc; phase 2 counts_out[0] = V */
 size_t isoext_mc_sparse_workspace_bytes(int64_t n);
 size_t isoext_sparse_scratch_bytes(int64_t n_candidates);

@@ -51,6 +51,12 @@ SIGNATURES = {
                                     _sz, _i64, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_sparse_points": (_int, [_i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp]),
     "isoext_sparse_crossing": (_int, [_vp, _i64, _f32, _vp, _vp]),
+    "isoext_setops_workspace_bytes": (_sz, [_i64]),
+    "isoext_ids_sort_unique": (_int, [_vp, _i64, _vp, _vp, _sz, _vp, _pi64]),
+    "isoext_ids_difference": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp, _pi64]),
+    "isoext_compact_flagged": (_int, [_vp, _int, _vp, _i64, _vp, _vp, _sz, _vp, _pi64]),
+    "isoext_grid_cells_dense": (_int, [_i64, _i64, _i64, _int, _vp, _vp]),
+    "isoext_vertex_layer_histogram": (_int, [_vp, _i64, _f32, _f32, _i64, _vp, _vp]),
     "isoext_mc_sparse_workspace_bytes": (_sz, [_i64]),
     "isoext_sparse_scratch_bytes": (_sz, [_i64]),
     "isoext_mc_sparse_count": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _vp, _sz, _vp, _pi64]),

@@ -1,4 +1,5 @@
 // api.cu -- error plumbing and library identification of the C-ABI (include/isoext_b200.h).
+#include "../../include/isoext_b200.h"   // the C-ABI prototypes are compiler-checked against the definitions
 #include "common.cuh"
 
 #include <cmath>

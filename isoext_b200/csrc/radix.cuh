@@ -200,8 +200,9 @@ k_radix_pass(const u32 *__restrict__ key_in, const u32 *__restrict__ perm_in, u3
 // Enqueue the whole sort on `stream`.  Result: b.perm[0] holds the sorted order (item ids).
 // kx/ky/kz: order-preserving u32 keys (float_key).  n may be 0.  If n_dev != nullptr the item count is read
 // on the device (it must be <= n, which then only sizes the launches and the descriptor reset).
+// first_pass (0, 4 or 8): skip the digit places of kz (and ky): 4 = 64-bit keys (kx, ky), 8 = 32-bit keys (kx).
 static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const RadixBuffers &b,
-                                       cudaStream_t stream, const u32 *n_dev = nullptr) {
+                                       cudaStream_t stream, const u32 *n_dev = nullptr, int first_pass = 0) {
     if (n == 0) return cudaSuccess;
     const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
     cudaError_t e = cudaMemsetAsync(b.hist, 0, (RADIX_PASSES * 256 + 16) * sizeof(u32), stream);
@@ -213,11 +214,11 @@ static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *
     ISX_LAUNCH(k_radix_hist, hist_blocks, 256, 0, stream, kx, ky, kz, n, b.hist, n_dev);
     ISX_LAUNCH(k_radix_prefix, 1, 32 * RADIX_PASSES, 0, stream, b.hist);
     const u32 *src[3] = {kz, ky, kx};
-    for (int p = 0; p < RADIX_PASSES; p++) {
+    for (int p = first_pass; p < RADIX_PASSES; p++) {
         const int in = p & 1, out = in ^ 1;
         const u32 shift = 8 * (p & 3);
         const u32 *coord = src[p >> 2];
-        if (p == 0)
+        if (p == first_pass)
             ISX_LAUNCH((k_radix_pass<true, true>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
                        shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
         else if ((p & 3) == 0)

@@ -103,7 +103,16 @@ def vertex_layer_histogram(v_own: torch.Tensor, X: int, aabb_min_x: float, aabb_
     """Vertices per cell layer of the GLOBAL mesh (sum over ranks of this rank's owned vertices): the measured
     surface load behind ``balanced_cuts``."""
     layers = X - 1
-    if v_own.numel():
+    if v_own.is_cuda:
+        from . import _lib
+        from .grid import _stream_ptr
+        h32 = torch.empty(layers, dtype=torch.int32, device=v_own.device)
+        v = v_own.contiguous()
+        with torch.cuda.device(v_own.device):
+            _lib.check(_lib.lib().isoext_vertex_layer_histogram(v.data_ptr(), v.shape[0], float(aabb_min_x), float(aabb_max_x), layers,
+                                                                h32.data_ptr(), _stream_ptr()))
+        h = h32.to(torch.float64)
+    elif v_own.numel():      # host tensors (CPU unit tests of the balancer)
         t = (v_own[:, 0].double() - aabb_min_x) / (aabb_max_x - aabb_min_x) * layers
         h = torch.bincount(t.floor().clamp_(0, layers - 1).long(), minlength=layers).to(torch.float64)
     else:

@@ -133,10 +133,15 @@ class UniformGrid(Grid):
         return self._values
 
     def get_cells(self) -> torch.Tensor:
-        """(X-1, Y-1, Z-1, 8) point ids per cell in Morton corner order (include/utils.cuh:32-60).
-        Only for inspection: no kernel of this package consumes it."""
+        """(X-1, Y-1, Z-1, 8) point ids per cell in Morton corner order (src/grid/uniform.cu:42-51,
+        include/utils.cuh:32-60): uint32 like the reference while the ids fit, int64 beyond 2^32 points (where the
+        reference overflows).  Only for inspection: no kernel of this package consumes it."""
         X, Y, Z = self.shape
-        ar = lambda n: torch.arange(n, device=self.device, dtype=torch.int64)
-        base = (ar(X - 1)[:, None, None] * Y + ar(Y - 1)[None, :, None]) * Z + ar(Z - 1)[None, None, :]
-        offs = torch.tensor([(i >> 2 & 1) * Y * Z + (i >> 1 & 1) * Z + (i & 1) for i in range(8)], device=self.device)
-        return _as_uint32(base[..., None] + offs)
+        wide = X * Y * Z > 0xFFFFFFFF + 1
+        try:
+            out = torch.empty((X - 1, Y - 1, Z - 1, 8), dtype=torch.int64 if wide else torch.uint32, device=self.device)
+        except (RuntimeError, TypeError):          # a torch build without uint32 CUDA tensors
+            wide, out = True, torch.empty((X - 1, Y - 1, Z - 1, 8), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().isoext_grid_cells_dense(X, Y, Z, int(wide), out.data_ptr(), _stream_ptr()))
+        return out

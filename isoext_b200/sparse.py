@@ -2,8 +2,8 @@
 mirror of the reference's SparseGrid binding (src/isoext_ext.cu:170-303, src/grid/sparse.cu) over the
 sm_100a kernels in csrc/sparse.cu.
 
-List maintenance (sorted-unique insert, set difference) is integer bookkeeping on N cell ids and uses
-torch; everything that touches corner values or positions goes through the C-ABI kernels.
+Everything goes through the C-ABI kernels: list maintenance (sorted-unique insert, set difference, filter
+compaction: csrc/setops.cu) as well as whatever touches corner values or positions (csrc/sparse.cu).
 Extension: cell-index tensors may be int64 (needed beyond INT_MAX points, e.g. 4096^3-equivalent
 narrow bands); int32 in -> int32 out, exactly like the reference, otherwise int64."""
 from __future__ import annotations
@@ -20,6 +20,22 @@ def _idx_tensor(t, what):
     if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dim() != 1 or t.dtype not in (torch.int32, torch.int64):
         raise TypeError(f"{what}: expected a 1-D int32 (or int64) CUDA tensor")
     return t.contiguous()
+
+
+def _ids64(t: torch.Tensor) -> torch.Tensor:
+    """int32 ids are the reference's API type; it reinterprets them as uint32 (NDArray<int>::cast<uint>)."""
+    return (t.to(torch.int64) & 0xFFFFFFFF) if t.dtype == torch.int32 else t
+
+
+def _setop(fn_name, ws: _Workspace, device, n_ws, out_n, *args):
+    """Run one csrc/setops.cu entry point: (args..., out, workspace, bytes, stream) -> first n_out items of out."""
+    lib = _lib.lib()
+    out = torch.empty(max(int(out_n), 1), dtype=torch.int64, device=device)
+    wsbuf = ws.get("setops", lib.isoext_setops_workspace_bytes(max(int(n_ws), 1)), device)
+    n_out = C.c_int64(0)
+    with torch.cuda.device(device):
+        _lib.check(getattr(lib, fn_name)(*args, out.data_ptr(), wsbuf.data_ptr(), wsbuf.numel(), _stream_ptr(), C.byref(n_out)))
+    return out[:n_out.value]
 
 
 class SparseGrid(Grid):
@@ -62,13 +78,17 @@ class SparseGrid(Grid):
         """Insert cells; like the reference this resets ALL values to the default (sparse.cu:94-95)."""
         t = _idx_tensor(new_cell_indices, "new_cell_indices")
         self._int32_api = self._int32_api and t.dtype == torch.int32
-        self._cells = torch.unique(torch.cat([self._cells, t.to(torch.int64)]))   # sorted + unique
+        both = torch.cat([self._cells, _ids64(t)])
+        self._cells = _setop("isoext_ids_sort_unique", self._ws, self.device, both.numel(), both.numel(),
+                             both.data_ptr(), both.numel()).clone()
         self._reset_values()
 
     def remove_cells(self, cell_indices: torch.Tensor) -> None:
         """Remove cells (set difference); resets all values to the default (sparse.cu:119-120)."""
-        t = _idx_tensor(cell_indices, "new_cell_indices").to(torch.int64)
-        self._cells = self._cells[~torch.isin(self._cells, t)]
+        t = _ids64(_idx_tensor(cell_indices, "new_cell_indices")).contiguous()
+        n = self._cells.numel()
+        self._cells = _setop("isoext_ids_difference", self._ws, self.device, max(n, t.numel()), n,
+                             self._cells.data_ptr(), n, t.data_ptr(), t.numel()).clone()
         self._reset_values()
 
     def get_cell_indices(self) -> torch.Tensor:
@@ -118,10 +138,19 @@ class SparseGrid(Grid):
         _expect_cuda(values, torch.float32, ndim=2, last=8, what="values")
         if values.shape[0] != t.numel():
             raise RuntimeError("values must have one row per cell index")
-        keep = torch.empty(t.numel(), dtype=torch.uint8, device=self.device)
+        n = t.numel()
+        if values.data_ptr() % 16:      # the kernel reads each row with two 128-bit loads
+            values = values.clone()
+        keep = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
+        out = torch.empty(max(n, 1), dtype=t.dtype, device=self.device)
+        lib = _lib.lib()
+        wsbuf = self._ws.get("setops", lib.isoext_setops_workspace_bytes(max(n, 1)), self.device)
+        n_out = C.c_int64(0)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().isoext_sparse_crossing(values.data_ptr(), t.numel(), float(level), keep.data_ptr(), _stream_ptr()))
-        return t[keep.bool()]
+            _lib.check(lib.isoext_sparse_crossing(values.data_ptr(), n, float(level), keep.data_ptr(), _stream_ptr()))
+            _lib.check(lib.isoext_compact_flagged(t.data_ptr(), t.element_size(), keep.data_ptr(), n, out.data_ptr(), wsbuf.data_ptr(),
+                                                  wsbuf.numel(), _stream_ptr(), C.byref(n_out)))
+        return out[:n_out.value]
 
     def _geom(self):
         X, Y, Z = self.shape

@@ -8,6 +8,7 @@ legs may import this package; ``isoext_b200`` never does.
 from .cpu import (  # noqa: F401
     build_c,
     case_histogram,
+    cells_dense,
     dual_contouring,
     get_intersection,
     mc_dense,

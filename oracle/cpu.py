@@ -95,6 +95,27 @@ def points_cells(shape, cell_idx, aabb_min=(-1, -1, -1), aabb_max=(1, 1, 1)) -> 
     return out
 
 
+def cells_dense(shape) -> np.ndarray:
+    """(X-1,Y-1,Z-1,8) corner point ids of every cell -- UniformGrid::get_cells, src/grid/uniform.cu:42-51 with
+    idx_to_cell_op, include/utils.cuh:32-60 (integer index arithmetic, restated in numpy; int64, no overflow)."""
+    X, Y, Z = (int(s) for s in shape)
+    i = np.arange((X - 1) * (Y - 1) * (Z - 1), dtype=np.int64)
+    z = i % (Z - 1); i = i // (Z - 1)
+    y = i % (Y - 1)
+    x = i // (Y - 1)
+    yz = Y * Z
+    c = np.empty((len(z), 8), np.int64)
+    c[:, 0] = x * yz + y * Z + z
+    c[:, 1] = c[:, 0] + 1
+    c[:, 2] = c[:, 0] + Z
+    c[:, 3] = c[:, 1] + Z
+    c[:, 4] = c[:, 0] + yz
+    c[:, 5] = c[:, 1] + yz
+    c[:, 6] = c[:, 2] + yz
+    c[:, 7] = c[:, 3] + yz
+    return c.reshape(X - 1, Y - 1, Z - 1, 8)
+
+
 def mc_dense(values, level=0.0, method="nagae", aabb_min=(-1, -1, -1), aabb_max=(1, 1, 1), x_range=None):
     """Marching cubes on a dense (X,Y,Z) field -- src/mc/mc.cu:17-68.  Returns (v, f, n_active)."""
     vals = _f32(values)

@@ -100,6 +100,13 @@ class UniformGrid(_GridBase):
         return _adopt(p.value, (*self.shape, 3), torch.float32)
 
 
+    def get_cells(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _ck(lib().ref_grid_cells(self.h, C.byref(p), C.byref(n)))
+        X, Y, Z = self.shape
+        return _adopt(p.value, (X - 1, Y - 1, Z - 1, 8), torch.int32)      # uint32 bits
+
+
 class SparseGrid(_GridBase):
     def __init__(self, shape, aabb_min=(-1, -1, -1), aabb_max=(1, 1, 1), default_value=3.4028234663852886e38):
         self.shape = tuple(int(s) for s in shape)

@@ -85,6 +85,14 @@ int ref_grid_points(void *g, float **d_points, size_t *n) {
     *d_points = reinterpret_cast<float *>(steal(p));
     REF_CATCH
 }
+// get_cells (src/grid/uniform.cu:42-51 / src/grid/sparse.cu:61-69): fresh device buffer of num_cells * 8 uint
+int ref_grid_cells(void *g, unsigned **d_cells, size_t *n) {
+    REF_TRY
+    NDArray<uint> c = static_cast<Grid *>(g)->get_cells();
+    *n = c.size();
+    *d_cells = steal(c);
+    REF_CATCH
+}
 int ref_grid_values(void *g, float **d_values, size_t *n) {
     REF_TRY
     NDArray<float> v = static_cast<Grid *>(g)->get_values();

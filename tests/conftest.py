@@ -10,6 +10,10 @@ for p in (str(ROOT), str(ROOT / "tests")):
         sys.path.insert(0, p)
 
 
+# the reference's own suite is vendored unmodified; it is run in a subprocess by test_ref_suite_gpu.py
+collect_ignore = ["ref_suite"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
