@@ -134,13 +134,18 @@ int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t 
  * counts_out[0] = welded vertices. */
 size_t isoext_dc_dense_workspace_bytes(int64_t n_entries, int64_t n_cells);
 size_t isoext_dc_dense_scratch_bytes(int64_t n_candidates);
+/* Slab support (no reference counterpart): emit_x_lo / emit_x_hi = local point planes [lo, hi) whose
+ * sign-change edges emit their quad (0 .. X on one GPU); dual vertices of ALL cells of the slab are welded, and the
+ * emit phase returns how many welded vertices lie below x_lo_threshold / x_hi_threshold (ownership by position,
+ * same rule as isoext_mc_dense_emit): counts_out = {V, n_lo, n_hi}.  Pass -inf / +inf on one GPU. */
 int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
-                          const float *aabb_max, const void *entries, int64_t n_entries, const uint32_t *row_start,
-                          const uint32_t *cellslot, const uint32_t *its_off, int64_t n_cells, const float *points,
-                          const float *normals, float reg, float svd_tol, float *dual_v, void *workspace,
-                          size_t workspace_bytes, void *stream, int64_t *counts_out);
+                          const float *aabb_max, int64_t emit_x_lo, int64_t emit_x_hi, const void *entries,
+                          int64_t n_entries, const uint32_t *row_start, const uint32_t *cellslot, const uint32_t *its_off,
+                          int64_t n_cells, const float *points, const float *normals, float reg, float svd_tol,
+                          float *dual_v, void *workspace, size_t workspace_bytes, void *stream, int64_t *counts_out);
 int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
-                         const float *aabb_max, const void *entries, int64_t n_entries, const uint32_t *row_start,
+                         const float *aabb_max, int64_t emit_x_lo, int64_t emit_x_hi, float x_lo_threshold,
+                         float x_hi_threshold, const void *entries, int64_t n_entries, const uint32_t *row_start,
                          const uint32_t *cellslot, const unsigned char *isout, int64_t n_cells, const float *dual_v,
                          void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
                          int64_t n_candidates, float *V, int32_t *F, int32_t *quads_out, void *stream,
@@ -178,13 +183,16 @@ int isoext_vertex_layer_histogram(const float *V, int64_t n, float aabb_min_x, f
 /* marching_cubes on a SparseGrid: phase 1 counts_out[0..1] = T, Vc; phase 2 counts_out[0] = V */
 size_t isoext_mc_sparse_workspace_bytes(int64_t n);
 size_t isoext_sparse_scratch_bytes(int64_t n_candidates);
+/* Slab support (the sorted cell list is partitioned by x layer): only the cells [emit_begin, emit_end) of
+ * the list emit triangles (0 .. n on one GPU); the vertices of ALL cells are welded, and the emit phase returns
+ * counts_out = {V, # with x < x_lo_threshold, # with x < x_hi_threshold} (ownership by position). */
 int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
-                           const float *aabb_min, const float *aabb_max, float level, int method, void *workspace,
-                           size_t workspace_bytes, void *stream, int64_t *counts_out);
+                           const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_begin,
+                           int64_t emit_end, void *workspace, size_t workspace_bytes, void *stream, int64_t *counts_out);
 int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
-                          const float *aabb_min, const float *aabb_max, float level, int method, void *workspace,
-                          size_t workspace_bytes, void *scratch, size_t scratch_bytes, int64_t n_candidates, float *V,
-                          int32_t *F, void *stream, int64_t *counts_out);
+                          const float *aabb_min, const float *aabb_max, float level, int method, float x_lo_threshold,
+                          float x_hi_threshold, void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
+                          int64_t n_candidates, float *V, int32_t *F, void *stream, int64_t *counts_out);
 /* get_intersection on a SparseGrid: cinfo / cellslot / its_off are caller-owned (n+1) u32 arrays kept by
  * the Intersection.  Phase 1 counts_out[0..1] = active cells, intersections.  emit mode: 0 points,
  * 1 points + normals, 2 normals only (compute_intersection_normals). */

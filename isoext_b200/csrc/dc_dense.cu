@@ -236,6 +236,26 @@ __device__ __forceinline__ bool quad_cells(const DenseParams &p, const uint2 *__
     return true;
 }
 
+// A dual vertex is part of the mesh iff some quad references it, i.e. iff one of its cell's sign-change edges has
+// all 4 incident cells inside the cell grid (on a dense grid they are then active, because they share the edge).
+// That is a function of the case and of the cell's GLOBAL position only, so every slab of a sharded grid marks
+// exactly the cells the single-device run marks, whatever its halo (the reference marks through idx_map /
+// get_triangles_op, src/dc.cu:184-203).  Edge e runs along `axis`; its origin is corner edge_c0(e).
+__device__ __forceinline__ bool cell_is_used(const DenseParams &p, u32 xg, u32 y, u32 z, u32 cs) {
+    const u32 Xg = (u32) p.g.Xg, Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 status = edge_mask_of_case(cs);
+    bool used = false;
+#pragma unroll
+    for (int e = 0; e < 12; e++) {
+        if (!((status >> e) & 1u)) continue;
+        const int c0 = edge_c0(e), d = c0 ^ edge_c1(e);            // d: 4 = x edge, 2 = y edge, 1 = z edge
+        const u32 ox = xg + ((c0 >> 2) & 1), oy = y + ((c0 >> 1) & 1), oz = z + (c0 & 1);
+        const bool inx = ox >= 1u && ox + 2u <= Xg, iny = oy >= 1u && oy + 2u <= Y, inz = oz >= 1u && oz + 2u <= Z;
+        used = used || (d == 4 ? (iny && inz) : (d == 2 ? (inx && inz) : (inx && iny)));
+    }
+    return used;
+}
+
 __global__ void __launch_bounds__(128) k_dc_quads(DenseParams p, const uint2 *__restrict__ entries, u32 S,
                                                   const u32 *__restrict__ row_start, const u32 *__restrict__ cellslot,
                                                   unsigned char *__restrict__ qmask, unsigned char *__restrict__ used) {
@@ -245,16 +265,15 @@ __global__ void __launch_bounds__(128) k_dc_quads(DenseParams p, const uint2 *__
         const u32 own = ent_own(e.y);
         u32 m = 0;
         const u32 x = e.x / Y;
-        // quads are attributed to the slab that owns the edge's origin plane
-        if (own && x >= p.emit_lo && x < p.emit_hi + 1) {
+        if (ent_cell(e.y) && cellslot[s] != 0xffffffffu)
+            used[cellslot[s]] = cell_is_used(p, x + (u32) p.g.x_off, e.x - x * Y, ent_z(e.y), ent_case(e.y)) ? 1 : 0;
+        // quads are attributed to the slab that owns the plane of the edge's origin: local planes [emit_lo, emit_hi)
+        if (own && x >= p.emit_lo && x < p.emit_hi) {
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 if (!((own >> a) & 1u)) continue;
                 u32 q[4];
-                if (quad_cells(p, entries, row_start, cellslot, e.x, ent_z(e.y), a, q)) {
-                    m |= 1u << a;
-                    used[q[0]] = 1; used[q[1]] = 1; used[q[2]] = 1; used[q[3]] = 1;
-                }
+                if (quad_cells(p, entries, row_start, cellslot, e.x, ent_z(e.y), a, q)) m |= 1u << a;
             }
         }
         qmask[s] = (unsigned char) m;
@@ -520,15 +539,18 @@ size_t isoext_dc_dense_scratch_bytes(int64_t n_candidates) {
 }
 
 // Phase 1 of dual_contouring: dual vertices (n_cells x 3, clipped) + quad / candidate counts.
+//   emit_x_lo / emit_x_hi: local point planes [lo, hi) whose sign-change edges emit their quad (0 .. X on one GPU;
+//   a slab emits the planes it owns and welds the dual vertices of its ghost layers as well).
 //   counts_out[0..1] = quads Q, used dual vertices Vc.
 int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
-                          const float *aabb_max, const void *entries, int64_t n_entries, const uint32_t *row_start,
+                          const float *aabb_max, int64_t emit_x_lo, int64_t emit_x_hi, const void *entries, int64_t n_entries,
+                          const uint32_t *row_start,
                           const uint32_t *cellslot, const uint32_t *its_off, int64_t n_cells, const float *points,
                           const float *normals, float reg, float svd_tol, float *dual_v, void *workspace,
                           size_t workspace_bytes, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DenseParams p;
-    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, 0, X - 1, &p);
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
     counts_out[0] = counts_out[1] = 0;
     if (n_entries <= 0 || n_cells <= 0) return OK;
@@ -539,7 +561,6 @@ int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int
     const u32 S = (u32) n_entries;
     const int sms = device_sms();
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
-    ISX_CUDA(cudaMemsetAsync(b.used, 0, (size_t) n_cells + 1, stream));
     ISX_CUDA(cudaMemsetAsync(b.descQ, 0, ((size_t) S / IT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) S / IT_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_dc_solve, sms * 8, 128, 0, stream, p, ent, S, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
@@ -555,17 +576,19 @@ int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int
 }
 
 // Phase 2: V (capacity Vc x 3), F (2Q x 3 int32), optional quads_out (Q x 4 cell slots, oriented).
-//   counts_out[0] = welded vertices.
+//   counts_out[0..2] = welded vertices, # with x < x_lo_threshold, # with x < x_hi_threshold (slab ownership; pass
+//   -inf / +inf on one GPU).
 int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global, const float *aabb_min,
-                         const float *aabb_max, const void *entries, int64_t n_entries, const uint32_t *row_start,
+                         const float *aabb_max, int64_t emit_x_lo, int64_t emit_x_hi, float x_lo_threshold, float x_hi_threshold,
+                         const void *entries, int64_t n_entries, const uint32_t *row_start,
                          const uint32_t *cellslot, const unsigned char *isout, int64_t n_cells, const float *dual_v,
                          void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes, int64_t n_candidates,
                          float *V, int32_t *F, int32_t *quads_out, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DenseParams p;
-    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, 0, X - 1, &p);
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
-    counts_out[0] = 0;
+    counts_out[0] = counts_out[1] = counts_out[2] = 0;
     if (n_candidates <= 0) return OK;
     Carver c(workspace);
     DcWs b;
@@ -580,7 +603,7 @@ int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int6
     ISX_LAUNCH(k_dc_keys, sms * 8, 256, 0, stream, (u32) n_cells, b.cand_of_cell, dual_v, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
-               host_float_key(-INFINITY), host_float_key(INFINITY));
+               host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
     ISX_LAUNCH(k_dc_faces, sms * 8, 128, 0, stream, p, ent, S, row_start, cellslot, b.qmask, isout, b.quad_off, b.cand_of_cell,
                s.cand_rank, dual_v, F, quads_out);
     ISX_CUDA(cudaGetLastError());
@@ -588,6 +611,8 @@ int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int6
     ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
     ISX_CUDA(cudaStreamSynchronize(stream));
     counts_out[0] = h[C_V];
+    counts_out[1] = h[C_NLO];
+    counts_out[2] = h[C_NHI];
     return OK;
 }
 

@@ -88,8 +88,11 @@ constexpr int SPT_ITEMS = 8;
 constexpr int SPT_TILE = 256 * SPT_ITEMS;
 
 // cinfo = case | trimask << 8 | usedmask << 16
+// Cells outside [emit_begin, emit_end) (the ghost cells of a slab) keep their used-edge mask -- their vertices are
+// welded so that the slab can number by position -- but emit no triangle.
 __global__ void __launch_bounds__(128) k_sp_mc_classify(const float *__restrict__ values8, const i64 *__restrict__ cell_idx,
-                                                        SparseParams p, u32 n, int method, u32 *__restrict__ cinfo) {
+                                                        SparseParams p, u32 n, int method, u32 *__restrict__ cinfo, u32 emit_begin,
+                                                        u32 emit_end) {
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         CellData c;
         load_sparse_cell(values8, p, s, cell_idx[s], c);
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(128) k_sp_mc_classify(const float *__restrict_
                 used |= (1u << a) | (1u << b) | (1u << d);
             }
         }
+        if (s < emit_begin || s >= emit_end) mask = 0;
         cinfo[s] = cs | (mask << 8) | (used << 16);
     }
 }
@@ -536,10 +540,11 @@ size_t isoext_sparse_scratch_bytes(int64_t n_candidates) {
     return carve_sp_scratch(c, (size_t) (n_candidates > 0 ? n_candidates : 1), nullptr);
 }
 
-// marching_cubes on a SparseGrid, phase 1: counts_out[0..1] = triangles T, vertex candidates Vc
+// marching_cubes on a SparseGrid, phase 1: counts_out[0..1] = triangles T, vertex candidates Vc.
+// Only the cells [emit_begin, emit_end) of the list emit triangles (0 .. n on one GPU; the owned cells of a slab).
 int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
-                           const float *aabb_min, const float *aabb_max, float level, int method, void *workspace,
-                           size_t workspace_bytes, void *stream_, int64_t *counts_out) {
+                           const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_begin,
+                           int64_t emit_end, void *workspace, size_t workspace_bytes, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     SparseParams p;
@@ -555,7 +560,9 @@ int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descB, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     stream_timer_mark(stream);
-    ISX_LAUNCH(k_sp_mc_classify, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, method, b.cinfo);
+    if (emit_begin < 0 || emit_end > n || emit_begin > emit_end) return fail(E_INVALID, "emit range out of bounds");
+    ISX_LAUNCH(k_sp_mc_classify, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, method, b.cinfo,
+               (u32) emit_begin, (u32) emit_end);
     stream_timer_mark(stream);
     ISX_LAUNCH(k_sp_scan2, sms * 4, 256, 0, stream, (u32) n, b.counters, b.cinfo, 8, 0xffu, 16, 0xfffu, b.offA, b.offB, b.descA,
                b.descB, (int) C_T, (int) C_VC, (int) C_TICKET_B);
@@ -568,16 +575,17 @@ int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     return OK;
 }
 
-// phase 2: V (capacity Vc x 3), F (T x 3); counts_out[0] = welded vertices
+// phase 2: V (capacity Vc x 3), F (T x 3); counts_out[0..2] = welded vertices, # with x < x_lo_threshold, # with
+// x < x_hi_threshold (slab ownership by position; -inf / +inf on one GPU)
 int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
-                          const float *aabb_min, const float *aabb_max, float level, int method, void *workspace,
-                          size_t workspace_bytes, void *scratch, size_t scratch_bytes, int64_t n_candidates, float *V, int32_t *F,
-                          void *stream_, int64_t *counts_out) {
+                          const float *aabb_min, const float *aabb_max, float level, int method, float x_lo_threshold,
+                          float x_hi_threshold, void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
+                          int64_t n_candidates, float *V, int32_t *F, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SparseParams p;
     int rc = make_sparse_params(X, Y, Z, aabb_min, aabb_max, level, n, &p);
     if (rc != OK) return rc;
-    counts_out[0] = 0;
+    counts_out[0] = counts_out[1] = counts_out[2] = 0;
     if (n == 0 || n_candidates <= 0) return OK;
     if (n_candidates >= ((i64) 1 << 31)) return fail(E_INVALID, "too many vertex candidates");
     Carver c(workspace);
@@ -592,13 +600,15 @@ int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t
     ISX_LAUNCH(k_sp_mc_keys, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, b.cinfo, b.offB, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
     ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
-               host_float_key(-INFINITY), host_float_key(INFINITY));
+               host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
     ISX_LAUNCH(k_sp_mc_faces, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, method, b.cinfo, b.offA, b.offB, s.cand_rank, F);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
     ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
     ISX_CUDA(cudaStreamSynchronize(stream));
     counts_out[0] = h[C_V];
+    counts_out[1] = h[C_NLO];
+    counts_out[2] = h[C_NHI];
     return OK;
 }
 

@@ -3,6 +3,7 @@ bindings (src/isoext_ext.cu:305-378) over the sm_100a kernels in csrc/dc_dense.c
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 
@@ -58,25 +59,30 @@ class Intersection:
         return Intersection._make(**d)
 
 
-def _its_dense(grid: UniformGrid, level: float, compute_normals: bool) -> Intersection:
+def its_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level: float, compute_normals: bool, ws, cap_hint=0,
+                  x_offset=0, x_global=None):
+    """Intersections of a dense (X, Y, Z) float32 CUDA field (a whole grid, or the extended slab of a sharded grid:
+    ``x_offset`` = global index of local plane 0, ``x_global`` = points along x of the whole grid).
+    Returns ``(Intersection, entry capacity used)``."""
     lib = _lib.lib()
-    X, Y, Z = grid.shape
-    dev = grid.device
-    amin, amax = _lib.f3(grid.aabb_min), _lib.f3(grid.aabb_max)
+    X, Y, Z = shape
+    xg = X if x_global is None else int(x_global)
+    dev = values.device
+    amin, amax = _lib.f3(aabb_min), _lib.f3(aabb_max)
     stream = _stream_ptr()
     counts = (C.c_int64 * 4)()
-    cap = max(int(grid._cap_hint), _initial_cap(grid.shape))
+    cap = max(int(cap_hint), _initial_cap(shape))
     row_start = torch.empty(X * Y + 2, dtype=torch.int32, device=dev)
     while True:
         nbytes = lib.isoext_its_dense_workspace_bytes(X, Y, Z, cap)
         if nbytes == 0:
             raise RuntimeError(_lib.last_error())
-        ws = grid._ws.get("its_ws", nbytes, dev)
+        wsbuf = ws.get("its_ws", nbytes, dev)
         entries = torch.empty((cap + 1, 2), dtype=torch.int32, device=dev)
         cellslot = torch.empty(cap, dtype=torch.int32, device=dev)
         its_off = torch.empty(cap, dtype=torch.int32, device=dev)
-        rc = lib.isoext_its_dense_count(grid._values.data_ptr(), X, Y, Z, 0, X, amin, amax, float(level), ws.data_ptr(),
-                                        ws.numel(), cap, entries.data_ptr(), row_start.data_ptr(), cellslot.data_ptr(),
+        rc = lib.isoext_its_dense_count(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), wsbuf.data_ptr(),
+                                        wsbuf.numel(), cap, entries.data_ptr(), row_start.data_ptr(), cellslot.data_ptr(),
                                         its_off.data_ptr(), stream, counts)
         if rc == _lib.E_CAPACITY:
             cap = int(counts[0]) + 1024
@@ -84,21 +90,28 @@ def _its_dense(grid: UniformGrid, level: float, compute_normals: bool) -> Inters
         _lib.check(rc)
         break
     S, n_cells, n_its = int(counts[0]), int(counts[1]), int(counts[2])
-    grid._cap_hint = max(cap, S)
     entries, cellslot, its_off = entries[:S + 1], cellslot[:max(S, 1)], its_off[:max(S, 1)]
     points = torch.empty((n_its, 3), dtype=torch.float32, device=dev)
     normals = torch.zeros((n_its, 3), dtype=torch.float32, device=dev)
     isout = torch.empty(max(S, 1), dtype=torch.uint8, device=dev)
     cell_offsets = torch.zeros(n_cells + 1, dtype=torch.int32, device=dev)
     cell_indices = torch.empty(n_cells, dtype=torch.int64, device=dev)
-    _lib.check(lib.isoext_its_dense_emit(grid._values.data_ptr(), X, Y, Z, 0, X, amin, amax, float(level),
+    _lib.check(lib.isoext_its_dense_emit(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level),
                                          int(bool(compute_normals)), entries.data_ptr(), S, cellslot.data_ptr(),
                                          its_off.data_ptr(), n_cells, n_its, points.data_ptr(), normals.data_ptr(),
                                          isout.data_ptr(), cell_offsets.data_ptr(), cell_indices.data_ptr(), stream))
-    return Intersection._make(kind="dense", shape=grid.shape, aabb_min=grid.aabb_min, aabb_max=grid.aabb_max, level=float(level),
-                              entries=entries, row_start=row_start, cellslot=cellslot, its_off=its_off, isout=isout,
-                              n_entries=S, n_cells=n_cells, points=points, normals=normals, cell_offsets=cell_offsets,
-                              cell_indices=cell_indices, _has_normals=bool(compute_normals))
+    its = Intersection._make(kind="dense", shape=tuple(shape), aabb_min=aabb_min, aabb_max=aabb_max, level=float(level),
+                             entries=entries, row_start=row_start, cellslot=cellslot, its_off=its_off, isout=isout,
+                             n_entries=S, n_cells=n_cells, points=points, normals=normals, cell_offsets=cell_offsets,
+                             cell_indices=cell_indices, x_offset=int(x_offset), x_global=xg, _has_normals=bool(compute_normals))
+    return its, max(cap, S)
+
+
+def _its_dense(grid: UniformGrid, level: float, compute_normals: bool) -> Intersection:
+    its, cap = its_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, compute_normals, grid._ws,
+                             cap_hint=grid._cap_hint)
+    grid._cap_hint = cap
+    return its
 
 
 def get_intersection(grid, level: float = 0.0, compute_normals: bool = False) -> Intersection:
@@ -114,36 +127,44 @@ def get_intersection(grid, level: float = 0.0, compute_normals: bool = False) ->
 
 def _normals_dense(grid: UniformGrid, its: Intersection) -> None:
     X, Y, Z = grid.shape
-    _lib.check(_lib.lib().isoext_its_dense_normals(grid._values.data_ptr(), X, Y, Z, 0, X, _lib.f3(grid.aabb_min),
+    _lib.check(_lib.lib().isoext_its_dense_normals(grid._values.data_ptr(), X, Y, Z, its.x_offset, its.x_global, _lib.f3(grid.aabb_min),
                                                    _lib.f3(grid.aabb_max), its.entries.data_ptr(), its.n_entries,
                                                    its.cellslot.data_ptr(), its.its_off.data_ptr(), its.points.data_ptr(),
                                                    its.normals.data_ptr(), _stream_ptr()))
     its._has_normals = True
 
 
-def dc_dense_raw(grid: UniformGrid, its: Intersection, reg: float, svd_tol: float, want_quads: bool = False,
-                 dual_v_in: torch.Tensor | None = None):
+def dc_dense_raw(grid, its: Intersection, reg: float, svd_tol: float, want_quads: bool = False,
+                 dual_v_in: torch.Tensor | None = None, emit_range=None, x_thresholds=(-math.inf, math.inf), with_counts=False):
     """Returns (v, f, dual_v, quads): welded mesh + per-active-cell dual vertices (+ oriented quads).
-    ``dual_v_in`` (n_cells, 3) replaces the solved dual vertices before the quad/split/weld stage (parity tests
-    feed the reference's own dual vertices through it to compare everything downstream of the solve)."""
+    ``grid`` only lends its device and workspace cache (a UniformGrid or a dist.SlabGrid); the geometry comes from
+    ``its`` (whole grid or extended slab).  ``dual_v_in`` (n_cells, 3) replaces the solved dual vertices before the
+    quad/split/weld stage (parity tests feed the reference's own dual vertices through it to compare everything
+    downstream of the solve).  Slabs: ``emit_range`` = local point planes [lo, hi) whose edges emit quads,
+    ``x_thresholds`` = ownership thresholds; ``with_counts`` appends (n_lo, n_hi) and then ``v`` holds ALL welded
+    vertices of the slab."""
     lib = _lib.lib()
-    X, Y, Z = grid.shape
-    dev = grid.device
-    amin, amax = _lib.f3(grid.aabb_min), _lib.f3(grid.aabb_max)
+    X, Y, Z = its.shape
+    dev = its.points.device
+    amin, amax = _lib.f3(its.aabb_min), _lib.f3(its.aabb_max)
+    xo, xg = its.x_offset, its.x_global
+    lo, hi = (0, X) if emit_range is None else emit_range
+    thr_lo, thr_hi = float(x_thresholds[0]), float(x_thresholds[1])
     stream = _stream_ptr()
     S, n_cells = its.n_entries, its.n_cells
     dual_v = torch.empty((n_cells, 3), dtype=torch.float32, device=dev)
+    empty = (None, None, dual_v, None) + ((0, 0) if with_counts else ())
     if S == 0 or n_cells == 0:
-        return None, None, dual_v, None
+        return empty
     ws = grid._ws.get("dc_ws", lib.isoext_dc_dense_workspace_bytes(S, n_cells), dev)
     counts = (C.c_int64 * 4)()
-    _lib.check(lib.isoext_dc_dense_count(X, Y, Z, 0, X, amin, amax, its.entries.data_ptr(), S, its.row_start.data_ptr(),
+    _lib.check(lib.isoext_dc_dense_count(X, Y, Z, xo, xg, amin, amax, lo, hi, its.entries.data_ptr(), S, its.row_start.data_ptr(),
                                          its.cellslot.data_ptr(), its.its_off.data_ptr(), n_cells, its.points.data_ptr(),
                                          its.normals.data_ptr(), float(reg), float(svd_tol), dual_v.data_ptr(), ws.data_ptr(),
                                          ws.numel(), stream, counts))
     Q, Vc = int(counts[0]), int(counts[1])
-    if Q == 0:
-        return None, None, dual_v, None
+    if Vc == 0 or (Q == 0 and not with_counts):
+        return empty
     if dual_v_in is not None:
         dual_v.copy_(dual_v_in)
     scratch = grid._ws.get("dc_scratch", lib.isoext_dc_dense_scratch_bytes(Vc), dev)
@@ -151,11 +172,12 @@ def dc_dense_raw(grid: UniformGrid, its: Intersection, reg: float, svd_tol: floa
     F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)
     quads = torch.empty((Q, 4), dtype=torch.int32, device=dev) if want_quads else None
     out = (C.c_int64 * 4)()
-    _lib.check(lib.isoext_dc_dense_emit(X, Y, Z, 0, X, amin, amax, its.entries.data_ptr(), S, its.row_start.data_ptr(),
-                                        its.cellslot.data_ptr(), its.isout.data_ptr(), n_cells, dual_v.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), scratch.data_ptr(), scratch.numel(), Vc, V.data_ptr(), F.data_ptr(),
-                                        quads.data_ptr() if want_quads else None, stream, out))
-    return V[:int(out[0])], F, dual_v, quads
+    _lib.check(lib.isoext_dc_dense_emit(X, Y, Z, xo, xg, amin, amax, lo, hi, thr_lo, thr_hi, its.entries.data_ptr(), S,
+                                        its.row_start.data_ptr(), its.cellslot.data_ptr(), its.isout.data_ptr(), n_cells,
+                                        dual_v.data_ptr(), ws.data_ptr(), ws.numel(), scratch.data_ptr(), scratch.numel(), Vc,
+                                        V.data_ptr(), F.data_ptr(), quads.data_ptr() if want_quads else None, stream, out))
+    res = (V[:int(out[0])], F, dual_v, quads)
+    return res + ((int(out[1]), int(out[2])) if with_counts else ())
 
 
 def dual_contouring(grid, level: float = 0.0, intersection: Intersection | None = None, reg: float = 1e-2,

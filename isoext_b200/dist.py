@@ -122,20 +122,22 @@ def vertex_layer_histogram(v_own: torch.Tensor, X: int, aabb_min_x: float, aabb_
     return h
 
 
-def slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
-    """Everything rank `rank` needs to know about its slab (all plane indices are GLOBAL)."""
+def slab_plan(X: int, rank: int, world: int, cuts=None, halo_below: int = 1) -> dict:
+    """Everything rank `rank` needs to know about its slab (all plane indices are GLOBAL).
+    ``halo_below``: planes fetched from the lower neighbour -- 1 for marching cubes, 2 when the slab also serves
+    dual contouring (dc_slab_plan explains why)."""
     c = partition_cells(X, world) if cuts is None else check_cuts(X, world, cuts)
     c_lo, c_hi = c[rank], c[rank + 1]
     own_lo, own_hi = c_lo, (c_hi if rank < world - 1 else X)        # owned point planes [own_lo, own_hi)
-    ext_lo, ext_hi = max(0, c_lo - 1), min(X - 1, c_hi + 1)           # extended slab planes [ext_lo, ext_hi]
+    ext_lo, ext_hi = max(0, c_lo - halo_below), min(X - 1, c_hi + 1)   # extended slab planes [ext_lo, ext_hi]
     return dict(c_lo=c_lo, c_hi=c_hi, own_lo=own_lo, own_hi=own_hi, ext_lo=ext_lo, ext_hi=ext_hi,
                 n_ext=ext_hi - ext_lo + 1, emit_lo=c_lo - ext_lo, emit_hi=c_hi - ext_lo,
-                halo_below=(c_lo - 1 if rank > 0 else None),                       # 1 plane from rank-1
+                halo_below=list(range(ext_lo, c_lo)) if rank > 0 else [],             # from rank-1 (its last planes)
                 halo_above=([p for p in (c_hi, c_hi + 1) if p <= X - 1] if rank < world - 1 else []))
 
 
 def dc_slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
-    """Slab geometry for dual contouring (host logic; the CUDA side is not built yet).
+    """Slab geometry for dual contouring (the CUDA side is dist.dual_contouring on a SlabGrid(dc=True)).
 
     Rank r emits the quads of the sign-change edges whose lower end point lies in planes ``[c_r, c_{r+1})`` and owns the
     welded vertices with ``px[c_r] <= x < px[c_{r+1}]``.  A quad joins cells of layers ``p_lo.x - 1`` and ``p_lo.x``, so
@@ -167,11 +169,13 @@ def sparse_slab_select(cell_idx, shape, rank: int, world: int, cuts=None):
 def exchange_halos(ext: torch.Tensor, plan: dict, rank: int, world: int, group=None) -> None:
     """Fill the halo planes of the extended slab `ext` ((n_ext, Y, Z), owned planes already in place).
 
-    Sends my first two owned planes down to rank-1 and my last owned plane up to rank+1."""
+    Sends my first two owned planes down to rank-1 and my last owned plane(s) up to rank+1 (as many as the halo
+    below is deep: every rank uses the same depth)."""
     if world == 1:
         return
     ops, keep = [], []
     base = plan["ext_lo"]
+    depth = max(1, plan["c_lo"] - plan["ext_lo"]) if rank > 0 else None
 
     def plane(g):
         return ext[g - base]
@@ -183,10 +187,13 @@ def exchange_halos(ext: torch.Tensor, plan: dict, rank: int, world: int, group=N
         for g in (plan["own_lo"], plan["own_lo"] + 1):                 # they are rank-1's halo_above
             t = plane(g).contiguous(); keep.append(t)
             ops.append(dist.P2POp(dist.isend, t, peer(rank - 1), group))
-        ops.append(dist.P2POp(dist.irecv, plane(plan["halo_below"]), peer(rank - 1), group))
+        for g in plan["halo_below"]:
+            ops.append(dist.P2POp(dist.irecv, plane(g), peer(rank - 1), group))
     if rank < world - 1:
-        t = plane(plan["c_hi"] - 1).contiguous(); keep.append(t)      # rank+1's halo_below
-        ops.append(dist.P2POp(dist.isend, t, peer(rank + 1), group))
+        up = plan.get("depth_up", 1)                                     # rank+1's halo_below
+        for g in range(plan["c_hi"] - up, plan["c_hi"]):
+            t = plane(g).contiguous(); keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, peer(rank + 1), group))
         for g in plan["halo_above"]:
             ops.append(dist.P2POp(dist.irecv, plane(g), peer(rank + 1), group))
     for w in dist.batch_isend_irecv(ops):
@@ -224,7 +231,7 @@ class SlabGrid:
     split, e.g. from ``balanced_cuts`` -- the extracted mesh does not depend on them."""
 
     def __init__(self, shape, aabb_min=(-1.0, -1.0, -1.0), aabb_max=(1.0, 1.0, 1.0), default_value=3.4028234663852886e38,
-                 group=None, device=None, rank=None, world=None, cuts=None):
+                 group=None, device=None, rank=None, world=None, cuts=None, dc=False):
         from . import _lib
         from .grid import _Workspace
         self.shape = tuple(int(s) for s in shape)
@@ -235,7 +242,9 @@ class SlabGrid:
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.cuts = None if cuts is None else check_cuts(self.shape[0], self.world, cuts)   # explicit slab boundaries
-        self.plan = slab_plan(self.shape[0], self.rank, self.world, self.cuts)
+        self.halo_below = 2 if dc else 1          # dual contouring needs two planes from the lower neighbour
+        self.plan = slab_plan(self.shape[0], self.rank, self.world, self.cuts, self.halo_below)
+        self.plan["depth_up"] = self.halo_below
         _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         X, Y, Z = self.shape
@@ -344,12 +353,13 @@ class SlabGrid:
         e = pr["epoch"]
         base = self._ext.data_ptr()
         seg = [(None, None, 0, None), (None, None, 0, None)]
-        if self.rank > 0:
-            q = slab_plan(X, self.rank - 1, self.world, self.cuts)
-            src = pr["peer_ext"][self.rank - 1] + (p["halo_below"] - q["ext_lo"]) * plane * 4
-            seg[0] = (base + (p["halo_below"] - p["ext_lo"]) * plane * 4, src, plane, pr["peer_sync"][self.rank - 1])
+        if self.rank > 0 and p["halo_below"]:
+            q = slab_plan(X, self.rank - 1, self.world, self.cuts, self.halo_below)
+            g0 = p["halo_below"][0]                                     # contiguous planes [g0, c_lo) of the lower neighbour
+            src = pr["peer_ext"][self.rank - 1] + (g0 - q["ext_lo"]) * plane * 4
+            seg[0] = (base + (g0 - p["ext_lo"]) * plane * 4, src, plane * len(p["halo_below"]), pr["peer_sync"][self.rank - 1])
         if self.rank < self.world - 1 and p["halo_above"]:
-            q = slab_plan(X, self.rank + 1, self.world, self.cuts)
+            q = slab_plan(X, self.rank + 1, self.world, self.cuts, self.halo_below)
             g0 = p["halo_above"][0]
             src = pr["peer_ext"][self.rank + 1] + (g0 - q["ext_lo"]) * plane * 4
             seg[1] = (base + (g0 - p["ext_lo"]) * plane * 4, src, plane * len(p["halo_above"]), pr["peer_sync"][self.rank + 1])
@@ -453,6 +463,92 @@ def globalize_faces_(sg: SlabGrid, f: torch.Tensor, n_lo: int, n_hi: int, peer: 
         return
     vb, fb, totals, _ = global_bases(n_hi - n_lo, int(f.shape[0]), sg.device, sg.group)
     relabel_faces_(f, n_lo, n_hi, vb, vb + (n_hi - n_lo))
+
+
+def dual_contouring_local(sg: SlabGrid, level: float = 0.0, reg: float = 1e-2, svd_tol: float = 1e-6):
+    """Rank-local part of the distributed dual contouring (no communication): ``(v_own, f_local, n_lo, n_hi)``.
+
+    The slab (SlabGrid(dc=True): point planes [c_r - 2, c_{r+1} + 1]) computes the intersections, normals and dual
+    vertices of ALL its cell layers, welds them, emits the quads of the sign-change edges whose origin lies in its own
+    planes [c_r, c_{r+1}) and owns the welded vertices with px[c_r] <= x < px[c_{r+1}] (dc_slab_plan)."""
+    from .dc import dc_dense_raw, its_dense_raw
+    if sg.halo_below < 2 and sg.world > 1:
+        raise RuntimeError("dual contouring on slabs needs SlabGrid(..., dc=True): two halo planes below")
+    p = sg.plan
+    X, Y, Z = sg.shape
+    with torch.cuda.device(sg.device):
+        its, cap = its_dense_raw(sg._ext, (p["n_ext"], Y, Z), sg.aabb_min, sg.aabb_max, level, True, sg._ws, cap_hint=sg._cap_hint,
+                                 x_offset=p["ext_lo"], x_global=X)
+        sg._cap_hint = cap
+        emit_hi = (p["c_hi"] if sg.rank < sg.world - 1 else X) - p["ext_lo"]
+        v, f, _, _, n_lo, n_hi = dc_dense_raw(sg, its, reg, svd_tol, emit_range=(p["emit_lo"], emit_hi),
+                                              x_thresholds=sg.thresholds, with_counts=True)
+    if v is None:
+        return (torch.empty((0, 3), dtype=torch.float32, device=sg.device),
+                torch.empty((0, 3), dtype=torch.int32, device=sg.device), 0, 0)
+    return v[n_lo:n_hi], f, n_lo, n_hi
+
+
+def dual_contouring(sg: SlabGrid, level: float = 0.0, reg: float = 1e-2, svd_tol: float = 1e-6, exchange: bool = True):
+    """Distributed ``dual_contouring`` (normals from the field, like the default of the single-device call): returns
+    this rank's part ``(v_own, f_own)`` of the global mesh; the parts of ranks 0..R-1 concatenate to exactly the
+    single-GPU ``(v, f)``."""
+    if exchange:
+        sg.exchange_halos()
+    v_own, f, n_lo, n_hi = dual_contouring_local(sg, level, reg, svd_tol)
+    globalize_faces_(sg, f, n_lo, n_hi, peer=exchange)
+    return v_own, f
+
+
+class SparseSlab:
+    """This rank's part of a SparseGrid cut along x: the owned cells (x layers [c_r, c_{r+1})) plus one
+    ghost layer of cells on either side, with their corner values.  Built from any SparseGrid that holds at least
+    those cells (e.g. the whole band); afterwards the rank needs nothing from its neighbours but two counts, because
+    sparse cells carry their own corner values -- there is no halo to exchange."""
+
+    def __init__(self, grid, group=None, rank=None, world=None, cuts=None):
+        from .sparse import SparseGrid
+        self.group = group
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        shape = grid.shape
+        ext, owned = sparse_slab_select(grid._cells, shape, self.rank, self.world, cuts)
+        c = partition_cells(shape[0], self.world) if cuts is None else check_cuts(shape[0], self.world, cuts)
+        local = SparseGrid(list(shape), grid.aabb_min, grid.aabb_max, grid.default_value, device=grid.device)
+        local._cells = grid._cells[ext].contiguous()
+        local._values = grid._values[ext].contiguous()
+        local._int32_api = grid._int32_api
+        self.local, self.device, self.shape = local, grid.device, shape
+        pos = torch.nonzero(owned[ext]).flatten()        # the owned cells are a contiguous run of the sorted list
+        self.emit = (int(pos[0]), int(pos[-1]) + 1) if pos.numel() else (0, 0)
+        from . import _lib
+        px = lambda i: float(_lib.lib().isoext_axis_position(i, shape[0], grid.aabb_min[0], grid.aabb_max[0]))
+        self.thresholds = (px(c[self.rank]) if self.rank > 0 else -math.inf,
+                           px(c[self.rank + 1]) if self.rank < self.world - 1 else math.inf)
+        self._peer = None
+
+    def set_values(self, values8: torch.Tensor) -> None:
+        self.local.set_values(values8)
+
+
+def marching_cubes_sparse_local(ss: SparseSlab, level: float = 0.0, method: str = "nagae"):
+    """Rank-local part (no communication): ``(v_own, f_local, n_lo, n_hi)``."""
+    from .mc import _method_id
+    from .sparse import mc_sparse
+    v, f, n_lo, n_hi = mc_sparse(ss.local, level, _method_id(method), emit_range=ss.emit, x_thresholds=ss.thresholds, with_counts=True)
+    if v is None:
+        return (torch.empty((0, 3), dtype=torch.float32, device=ss.device),
+                torch.empty((0, 3), dtype=torch.int32, device=ss.device), 0, 0)
+    return v[n_lo:n_hi], f, n_lo, n_hi
+
+
+def marching_cubes_sparse(ss: SparseSlab, level: float = 0.0, method: str = "nagae"):
+    """Distributed ``marching_cubes`` over a slab-partitioned SparseGrid: this rank's ``(v_own, f_own)``; the parts
+    of ranks 0..R-1 concatenate to exactly the single-device sparse mesh (global vertex ids)."""
+    v_own, f, n_lo, n_hi = marching_cubes_sparse_local(ss, level, method)
+    vb, fb, totals, _ = global_bases(n_hi - n_lo, int(f.shape[0]), ss.device, ss.group)
+    relabel_faces_(f, n_lo, n_hi, vb, vb + (n_hi - n_lo))
+    return v_own, f
 
 
 def gather_mesh(v_own: torch.Tensor, f_own: torch.Tensor, group=None):

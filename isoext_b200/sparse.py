@@ -9,6 +9,7 @@ narrow bands); int32 in -> int32 out, exactly like the reference, otherwise int6
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 
@@ -157,29 +158,37 @@ class SparseGrid(Grid):
         return X, Y, Z, _lib.f3(self.aabb_min), _lib.f3(self.aabb_max)
 
 
-def mc_sparse(grid: SparseGrid, level: float, method_id: int):
+def mc_sparse(grid: SparseGrid, level: float, method_id: int, emit_range=None, x_thresholds=(-math.inf, math.inf),
+              with_counts: bool = False):
+    """Marching cubes over the cell list.  Slabs (dist.SparseSlab): only the cells ``emit_range`` = [begin, end) of the
+    list emit triangles, the vertices of all cells are welded, and with ``with_counts`` the result is
+    ``(V_all, F, n_lo, n_hi)`` -- all welded vertices plus the ownership counts against ``x_thresholds``."""
     lib = _lib.lib()
     n = grid.get_num_cells()
+    empty = (None, None, 0, 0) if with_counts else (None, None)
     if n == 0:
-        return None, None
+        return empty
     X, Y, Z, amin, amax = grid._geom()
     dev = grid.device
+    e0, e1 = (0, n) if emit_range is None else emit_range
     with torch.cuda.device(dev):
         stream = _stream_ptr()
         ws = grid._ws.get("mc_ws", lib.isoext_mc_sparse_workspace_bytes(n), dev)
         counts = (C.c_int64 * 4)()
         _lib.check(lib.isoext_mc_sparse_count(grid._values.data_ptr(), grid._cells.data_ptr(), n, X, Y, Z, amin, amax, float(level),
-                                              method_id, ws.data_ptr(), ws.numel(), stream, counts))
+                                              method_id, e0, e1, ws.data_ptr(), ws.numel(), stream, counts))
         T, Vc = int(counts[0]), int(counts[1])
-        if T == 0:
-            return None, None
+        if Vc == 0 or (T == 0 and not with_counts):
+            return empty
         scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc), dev)
         V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
         F = torch.empty((T, 3), dtype=torch.int32, device=dev)
         out = (C.c_int64 * 4)()
         _lib.check(lib.isoext_mc_sparse_emit(grid._values.data_ptr(), grid._cells.data_ptr(), n, X, Y, Z, amin, amax, float(level),
-                                             method_id, ws.data_ptr(), ws.numel(), scratch.data_ptr(), scratch.numel(), Vc,
-                                             V.data_ptr(), F.data_ptr(), stream, out))
+                                             method_id, float(x_thresholds[0]), float(x_thresholds[1]), ws.data_ptr(), ws.numel(),
+                                             scratch.data_ptr(), scratch.numel(), Vc, V.data_ptr(), F.data_ptr(), stream, out))
+    if with_counts:
+        return V[:int(out[0])], F, int(out[1]), int(out[2])
     return V[:int(out[0])], F
 
 

@@ -26,13 +26,14 @@ def test_partition_covers_all_layers():
 
 def test_slab_plan_halo_geometry():
     X, world = 64, 4
-    plans = [idist.slab_plan(X, r, world) for r in range(world)]
-    assert plans[0]["halo_below"] is None and plans[-1]["halo_above"] == []
-    for r in range(world - 1):
-        assert plans[r]["halo_above"] == [plans[r + 1]["own_lo"], plans[r + 1]["own_lo"] + 1]
-        assert plans[r + 1]["halo_below"] == plans[r]["own_hi"] - 1
-    assert sum(p["own_hi"] - p["own_lo"] for p in plans) == X
-    assert [p["emit_hi"] - p["emit_lo"] for p in plans] == [p["c_hi"] - p["c_lo"] for p in plans]
+    for depth in (1, 2):        # 1: marching cubes, 2: slabs that also serve dual contouring
+        plans = [idist.slab_plan(X, r, world, halo_below=depth) for r in range(world)]
+        assert plans[0]["halo_below"] == [] and plans[-1]["halo_above"] == []
+        for r in range(world - 1):
+            assert plans[r]["halo_above"] == [plans[r + 1]["own_lo"], plans[r + 1]["own_lo"] + 1]
+            assert plans[r + 1]["halo_below"] == list(range(plans[r]["own_hi"] - depth, plans[r]["own_hi"]))
+        assert sum(p["own_hi"] - p["own_lo"] for p in plans) == X
+        assert [p["emit_hi"] - p["emit_lo"] for p in plans] == [p["c_hi"] - p["c_lo"] for p in plans]
 
 
 def _halo_worker(rank, world, port, shape):
@@ -40,11 +41,13 @@ def _halo_worker(rank, world, port, shape):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         full = fields.noise(shape, 11)
-        plan = idist.slab_plan(shape[0], rank, world)
-        ext = torch.full((plan["n_ext"], shape[1], shape[2]), float("nan"))
-        ext[plan["own_lo"] - plan["ext_lo"]:plan["own_hi"] - plan["ext_lo"]] = full[plan["own_lo"]:plan["own_hi"]]
-        idist.exchange_halos(ext, plan, rank, world)
-        assert torch.equal(ext, full[plan["ext_lo"]:plan["ext_hi"] + 1]), f"rank {rank}: halo mismatch"
+        for depth in (1, 2):
+            plan = idist.slab_plan(shape[0], rank, world, halo_below=depth)
+            plan["depth_up"] = depth
+            ext = torch.full((plan["n_ext"], shape[1], shape[2]), float("nan"))
+            ext[plan["own_lo"] - plan["ext_lo"]:plan["own_hi"] - plan["ext_lo"]] = full[plan["own_lo"]:plan["own_hi"]]
+            idist.exchange_halos(ext, plan, rank, world)
+            assert torch.equal(ext, full[plan["ext_lo"]:plan["ext_hi"] + 1]), f"rank {rank}: halo mismatch (depth {depth})"
         vb, fb, totals, allc = idist.global_bases(10 + rank, 100 + rank, torch.device("cpu"))
         assert vb == sum(10 + r for r in range(rank)) and fb == sum(100 + r for r in range(rank))
         assert totals == (sum(10 + r for r in range(world)), sum(100 + r for r in range(world)))

@@ -73,6 +73,96 @@ def test_simulated_ranks_with_uneven_cuts(iso, name, cuts):
     assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf)
 
 
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("name", sorted(FIELDS))
+def test_dual_contouring_simulated_ranks_concatenate_to_single_gpu_mesh(iso, name, world):
+    """DC on slabs, CUDA side (dist.dual_contouring_local on SlabGrid(dc=True): two halo planes below, dual vertices of
+    the ghost layers welded too, quads of the owned planes, ownership by position): the per-rank parts, relabelled
+    by the CUDA kernel, concatenate to the single-GPU dual-contouring mesh bit for bit (V bits and F)."""
+    from isoext_b200 import dist as idist
+    vals = FIELDS[name]().cuda()
+    g = iso.UniformGrid(list(vals.shape))
+    g.set_values(vals)
+    gv, gf = iso.dual_contouring(g)
+    parts = []
+    for r in range(world):
+        sg = idist.SlabGrid(list(vals.shape), rank=r, world=world, dc=True)
+        p = sg.plan
+        assert p["ext_lo"] == max(0, p["c_lo"] - 2)
+        sg._ext.copy_(vals[p["ext_lo"]:p["ext_hi"] + 1])
+        parts.append(idist.dual_contouring_local(sg))
+    bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])])
+    for r, (v_own, f, n_lo, n_hi) in enumerate(parts):
+        idist.relabel_faces_(f, n_lo, n_hi, int(bases[r]), int(bases[r + 1]))
+    v, f = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    assert v.shape == gv.shape and torch.equal(v.view(torch.int32), gv.view(torch.int32))
+    assert torch.equal(f, gf)
+    # the same slabs serve marching cubes (one more ghost layer below changes nothing)
+    mv, mf = iso.marching_cubes(g)
+    mparts = []
+    for r in range(world):
+        sg = idist.SlabGrid(list(vals.shape), rank=r, world=world, dc=True)
+        p = sg.plan
+        sg._ext.copy_(vals[p["ext_lo"]:p["ext_hi"] + 1])
+        mparts.append(idist.marching_cubes_local(sg))
+    bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in mparts])])
+    for r, (v_own, f, n_lo, n_hi) in enumerate(mparts):
+        idist.relabel_faces_(f, n_lo, n_hi, int(bases[r]), int(bases[r + 1]))
+    assert torch.equal(torch.cat([p[0] for p in mparts]).view(torch.int32), mv.view(torch.int32))
+    assert torch.equal(torch.cat([p[1] for p in mparts]), mf)
+
+
+def test_dual_contouring_slabs_with_uneven_cuts_and_level(iso):
+    from isoext_b200 import dist as idist
+    vals = FIELDS["csg72"]().cuda()
+    g = iso.UniformGrid(list(vals.shape))
+    g.set_values(vals)
+    for level, cuts in ((0.0, [0, 30, 32, 71]), (0.02, [0, 2, 4, 60, 71]), (-0.01, [0, 35, 37, 39, 71])):
+        gv, gf = iso.dual_contouring(g, level)
+        world, parts = len(cuts) - 1, []
+        for r in range(world):
+            sg = idist.SlabGrid(list(vals.shape), rank=r, world=world, cuts=cuts, dc=True)
+            p = sg.plan
+            sg._ext.copy_(vals[p["ext_lo"]:p["ext_hi"] + 1])
+            parts.append(idist.dual_contouring_local(sg, level))
+        bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])])
+        for r, (v_own, f, n_lo, n_hi) in enumerate(parts):
+            idist.relabel_faces_(f, n_lo, n_hi, int(bases[r]), int(bases[r + 1]))
+        assert torch.equal(torch.cat([p[0] for p in parts]).view(torch.int32), gv.view(torch.int32))
+        assert torch.equal(torch.cat([p[1] for p in parts]), gf)
+
+
+def _band_grid(iso, vals):
+    """Sparse narrow band of a dense field: every crossing cell, with its own 8 corner values."""
+    import oracle  # noqa: F401  (test infrastructure only)
+    from test_dist_cpu import _sparse_band
+    cells, v8 = _sparse_band(vals.cpu().numpy())
+    g = iso.SparseGrid(list(vals.shape))
+    g.add_cells(torch.from_numpy(cells).to(torch.int32).cuda())
+    g.set_values(torch.from_numpy(v8).cuda())
+    return g
+
+
+@pytest.mark.parametrize("method", ["nagae", "lorensen"])
+@pytest.mark.parametrize("world", [2, 3, 6])
+@pytest.mark.parametrize("name", sorted(FIELDS))
+def test_sparse_grid_simulated_slabs_concatenate_to_single_device_mesh(iso, name, world, method):
+    """SparseGrid on slabs, CUDA side (dist.SparseSlab: owned cells + one ghost layer either side, emit range over the
+    cell list, ownership by position): parts relabelled by the CUDA kernel concatenate to the single-device sparse
+    mesh bit for bit."""
+    from isoext_b200 import dist as idist
+    vals = FIELDS[name]()
+    g = _band_grid(iso, vals)
+    gv, gf = iso.marching_cubes(g, 0.0, method)
+    parts = [idist.marching_cubes_sparse_local(idist.SparseSlab(g, rank=r, world=world), 0.0, method) for r in range(world)]
+    bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])])
+    for r, (v_own, f, n_lo, n_hi) in enumerate(parts):
+        idist.relabel_faces_(f, n_lo, n_hi, int(bases[r]), int(bases[r + 1]))
+    v, f = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    assert v.shape == gv.shape and torch.equal(v.view(torch.int32), gv.view(torch.int32))
+    assert torch.equal(f, gf)
+
+
 def test_c3_2048_csg_two_slabs_equal_single_gpu():
     """BASELINE.json configs[2] at FULL size on one GPU: the 2048^3 CSG field extracted whole and as two simulated
     slabs with load-balanced cuts must agree bit for bit; the mesh is a closed genus-0 surface whose x-sorted
@@ -149,6 +239,23 @@ def _nccl_worker(rank, world, port, transport, field_name):
                 assert len(v) == 0 and len(f) == 0, f"rank {rank} step {step}: expected an empty mesh"
                 continue
             assert torch.equal(v.view(torch.int32), gv.view(torch.int32)) and torch.equal(f, gf), f"rank {rank} step {step}: mismatch"
+        # dual contouring on slabs that fetch two planes from below (peer pull of 2 + 2 planes / NCCL send-recv)
+        sgd = idist.SlabGrid(list(vals.shape), dc=True)
+        sgd.set_owned_values(vals[lo:hi].contiguous())
+        g.set_values(vals)
+        for level in (0.0, 0.02):
+            dv, df = idist.gather_mesh(*idist.dual_contouring(sgd, level))
+            gdv, gdf = iso.dual_contouring(g, level)
+            assert torch.equal(dv.view(torch.int32), gdv.view(torch.int32)) and torch.equal(df, gdf), f"rank {rank}: DC slabs level {level}"
+            mv, mf = idist.gather_mesh(*idist.marching_cubes(sgd, level))
+            gmv, gmf = iso.marching_cubes(g, level)
+            assert torch.equal(mv.view(torch.int32), gmv.view(torch.int32)) and torch.equal(mf, gmf), f"rank {rank}: MC on dc slabs"
+        sgd.close()
+        # SparseGrid on slabs: every rank keeps its part of the band (+ ghost cells); only two counts cross ranks
+        band = _band_grid(iso, vals)
+        sv, sf = idist.gather_mesh(*idist.marching_cubes_sparse(idist.SparseSlab(band)))
+        gsv, gsf = iso.marching_cubes(band)
+        assert torch.equal(sv.view(torch.int32), gsv.view(torch.int32)) and torch.equal(sf, gsf), f"rank {rank}: sparse slabs"
         # same values again without a new set_owned_values, and the explicit no-exchange variant
         v_own, f_own = idist.marching_cubes(sg, 0.0)
         v2_own, f2_own = idist.marching_cubes(sg, 0.0, exchange=False)
