@@ -52,6 +52,8 @@ float isoext_axis_position(int64_t i, int64_t res, float amin, float amax);
 /* Tuning knob of the volume-streaming kernel (development only): low byte = variant, next byte =
  * launched blocks per SM; 0 = default. */
 int isoext_debug_set_signbits_variant(int v);
+/* Development tuning knobs (key 0: blocks per SM of the chained-scan kernels); value 0 = default. */
+int isoext_debug_set_tuning(int key, int value);
 
 /* Development: per-kernel CUDA-event timing of every launch of this library. */
 int isoext_debug_detail_enable(int on);
@@ -223,13 +225,16 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
  * triangles, or big_cap (candidates in oversized sort buckets that the second bucket level was sized for;
  * 0 = not enqueued) -- or if n_radix > 0 candidates needed the radix last resort of the sort while
  * radix == 0 (not enqueued): the caller then uses isoext_mc_dense_count + isoext_mc_dense_emit and passes
- * radix = 1 next time. */
+ * radix = 1 next time.
+ * Halo split (slabs): if halo_event (a cudaEvent_t) is not NULL, the first halo_planes_lo and the last halo_planes_hi
+ * x planes of `values` are still being filled on another stream, which records halo_event when done: the volume
+ * stream over the planes in between starts immediately and only the halo planes wait for the event. */
 int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                         const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
                         size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, int radix,
-                        float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
-                        int64_t *counts_out);
+                        float x_lo_threshold, float x_hi_threshold, int64_t halo_planes_lo, int64_t halo_planes_hi,
+                        void *halo_event, float *V, int32_t *F, void *stream, int64_t *counts_out);
 
 /* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
  * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->

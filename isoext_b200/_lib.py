@@ -25,6 +25,7 @@ SIGNATURES = {
     "isoext_abi_version": (_int, []),
     "isoext_axis_position": (_f32, [_i64, _i64, _f32, _f32]),
     "isoext_debug_set_signbits_variant": (_int, [_int]),
+    "isoext_debug_set_tuning": (_int, [_int, _int]),
     "isoext_debug_detail_enable": (_int, [_int]),
     "isoext_debug_detail_report": (_int, [C.c_char_p, _int]),
     "isoext_debug_detail_timeline": (_int, [C.c_char_p, _int]),
@@ -71,7 +72,7 @@ SIGNATURES = {
     "isoext_dc_sparse_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i64, _vp, _vp, _vp,
                                      _vp, _pi64]),
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
-                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _vp, _vp, _vp, _pi64]),
+                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "isoext_peer_sync_words": (_int, []),
     "isoext_peer_alloc": (_int, [_sz, C.POINTER(_vp), C.POINTER(C.c_ubyte)]),

@@ -31,6 +31,7 @@ void detail_mark(const char *name, cudaStream_t s, bool begin) {
 }
 long long g_kernel_launches = 0;
 int g_signbits_variant = 0;
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 StreamTimer g_stream_timer;
 void stream_timer_mark(cudaStream_t s) {
     StreamTimer &t = g_stream_timer;
@@ -46,6 +47,12 @@ void stream_timer_mark(cudaStream_t s) {
 extern "C" {
 // tuning knob for the streaming kernel: low byte = variant, next byte = blocks per SM (0 = default)
 int isoext_debug_set_signbits_variant(int v) { isx::g_signbits_variant = v; return 0; }
+// development tuning knobs (common.cuh: g_tuning); 0 restores the default
+int isoext_debug_set_tuning(int key, int value) {
+    if (key < 0 || key >= 8) return -1;
+    isx::g_tuning[key] = value;
+    return 0;
+}
 // Development: per-kernel CUDA-event timing.  enable(1) starts collecting; report() synchronises, writes
 // "name total_us launches" lines into buf and clears the records.
 int isoext_debug_detail_enable(int on) { isx::g_detail_timing = on != 0; return 0; }

@@ -38,6 +38,9 @@ int fail(int code, const std::string &msg);
 // bench.py reads these through isoext_profile_begin/end (api.cu); the product path never depends on them.
 extern long long g_kernel_launches;
 extern int g_signbits_variant;
+// development tuning knobs (isoext_debug_set_tuning): [0] blocks per SM of the chained-scan kernels (default 4)
+extern int g_tuning[8];
+static inline int scan_blocks(int sms) { return sms * (g_tuning[0] > 0 ? g_tuning[0] : 4); }
 struct StreamTimer {
     bool enabled = false;
     static constexpr int kMaxPairs = 4096;

@@ -477,7 +477,7 @@ int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z,
     const int sms = device_sms();
     launch_signbits(values, b.bits, p.P, level, stream);
     launch_compact(b.bits, p, ent, cap, row_start, b.descA, b.counters, b.span_cnt, b.heavy_list, stream);
-    ISX_LAUNCH(k_its_scan, sms * 4, 256, 0, stream, cap, b.counters, ent, cellslot, its_off, b.descC, b.descI);
+    ISX_LAUNCH(k_its_scan, scan_blocks(sms), 256, 0, stream, cap, b.counters, ent, cellslot, its_off, b.descC, b.descI);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
     ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -565,7 +565,7 @@ int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int
     ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) S / IT_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_dc_solve, sms * 8, 128, 0, stream, p, ent, S, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
     ISX_LAUNCH(k_dc_quads, sms * 8, 128, 0, stream, p, ent, S, row_start, cellslot, b.qmask, b.used);
-    ISX_LAUNCH(k_dc_scan, sms * 4, 256, 0, stream, S, b.counters, cellslot, b.qmask, b.used, b.quad_off, b.cand_of_cell, b.descQ, b.descU);
+    ISX_LAUNCH(k_dc_scan, scan_blocks(sms), 256, 0, stream, S, b.counters, cellslot, b.qmask, b.used, b.quad_off, b.cand_of_cell, b.descQ, b.descU);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
     ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -602,7 +602,7 @@ int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int6
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_dc_keys, sms * 8, 256, 0, stream, (u32) n_cells, b.cand_of_cell, dual_v, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
+    ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
                host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
     ISX_LAUNCH(k_dc_faces, sms * 8, 128, 0, stream, p, ent, S, row_start, cellslot, b.qmask, isout, b.quad_off, b.cand_of_cell,
                s.cand_rank, dual_v, F, quads_out);

@@ -113,7 +113,8 @@ __device__ __forceinline__ void ld_stream_f8(const float *p, float4 &a, float4 &
 
 // tail group (possibly empty) + one zero group of padding so that readers may over-fetch
 __device__ __forceinline__ void signbits_tail(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level,
-                                              i64 first_tail_group, i64 ngroups_total, u32 lane) {
+                                              i64 first_tail_group, i64 ngroups_total, u32 lane, bool pad) {
+    if (!pad && first_tail_group >= ngroups_total && (P & 127) == 0) return;   // sub-range of a larger volume: nothing to finish
     for (i64 g = first_tail_group; g <= ngroups_total; g++) {   // remaining full groups + the partial one
         i64 base = g << 7;
         u32 nib = 0;
@@ -125,12 +126,13 @@ __device__ __forceinline__ void signbits_tail(const float *__restrict__ v, u32 *
         u32 w = gather_word(nib, lane);
         if ((lane & 7) == 0) bits[(g << 2) + (lane >> 3)] = w;
     }
-    if ((lane & 7) == 0) bits[((ngroups_total + 1) << 2) + (lane >> 3)] = 0u;
+    if (pad && (lane & 7) == 0) bits[((ngroups_total + 1) << 2) + (lane >> 3)] = 0u;
 }
 
 // VEC8 = false: one float4 per lane per step (warp = 128 points); true: one 256-bit load (warp = 256 points).
 template <bool VEC8, int UNROLL>
-static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level) {
+static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level,
+                                                           bool pad) {
     const u32 lane = threadIdx.x & 31;
     const i64 ngroups = P >> 7;   // full groups of 128 points
     const i64 nwarps = ((i64) gridDim.x * blockDim.x) >> 5;
@@ -148,7 +150,7 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
                     if ((lane & 7) == 0) bits[((g + u) << 2) + (lane >> 3)] = w;
                 }
         }
-        if (wg == 0) signbits_tail(v, bits, P, level, ngroups, ngroups, lane);
+        if (wg == 0) signbits_tail(v, bits, P, level, ngroups, ngroups, lane, pad);
     } else {
         const i64 npairs = ngroups >> 1;   // units of 256 points
         for (i64 g = wg * UNROLL; g < npairs; g += nwarps * UNROLL) {
@@ -167,14 +169,15 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
                     if ((lane & 3) == 0) bits[((g + u) << 3) + (lane >> 2)] = w;
                 }
         }
-        if (wg == 0) signbits_tail(v, bits, P, level, npairs << 1, ngroups, lane);
+        if (wg == 0) signbits_tail(v, bits, P, level, npairs << 1, ngroups, lane, pad);
     }
 }
 
 int device_sms();
 extern int g_signbits_variant;   // tuning knob (api.cu); 0 = default
 // Launch the volume-streaming kernel (timed by the bench hooks).
-static inline void launch_signbits(const float *values, u32 *bits, i64 P, float level, cudaStream_t stream) {
+// pad = false: the range is a piece (a multiple of 256 points) of a larger volume whose last piece writes the padding
+static inline void launch_signbits(const float *values, u32 *bits, i64 P, float level, cudaStream_t stream, bool pad = true) {
     const int sms = device_sms();
     const int var = g_signbits_variant;
     const int per_sm = (var >> 8) ? (var >> 8) : 32;          // blocks per SM to launch (tools/tune_signbits.py)
@@ -183,12 +186,12 @@ static inline void launch_signbits(const float *values, u32 *bits, i64 P, float 
     int blocks = (int) (want < 1 ? 1 : (want > (i64) sms * per_sm ? (i64) sms * per_sm : want));
     stream_timer_mark(stream);
     switch (var & 0xff) {
-        case 1: ISX_LAUNCH((k_signbits_t<false, 8>), blocks, 256, 0, stream, values, bits, P, level); break;
-        case 3: ISX_LAUNCH((k_signbits_t<true, 4>), blocks, 256, 0, stream, values, bits, P, level); break;
-        case 4: ISX_LAUNCH((k_signbits_t<false, 4>), blocks, 256, 0, stream, values, bits, P, level); break;
-        case 5: ISX_LAUNCH((k_signbits_t<true, 1>), blocks, 256, 0, stream, values, bits, P, level); break;
+        case 1: ISX_LAUNCH((k_signbits_t<false, 8>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
+        case 3: ISX_LAUNCH((k_signbits_t<true, 4>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
+        case 4: ISX_LAUNCH((k_signbits_t<false, 4>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
+        case 5: ISX_LAUNCH((k_signbits_t<true, 1>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
         // default: 256-bit loads, 2 in flight per lane -- 6.0 TB/s at 512^3, 6.6 TB/s at 1024^3 on B200
-        default: ISX_LAUNCH((k_signbits_t<true, 2>), blocks, 256, 0, stream, values, bits, P, level); break;
+        default: ISX_LAUNCH((k_signbits_t<true, 2>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
     }
     stream_timer_mark(stream);
 }
@@ -769,7 +772,7 @@ static inline void launch_compact(const u32 *bits, const DenseParams &p, uint2 *
         xchunk = xchunk < 1 ? 1 : (xchunk > 8 ? 8 : xchunk);
         dim3 grid(((u32) p.g.Y * spr + 255) / 256, ((u32) p.g.X + xchunk - 1) / xchunk);
         ISX_LAUNCH(k_rowcount128, grid, 256, 0, stream, bits, p, row_start, span_cnt, xchunk);
-        ISX_LAUNCH(k_scan_rows, 148 * 4, 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+        ISX_LAUNCH(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
         const u32 heavy_cap = compact_heavy_cap(cap);
         ISX_LAUNCH(k_rowfill128, (p.R + 127u) / 128u, 128, 0, stream, bits, p, row_start, span_cnt, entries, cap, heavy_list, heavy_cap,
                    counters + C_NHEAVY);

@@ -260,25 +260,57 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
         if (tile >= ntiles) break;
         const u32 win0 = (entries[tile * SE_TILE].x / Y) * nsub;   // first bucket of layer x-1 of the tile's first entry
         const u32 s0 = tile * SE_TILE + threadIdx.x * SE_ITEMS;
-        u32 nt[SE_ITEMS], um[SE_ITEMS], sumT = 0, sumU = 0;
+        u32 nt[SE_ITEMS], um[SE_ITEMS], ex_[SE_ITEMS], bd_[SE_ITEMS], sumT = 0, sumU = 0;
+        if (s0 + SE_ITEMS <= S) {
+            // full group of 8 entries: ALL loads are issued before anything depends on them (the per-item version
+            // serialised 16 dependent L2 round trips per tile: byte loads -> branch -> entry/bucket loads -> atomics)
+            static_assert(SE_ITEMS == 8, "vector loads below assume 8 entries per thread");
+            const uint2 n8 = *reinterpret_cast<const uint2 *>(ntri + s0);
+            const uint2 ua = *reinterpret_cast<const uint2 *>(used + 3 * (size_t) s0);
+            const uint2 ub = *reinterpret_cast<const uint2 *>(used + 3 * (size_t) s0 + 8);
+            const uint2 uc = *reinterpret_cast<const uint2 *>(used + 3 * (size_t) s0 + 16);
+            const uint4 *ep = reinterpret_cast<const uint4 *>(entries + s0);
+            const uint4 e0 = ep[0], e1 = ep[1], e2 = ep[2], e3 = ep[3];
+            const uint4 b0 = *reinterpret_cast<const uint4 *>(bdelta + s0), b1 = *reinterpret_cast<const uint4 *>(bdelta + s0 + 4);
+            const u32 nw[2] = {n8.x, n8.y};
+            const u32 uw[6] = {ua.x, ua.y, ub.x, ub.y, uc.x, uc.y};
+            ex_[0] = e0.x; ex_[1] = e0.z; ex_[2] = e1.x; ex_[3] = e1.z; ex_[4] = e2.x; ex_[5] = e2.z; ex_[6] = e3.x; ex_[7] = e3.z;
+            bd_[0] = b0.x; bd_[1] = b0.y; bd_[2] = b0.z; bd_[3] = b0.w; bd_[4] = b1.x; bd_[5] = b1.y; bd_[6] = b1.z; bd_[7] = b1.w;
+#pragma unroll
+            for (int j = 0; j < SE_ITEMS; j++) {
+                nt[j] = (nw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                u32 m = 0;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const int byte = 3 * j + a;
+                    m |= ((uw[byte >> 2] >> (8 * (byte & 3))) & 0xffu) ? (1u << a) : 0u;
+                }
+                um[j] = m;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SE_ITEMS; j++) {
+                const u32 s = s0 + j;
+                nt[j] = 0; um[j] = 0; ex_[j] = 0; bd_[j] = 0;
+                if (s < S) {
+                    nt[j] = ntri[s];
+                    um[j] = (used[3 * s] ? 1u : 0u) | (used[3 * s + 1] ? 2u : 0u) | (used[3 * s + 2] ? 4u : 0u);
+                    ex_[j] = entries[s].x;
+                    bd_[j] = bdelta[s];
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < SE_ITEMS; j++) {
-            const u32 s = s0 + j;
-            nt[j] = 0;
-            um[j] = 0;
-            if (s < S) {
-                nt[j] = ntri[s];
-                um[j] = (used[3 * s] ? 1u : 0u) | (used[3 * s + 1] ? 2u : 0u) | (used[3 * s + 2] ? 4u : 0u);
-                if (um[j]) {   // x-bucket histogram of the vertices this entry owns (segsort.cuh)
-                    const u32 x = entries[s].x / Y, bd = bdelta[s];
+            if (um[j]) {   // x-bucket histogram of the vertices this entry owns (segsort.cuh)
+                const u32 x = ex_[j] / Y, bd = bd_[j];
 #pragma unroll
-                    for (int a = 0; a < 3; a++)
-                        if ((um[j] >> a) & 1u) {
-                            const u32 bkt = bucket_of(x, bd >> (8 * a), nsub);
-                            if (bkt - win0 < WIN) atomicAdd(&s_hist[bkt - win0], 1u);
-                            else atomicAdd(&bucket_count[bkt], 1u);
-                        }
-                }
+                for (int a = 0; a < 3; a++)
+                    if ((um[j] >> a) & 1u) {
+                        const u32 bkt = bucket_of(x, bd >> (8 * a), nsub);
+                        if (bkt - win0 < WIN) atomicAdd(&s_hist[bkt - win0], 1u);
+                        else atomicAdd(&bucket_count[bkt], 1u);
+                    }
             }
             sumT += nt[j];
             sumU += __popc(um[j]);
@@ -298,17 +330,36 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
         if (threadIdx.x < WIN && s_hist[threadIdx.x]) atomicAdd(&bucket_count[win0 + threadIdx.x], s_hist[threadIdx.x]);
         exT += s_preT;
         exU += s_preU;
+        if (s0 + SE_ITEMS <= S) {
+            u32 to[SE_ITEMS], ci[SE_ITEMS];
 #pragma unroll
-        for (int j = 0; j < SE_ITEMS; j++) {
-            const u32 s = s0 + j;
-            if (s < S) {
-                tri_off[s] = exT;
-                cand_info[s] = exU | (um[j] << 29);
+            for (int j = 0; j < SE_ITEMS; j++) {
+                to[j] = exT;
+                ci[j] = exU | (um[j] << 29);
                 exT += nt[j];
                 exU += __popc(um[j]);
-                if (s == S - 1) {
-                    counters[C_T] = exT;
-                    counters[C_VC] = exU;
+            }
+            *reinterpret_cast<uint4 *>(tri_off + s0) = make_uint4(to[0], to[1], to[2], to[3]);
+            *reinterpret_cast<uint4 *>(tri_off + s0 + 4) = make_uint4(to[4], to[5], to[6], to[7]);
+            *reinterpret_cast<uint4 *>(cand_info + s0) = make_uint4(ci[0], ci[1], ci[2], ci[3]);
+            *reinterpret_cast<uint4 *>(cand_info + s0 + 4) = make_uint4(ci[4], ci[5], ci[6], ci[7]);
+            if (s0 + SE_ITEMS == S) {
+                counters[C_T] = exT;
+                counters[C_VC] = exU;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SE_ITEMS; j++) {
+                const u32 s = s0 + j;
+                if (s < S) {
+                    tri_off[s] = exT;
+                    cand_info[s] = exU | (um[j] << 29);
+                    exT += nt[j];
+                    exU += __popc(um[j]);
+                    if (s == S - 1) {
+                        counters[C_T] = exT;
+                        counters[C_VC] = exU;
+                    }
                 }
             }
         }
@@ -567,8 +618,27 @@ static int enqueue_zero(const McBuffers &b, cudaStream_t stream) {
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, b.zero_bytes, stream));
     return OK;
 }
-static void enqueue_signbits(const float *values, const DenseParams &p, const McBuffers &b, cudaStream_t stream) {
-    launch_signbits(values, b.bits, p.P, p.level, stream);
+// Halo split (slab-sharded grids): the first halo_lo and the last halo_hi x planes of the slab are still being pulled
+// from the neighbours (on another stream; `halo_event` is recorded behind the pull).  The volume stream over the
+// owned planes starts at once and only the few halo planes wait for the event, so the pull costs no time.
+struct HaloSplit { i64 lo = 0, hi = 0; cudaEvent_t event = nullptr; };
+static int enqueue_signbits(const float *values, const DenseParams &p, const McBuffers &b, cudaStream_t stream, const HaloSplit &h = HaloSplit()) {
+    const i64 plane = p.YZ;
+    if (!h.event) {
+        launch_signbits(values, b.bits, p.P, p.level, stream);
+        return OK;
+    }
+    if ((plane & 255) != 0 || h.lo < 0 || h.hi < 0 || h.lo + h.hi >= p.g.X) {   // pieces must be multiples of 256 points
+        ISX_CUDA(cudaStreamWaitEvent(stream, h.event, 0));
+        launch_signbits(values, b.bits, p.P, p.level, stream);
+        return OK;
+    }
+    const i64 lo = h.lo * plane, hi = h.hi * plane, mid = p.P - lo - hi;
+    launch_signbits(values + lo, b.bits + (lo >> 5), mid, p.level, stream, hi == 0);
+    ISX_CUDA(cudaStreamWaitEvent(stream, h.event, 0));
+    if (lo) launch_signbits(values, b.bits, lo, p.level, stream, false);
+    if (hi) launch_signbits(values + lo + mid, b.bits + ((lo + mid) >> 5), hi, p.level, stream, true);
+    return OK;
 }
 static void enqueue_compact(const DenseParams &p, const McBuffers &b, u32 cap, cudaStream_t stream) {
     launch_compact(b.bits, p, b.entries, cap, b.row_start, b.descA, b.counters, b.span_cnt, b.heavy_list, stream);
@@ -578,15 +648,17 @@ static int enqueue_analysis(const float *values, const DenseParams &p, int metho
     const u32 nb = sort_buckets(p);
     ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                b.trimask, b.used, b.bdelta);
-    ISX_LAUNCH(k_scan_entries, sms * 4, 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
+    ISX_LAUNCH(k_scan_entries, scan_blocks(sms), 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
                b.entries, b.bdelta, (u32) p.g.Y, sort_nsub(p), b.seg.count, nb, b.seg);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }
-static int enqueue_phase1(const float *values, const DenseParams &p, int method, const McBuffers &b, u32 cap, cudaStream_t stream) {
+static int enqueue_phase1(const float *values, const DenseParams &p, int method, const McBuffers &b, u32 cap, cudaStream_t stream,
+                          const HaloSplit &halo = HaloSplit()) {
     int rc = enqueue_zero(b, stream);
     if (rc != OK) return rc;
-    enqueue_signbits(values, p, b, stream);
+    rc = enqueue_signbits(values, p, b, stream, halo);
+    if (rc != OK) return rc;
     enqueue_compact(p, b, cap, stream);
     return enqueue_analysis(values, p, method, b, cap, stream);
 }
@@ -622,7 +694,7 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     if (device_counts)
         ISX_LAUNCH(k_phase2_gate, 1, 1, 0, stream, b.counters, entry_cap, cand_cap, tri_cap, big_cap, allow_radix ? 1 : 0);
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
-    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
+    ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
                b.descV, klo, khi, n_dev, cand_cap, true);
     ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
                s.cand_rank, F, cand_cap, tri_cap, entry_cap);
@@ -714,7 +786,8 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
                         const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
                         size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, int radix, float x_lo_threshold,
-                        float x_hi_threshold, float *V, int32_t *F, void *stream_, int64_t *counts_out) {
+                        float x_hi_threshold, int64_t halo_planes_lo, int64_t halo_planes_hi, void *halo_event, float *V, int32_t *F,
+                        void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
@@ -730,7 +803,9 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
     McScratch s;
     if (carve_mc_scratch(cs, (size_t) cand_cap, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
     const u32 cap = (u32) cap_entries;
-    rc = enqueue_phase1(values, p, method, b, cap, stream);
+    HaloSplit halo;
+    halo.lo = halo_planes_lo; halo.hi = halo_planes_hi; halo.event = static_cast<cudaEvent_t>(halo_event);
+    rc = enqueue_phase1(values, p, method, b, cap, stream, halo);
     if (rc != OK) return rc;
     if (big_cap < 0 || big_cap > cand_cap) return fail(E_INVALID, "big_cap out of range");
     rc = enqueue_phase2(values, p, method, b, s, cap, 0, 0, true, (u32) cand_cap, (u32) (tri_cap > 0xffffffffLL ? 0xffffffffLL : tri_cap),

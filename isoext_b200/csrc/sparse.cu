@@ -564,7 +564,7 @@ int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_LAUNCH(k_sp_mc_classify, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, method, b.cinfo,
                (u32) emit_begin, (u32) emit_end);
     stream_timer_mark(stream);
-    ISX_LAUNCH(k_sp_scan2, sms * 4, 256, 0, stream, (u32) n, b.counters, b.cinfo, 8, 0xffu, 16, 0xfffu, b.offA, b.offB, b.descA,
+    ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, b.cinfo, 8, 0xffu, 16, 0xfffu, b.offA, b.offB, b.descA,
                b.descB, (int) C_T, (int) C_VC, (int) C_TICKET_B);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
@@ -599,7 +599,7 @@ int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_mc_keys, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, b.cinfo, b.offB, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
+    ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
                host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
     ISX_LAUNCH(k_sp_mc_faces, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, method, b.cinfo, b.offA, b.offB, s.cand_rank, F);
     ISX_CUDA(cudaGetLastError());
@@ -628,7 +628,7 @@ int isoext_its_sparse_count(const float *values8, int64_t n, float level, uint32
     ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descB, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_case, grid_for(n, 256, sms * 16), 256, 0, stream, values8, (u32) n, level, cinfo);
-    ISX_LAUNCH(k_sp_scan2, sms * 4, 256, 0, stream, (u32) n, b.counters, cinfo, 8, 1u, 16, 0xfffu, cellslot, its_off, b.descA, b.descB,
+    ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, cinfo, 8, 1u, 16, 0xfffu, cellslot, its_off, b.descA, b.descB,
                (int) C_T, (int) C_I, (int) C_TICKET_B);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
@@ -691,7 +691,7 @@ int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_LAUNCH(k_sp_dc_solve, blocks, 128, 0, stream, cell_idx, p, (u32) n, cinfo, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
     ISX_LAUNCH(k_sp_dc_quads, blocks, 128, 0, stream, values8, cell_idx, p, (u32) n, cinfo, b.dinfo, b.used);
     ISX_LAUNCH(k_sp_fold_used, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.used, b.dinfo);
-    ISX_LAUNCH(k_sp_scan2, sms * 4, 256, 0, stream, (u32) n, b.counters, b.dinfo, 0, 7u, 8, 1u, b.quad_off, b.cand_off, b.descA, b.descB,
+    ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, b.dinfo, 0, 7u, 8, 1u, b.quad_off, b.cand_off, b.descA, b.descB,
                (int) C_Q, (int) C_VC, (int) C_TICKET_D);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
@@ -723,7 +723,7 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_dc_keys, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.dinfo, b.cand_off, cellslot, dual_v, s.kx, s.ky, s.kz);
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    ISX_LAUNCH(k_unique, sms * 4, 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
+    ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
                host_float_key(-INFINITY), host_float_key(INFINITY));
     ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.dinfo, b.quad_off, b.cand_off, cellslot,
                s.cand_rank, dual_v, F, quads_out);

@@ -36,18 +36,47 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
         u32 c[UQ_ITEMS], x[UQ_ITEMS], y[UQ_ITEMS], z[UQ_ITEMS], isnew = 0, cnt = 0, nlo = 0, nhi = 0;
         // predecessor of the thread's first item
         u32 px = 0, py = 0, pz = 0;
+        const bool full = i0 + UQ_ITEMS <= n;
         // keys_sorted: kx/ky/kz are already in sorted order (indexed by position, not by candidate id)
-        if (i0 > 0 && i0 < n) {
-            const u32 pc = keys_sorted ? i0 - 1 : perm[i0 - 1];
-            px = kx[pc]; py = ky[pc]; pz = kz[pc];
+        if (full && keys_sorted) {
+            // all loads up front, 128 bits each (the per-item version serialised its L2 round trips)
+            static_assert(UQ_ITEMS == 8, "vector loads below assume 8 candidates per thread");
+            const uint4 c0 = *reinterpret_cast<const uint4 *>(perm + i0), c1 = *reinterpret_cast<const uint4 *>(perm + i0 + 4);
+            const uint4 x0 = *reinterpret_cast<const uint4 *>(kx + i0), x1 = *reinterpret_cast<const uint4 *>(kx + i0 + 4);
+            const uint4 y0 = *reinterpret_cast<const uint4 *>(ky + i0), y1 = *reinterpret_cast<const uint4 *>(ky + i0 + 4);
+            const uint4 z0 = *reinterpret_cast<const uint4 *>(kz + i0), z1 = *reinterpret_cast<const uint4 *>(kz + i0 + 4);
+            if (i0 > 0) { px = kx[i0 - 1]; py = ky[i0 - 1]; pz = kz[i0 - 1]; }
+            c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+            x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+            y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
+            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+        } else if (full) {
+            const uint4 c0 = *reinterpret_cast<const uint4 *>(perm + i0), c1 = *reinterpret_cast<const uint4 *>(perm + i0 + 4);
+            c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+            const u32 pc = i0 > 0 ? perm[i0 - 1] : 0u;
+#pragma unroll
+            for (int j = 0; j < UQ_ITEMS; j++) { x[j] = kx[c[j]]; y[j] = ky[c[j]]; z[j] = kz[c[j]]; }
+            if (i0 > 0) { px = kx[pc]; py = ky[pc]; pz = kz[pc]; }
+        } else {
+            if (i0 > 0 && i0 < n) {
+                const u32 pc = keys_sorted ? i0 - 1 : perm[i0 - 1];
+                px = kx[pc]; py = ky[pc]; pz = kz[pc];
+            }
+#pragma unroll
+            for (int j = 0; j < UQ_ITEMS; j++) {
+                const u32 i = i0 + j;
+                c[j] = 0; x[j] = 0; y[j] = 0; z[j] = 0;
+                if (i < n) {
+                    c[j] = perm[i];
+                    const u32 kidx = keys_sorted ? i : c[j];
+                    x[j] = kx[kidx]; y[j] = ky[kidx]; z[j] = kz[kidx];
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < UQ_ITEMS; j++) {
             const u32 i = i0 + j;
             if (i < n) {
-                c[j] = perm[i];
-                const u32 kidx = keys_sorted ? i : c[j];
-                x[j] = kx[kidx]; y[j] = ky[kidx]; z[j] = kz[kidx];
                 const bool nw = (i == 0) || x[j] != px || y[j] != py || z[j] != pz;
                 px = x[j]; py = y[j]; pz = z[j];
                 if (nw) {

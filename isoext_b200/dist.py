@@ -281,11 +281,15 @@ class SlabGrid:
         self._guard_overwrite()
         own.copy_(values)
 
-    def exchange_halos(self) -> None:
+    def exchange_halos(self, overlap: bool = False):
+        """Fill the halo planes.  ``overlap=True`` (peer transport only): the pull runs on a side stream and the call
+        returns ``(planes_below, planes_above, event)`` for ``mc_dense_raw(halo=...)`` -- the volume stream over the owned
+        planes then starts while the halo planes are still in flight; otherwise returns None (halo complete in stream
+        order)."""
         if self._peer is not None:
-            self._peer_exchange()
-        else:
-            exchange_halos(self._ext, self.plan, self.rank, self.world, self.group)
+            return self._peer_exchange(overlap)
+        exchange_halos(self._ext, self.plan, self.rank, self.world, self.group)
+        return None
 
     # ---- NVLink peer transport (csrc/peer.cu) -------------------------------------------------------
     def _peer_setup(self, ext_shape) -> None:
@@ -342,7 +346,7 @@ class SlabGrid:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().isoext_peer_wait(done[0], done[1], pr["epoch"], pr["err"].data_ptr(), _stream_ptr()))
 
-    def _peer_exchange(self) -> None:
+    def _peer_exchange(self, overlap: bool = False):
         from . import _lib
         from .grid import _stream_ptr
         lib, pr, p = _lib.lib(), self._peer, self.plan
@@ -364,11 +368,24 @@ class SlabGrid:
             src = pr["peer_ext"][self.rank + 1] + (g0 - q["ext_lo"]) * plane * 4
             seg[1] = (base + (g0 - p["ext_lo"]) * plane * 4, src, plane * len(p["halo_above"]), pr["peer_sync"][self.rank + 1])
         with torch.cuda.device(self.device):
-            st = _stream_ptr()
-            _lib.check(lib.isoext_peer_publish(pr["sync_ptr"], e, st))                        # my values of epoch e are in place
-            _lib.check(lib.isoext_peer_halo_pull(seg[0][0], seg[0][1], seg[0][2], seg[0][3], seg[1][0], seg[1][1], seg[1][2],
-                                                 seg[1][3], e, pr["err"].data_ptr(), st))
-            _lib.check(lib.isoext_peer_publish(pr["sync_ptr"] + 8, e, st))                    # I have pulled: neighbours may overwrite
+            main = torch.cuda.current_stream()
+            side = main
+            if overlap:
+                if pr.get("side") is None:
+                    pr["side"] = torch.cuda.Stream(device=self.device)
+                side = pr["side"]
+                side.wait_stream(main)      # this epoch's values are in place, the previous extraction has read its halo
+            with torch.cuda.stream(side):
+                st = _stream_ptr()
+                _lib.check(lib.isoext_peer_publish(pr["sync_ptr"], e, st))                    # my values of epoch e are in place
+                _lib.check(lib.isoext_peer_halo_pull(seg[0][0], seg[0][1], seg[0][2], seg[0][3], seg[1][0], seg[1][1], seg[1][2],
+                                                     seg[1][3], e, pr["err"].data_ptr(), st))
+                _lib.check(lib.isoext_peer_publish(pr["sync_ptr"] + 8, e, st))                # I have pulled: neighbours may overwrite
+                if overlap:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    return (len(p["halo_below"]), len(p["halo_above"]), ev)
+        return None
 
     def close(self) -> None:
         """Collective: unmap the peers' memory and free the exported allocations."""
@@ -403,9 +420,10 @@ def _device_view(ptr: int, n: int, dtype, device) -> torch.Tensor:
     return torch.as_tensor(_RawDevice(ptr, n, typestr), device=device)
 
 
-def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae"):
+def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae", halo=None):
     """The rank-local part of the distributed extraction (no communication): returns
-    ``(v_own, f_local, n_lo, n_hi)`` where ``f_local`` still holds extended-slab vertex ids."""
+    ``(v_own, f_local, n_lo, n_hi)`` where ``f_local`` still holds extended-slab vertex ids.
+    ``halo``: what ``sg.exchange_halos(overlap=True)`` returned (halo planes still in flight on a side stream)."""
     from .mc import _method_id, mc_dense_raw
     mid = _method_id(method)
     p = sg.plan
@@ -414,7 +432,7 @@ def marching_cubes_local(sg: SlabGrid, level: float = 0.0, method: str = "nagae"
         v_own, f, n_lo, n_hi, cap = mc_dense_raw(sg._ext, (p["n_ext"], Y, Z), sg.aabb_min, sg.aabb_max, level, mid, sg._ws,
                                                  cap_hint=sg._cap_hint, x_offset=p["ext_lo"], x_global=X,
                                                  emit_range=(p["emit_lo"], p["emit_hi"]), x_thresholds=sg.thresholds,
-                                                 hints=sg._hints)
+                                                 hints=sg._hints, halo=halo)
     sg._cap_hint = cap
     if v_own is None:
         return (torch.empty((0, 3), dtype=torch.float32, device=sg.device),
@@ -436,9 +454,8 @@ def marching_cubes(sg: SlabGrid, level: float = 0.0, method: str = "nagae", exch
 
     Concatenating the parts of ranks 0..R-1 gives exactly the single-GPU ``(v, f)`` (global vertex ids).
     Either element may be an empty tensor on a rank whose slab misses the surface."""
-    if exchange:
-        sg.exchange_halos()
-    v_own, f, n_lo, n_hi = marching_cubes_local(sg, level, method)
+    halo = sg.exchange_halos(overlap=True) if exchange else None
+    v_own, f, n_lo, n_hi = marching_cubes_local(sg, level, method, halo=halo)
     globalize_faces_(sg, f, n_lo, n_hi, peer=exchange)
     return v_own, f
 

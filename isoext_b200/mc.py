@@ -25,7 +25,7 @@ def _initial_cap(shape) -> int:
 
 
 def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_id, ws, cap_hint=0, x_offset=0,
-                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf), hints=None):
+                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf), hints=None, halo=None):
     """Run the dense pipeline on a (X,Y,Z) float32 CUDA tensor.
 
     Returns ``(V_own, F, n_lo, n_hi, cap_used)``: ``V_own`` the position-sorted welded vertices OWNED by
@@ -37,6 +37,10 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     ``hints``: a dict owned by the caller (one per grid) remembering the sizes of the previous extraction.
     With hints the single-call fast path (``isoext_mc_dense_run``: one stream sync, no host round trip
     between the phases) is tried first; any capacity miss falls back to count + emit.
+
+    ``halo``: ``(planes_lo, planes_hi, event)`` -- the first / last x planes of ``values`` are still being written on
+    another stream that records ``event`` (a ``torch.cuda.Event``) when done; the fast path starts streaming the planes
+    in between at once (slab halo pull overlapped with the volume stream), every other path waits for the event first.
     """
     lib = _lib.lib()
     X, Y, Z = shape
@@ -58,9 +62,12 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         scratch = ws.get("mc_scratch", lib.isoext_mc_dense_scratch_bytes(cand_cap), dev)
         V = torch.empty((cand_cap, 3), dtype=torch.float32, device=dev)
         F = torch.empty((tri_cap, 3), dtype=torch.int32, device=dev)
+        h_lo, h_hi, h_ev = (0, 0, None) if halo is None else (int(halo[0]), int(halo[1]), halo[2].cuda_event)
+        halo = None      # consumed: whatever follows this call runs behind the event
         rc = lib.isoext_mc_dense_run(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
                                      wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(), cand_cap, tri_cap,
-                                     big_cap, 1 if hints.get("radix") else 0, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), stream, counts)
+                                     big_cap, 1 if hints.get("radix") else 0, thr_lo, thr_hi, h_lo, h_hi, h_ev, V.data_ptr(),
+                                     F.data_ptr(), stream, counts)
         hints["radix"] = int(counts[7]) > 0     # the sort's radix last resort is only enqueued when it was needed last time
         if rc == 0:
             S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
@@ -74,6 +81,8 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
             cap = int(counts[0]) + 1024
         # fall through to the two-phase path
 
+    if halo is not None:
+        torch.cuda.current_stream().wait_event(halo[2])
     while True:
         nbytes = lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap)
         if nbytes == 0:
