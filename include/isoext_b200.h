@@ -136,6 +136,13 @@ int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t 
  * counts_out[0] = welded vertices. */
 size_t isoext_dc_dense_workspace_bytes(int64_t n_entries, int64_t n_cells);
 size_t isoext_dc_dense_scratch_bytes(int64_t n_candidates);
+/* GPU sparse-grid population from a dense field: replaces the Python chunk loop of the reference's
+ * recipe (tests/conftest.py:39-61 of the reference; doc/grids.ipynb runs 10,738 iterations of it at 1024^3).  Step 1 is
+ * isoext_its_dense_count (entries, cellslot; counts_out[1] = crossing cells); this is step 2: the ascending cell ids
+ * and the (n_cells, 8) corner values in the corner order of include/utils.cuh:32-60. */
+int isoext_band_from_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                                const void *entries, int64_t n_entries, const uint32_t *cellslot, int64_t *d_cell_idx,
+                                float *d_values8, void *stream);
 /* Slab support (no reference counterpart): emit_x_lo / emit_x_hi = local point planes [lo, hi) whose
  * sign-change edges emit their quad (0 .. X on one GPU); dual vertices of ALL cells of the slab are welded, and the
  * emit phase returns how many welded vertices lie below x_lo_threshold / x_hi_threshold (ownership by position,
@@ -271,6 +278,20 @@ int isoext_peer_publish_counts(uint64_t *d_sync, uint64_t epoch, int64_t n_own, 
 int isoext_relabel_faces_peer(int32_t *d_F, int64_t n_ids, int64_t n_lo, int64_t n_hi, int64_t n_own,
                               const uint64_t *const *peer_syncs, int rank, uint64_t epoch, int64_t *d_bases_out,
                               uint32_t *err_mapped, void *stream);
+
+/* ---- gaussian_smooth (src/isoext/utils.py:5-39 is a dense k^3 conv3d) ----------------
+ * Separable: three 1-D passes with clamped indices (= replicate padding).  taps_host: the k normalised 1-D weights
+ * (k odd, <= 127; the host layer computes them with the reference's expressions).  field, tmp and out are three
+ * distinct device buffers of X*Y*Z floats.  Agrees with the dense convolution to float32 rounding. */
+int isoext_gaussian_smooth_separable(const float *field, int64_t X, int64_t Y, int64_t Z, const float *taps_host, int k,
+                                     float *d_tmp, float *d_out, void *stream);
+
+/* ---- mesh output (host code, csrc/meshio.cu) --------------------------------------
+ * write_obj (src/isoext/utils.py:42-63 is a Python loop over v.tolist()): the same BYTES -- coordinates printed like
+ * Python's repr(float(x)), one-based face ids -- formatted on all host cores.  v (nv x 3 f32) and f (nf x 3 i32,
+ * zero-based) are HOST pointers.  An empty mesh leaves an empty file.  write_ply: binary little-endian PLY (extension). */
+int isoext_write_obj(const char *path, const float *v_host, int64_t nv, const int32_t *f_host, int64_t nf);
+int isoext_write_ply(const char *path, const float *v_host, int64_t nv, const int32_t *f_host, int64_t nf);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "isoext_its_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _vp, _i64, _vp, _vp, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "isoext_its_dense_normals": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "isoext_band_from_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "isoext_dc_dense_workspace_bytes": (_sz, [_i64, _i64]),
     "isoext_dc_dense_scratch_bytes": (_sz, [_i64]),
     "isoext_dc_dense_count": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _f32,
@@ -74,6 +75,9 @@ SIGNATURES = {
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "isoext_gaussian_smooth_separable": (_int, [_vp, _i64, _i64, _i64, _f3, _int, _vp, _vp, _vp]),
+    "isoext_write_obj": (_int, [C.c_char_p, _vp, _i64, _vp, _i64]),
+    "isoext_write_ply": (_int, [C.c_char_p, _vp, _i64, _vp, _i64]),
     "isoext_peer_sync_words": (_int, []),
     "isoext_peer_alloc": (_int, [_sz, C.POINTER(_vp), C.POINTER(C.c_ubyte)]),
     "isoext_peer_free": (_int, [_vp]),

@@ -181,6 +181,28 @@ __global__ void __launch_bounds__(128) k_its_emit(const float *__restrict__ valu
     }
 }
 
+// GPU sparse-grid population (replaces the Python chunk loop of the reference's recipe,
+// tests/conftest.py:39-61: get_potential_cell_indices -> get_points_by_cell_indices -> sdf -> filter_cell_indices ->
+// add_cells -> set_values): every crossing cell of the dense field becomes a sparse cell with its 8 corner values in
+// Morton corner order.  The ordered entry list already is the ascending cell list.
+__global__ void __launch_bounds__(256) k_band_emit(const float *__restrict__ values, DenseParams p, const uint2 *__restrict__ entries,
+                                                   u32 S, const u32 *__restrict__ cellslot, i64 *__restrict__ cell_idx,
+                                                   float *__restrict__ values8) {
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const uint2 e = entries[s];
+        if (!ent_cell(e.y)) continue;
+        const u32 slot = cellslot[s], r = e.x, z = ent_z(e.y);
+        const u32 x = r / Y, y = r - x * Y;
+        cell_idx[slot] = ((i64) (x + (u32) p.g.x_off) * (Y - 1) + y) * (Z - 1) + z;
+        CellData c;
+        load_cell_values(values, p, r, z, c);
+        float4 *o = reinterpret_cast<float4 *>(values8 + 8 * (size_t) slot);
+        o[0] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+        o[1] = make_float4(c.v[4], c.v[5], c.v[6], c.v[7]);
+    }
+}
+
 // QEF + solve + clip, one thread per active cell (dcmath.cuh: qef_solve_clip).
 __global__ void __launch_bounds__(128) k_dc_solve(DenseParams p, const uint2 *__restrict__ entries, u32 S,
                                                   const u32 *__restrict__ cellslot, const u32 *__restrict__ its_off,
@@ -525,6 +547,24 @@ int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t 
     if (n_entries <= 0) return OK;
     ISX_LAUNCH((k_its_emit<false, true>), device_sms() * 8, 128, 0, stream, values, p, static_cast<const uint2 *>(entries),
                (u32) n_entries, cellslot, its_off, const_cast<float *>(points), normals, nullptr, nullptr, nullptr, 0u, 0u);
+    ISX_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// Second step of the sparse population from a dense field (first step: isoext_its_dense_count, whose counts_out[1]
+// is the number of crossing cells): cell_idx (n_cells, ascending) and values8 (n_cells x 8).
+int isoext_band_from_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                                const void *entries, int64_t n_entries, const uint32_t *cellslot, int64_t *cell_idx,
+                                float *values8, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DenseParams p;
+    const float z3[3] = {0, 0, 0}, o3[3] = {1, 1, 1};
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, z3, o3, 0.f, 0, X, &p);
+    if (rc != OK) return rc;
+    if (n_entries <= 0) return OK;
+    if ((reinterpret_cast<uintptr_t>(values8) & 15u) != 0) return fail(E_INVALID, "values8 must be 16-byte aligned");
+    ISX_LAUNCH(k_band_emit, device_sms() * 8, 256, 0, stream, values, p, static_cast<const uint2 *>(entries), (u32) n_entries, cellslot,
+               cell_idx, values8);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }

@@ -157,6 +157,43 @@ class SparseGrid(Grid):
         X, Y, Z = self.shape
         return X, Y, Z, _lib.f3(self.aabb_min), _lib.f3(self.aabb_max)
 
+    # -- population on the GPU (extension) ----------------------------------------------
+    def populate_from_dense(self, values, level: float = 0.0, x_chunk: int | None = None) -> "SparseGrid":
+        """Make this grid the narrow band of a dense field: every cell whose 8 corner values straddle ``level``
+        (case not 0 / 255), with those values -- the result of the reference's population recipe
+        (tests/conftest.py:39-61 of the reference: potential ids -> points -> sdf -> filter -> add_cells -> set_values)
+        in one pass over the field instead of a Python loop over chunks.
+
+        ``values``: a UniformGrid of the same shape and AABB, or an (X, Y, Z) float32 CUDA tensor.  ``x_chunk``: planes
+        per pass (default: all); chunks bound the sign-bit workspace for very large fields."""
+        from .dc import its_dense_raw
+        from .grid import UniformGrid
+        vals = values._values if isinstance(values, UniformGrid) else values
+        _expect_cuda(vals, torch.float32, ndim=3, what="values")
+        if tuple(vals.shape) != self.shape:
+            raise RuntimeError("Cannot set values with different shapes")
+        lib = _lib.lib()
+        X, Y, Z = self.shape
+        step = X if not x_chunk else max(2, int(x_chunk))
+        cells, vals8 = [], []
+        with torch.cuda.device(self.device):
+            for x0 in range(0, X - 1, step - 1 if step < X else X):
+                x1 = min(X, x0 + step)                      # planes [x0, x1): cell layers [x0, x1 - 1)
+                sub = vals[x0:x1]
+                its, _ = its_dense_raw(sub, (x1 - x0, Y, Z), self.aabb_min, self.aabb_max, level, False, self._ws, x_offset=x0, x_global=X)
+                n = its.n_cells
+                ci = torch.empty(n, dtype=torch.int64, device=self.device)
+                v8 = torch.empty((n, 8), dtype=torch.float32, device=self.device)
+                _lib.check(lib.isoext_band_from_dense_emit(sub.data_ptr(), x1 - x0, Y, Z, x0, X, its.entries.data_ptr(), its.n_entries,
+                                                           its.cellslot.data_ptr(), ci.data_ptr(), v8.data_ptr(), _stream_ptr()))
+                cells.append(ci); vals8.append(v8)
+                if x1 >= X:
+                    break
+        self._cells = torch.cat(cells) if len(cells) > 1 else cells[0]
+        self._values = torch.cat(vals8) if len(vals8) > 1 else vals8[0]
+        self._int32_api = X * Y * Z <= 2147483647
+        return self
+
 
 def mc_sparse(grid: SparseGrid, level: float, method_id: int, emit_range=None, x_thresholds=(-math.inf, math.inf),
               with_counts: bool = False):

@@ -81,3 +81,21 @@ def test_sdf_primitives_and_ops(iso):
     assert torch.allclose(n.norm(dim=-1), torch.ones(2, device="cuda"), atol=1e-6)
     sm = S.SmoothUnionOp([S.SphereSDF(0.3), S.SphereSDF(0.4)], k=0.1)
     assert float(sm(p)[0]) <= -0.4 + 1e-6
+
+
+@pytest.mark.parametrize("shape,sigma,k", [((40, 33, 57), 1.0, None), ((16, 16, 16), 2.5, None), ((9, 70, 5), 0.8, 9), ((64, 64, 64), 1.5, 5)])
+def test_gaussian_smooth_separable_kernel_equals_dense_conv3d(iso, shape, sigma, k):
+    """csrc/smooth.cu (three 1-D passes, clamped indices) vs the reference's dense k^3 conv3d with replicate padding
+    (src/isoext/utils.py:5-39): float tolerance 1e-6 of the field's range (the summation order differs)."""
+    from isoext_b200 import utils as U
+    gen = torch.Generator().manual_seed(7)
+    field = torch.randn(shape, generator=gen).cuda() * 3.0 + 1.0
+    a = U.gaussian_smooth(field, sigma, k)                       # native separable path (default on CUDA float32)
+    b = U.gaussian_smooth(field, sigma, k, separable=False)      # the reference's expression
+    assert a.shape == field.shape and a.dtype == torch.float32
+    tol = 1e-6 * float(field.max() - field.min())
+    assert float((a - b).abs().max()) <= tol
+    # a constant field stays constant; the input is not modified
+    c = torch.full(shape, 2.5, device="cuda")
+    assert float((U.gaussian_smooth(c, sigma, k) - 2.5).abs().max()) < 1e-6
+    assert torch.equal(field, torch.randn(shape, generator=torch.Generator().manual_seed(7)).cuda() * 3.0 + 1.0)

@@ -199,3 +199,42 @@ def test_int64_indices_beyond_int_max(iso):
     assert len(v) > 0 and float((v.double().norm(dim=-1) - 0.7).abs().max()) < 1e-5
     dv, df = iso.dual_contouring(g)
     assert dv is not None and len(df) % 2 == 0
+
+
+@pytest.mark.parametrize("name", sorted(SDFS))
+def test_populate_from_dense_equals_the_reference_recipe(iso, name):
+    """SparseGrid.populate_from_dense (one pass of kernels over the field) == the reference's population recipe
+    (tests/conftest.py:39-61 of the reference, a Python loop over chunks): same cell list, same (N, 8) values,
+    hence the same meshes; also in x-chunks."""
+    mk, shape = SDFS[name]
+    sdf = mk()
+    want = populate(iso.SparseGrid(list(shape)), sdf, chunk=4096)
+    d = iso.UniformGrid(list(shape))
+    d.set_values(sdf(d.get_points()))
+    for chunk in (None, 9, 2):
+        g = iso.SparseGrid(list(shape)).populate_from_dense(d, 0.0, x_chunk=chunk)
+        assert g.get_cell_indices().dtype == torch.int32
+        assert torch.equal(g.get_cell_indices(), want.get_cell_indices())
+        assert torch.equal(g.get_values().view(torch.int32), want.get_values().view(torch.int32))
+    v, f = iso.marching_cubes(g)
+    dv, df = iso.marching_cubes(d)
+    assert torch.equal(v.view(torch.int32), dv.view(torch.int32)) and torch.equal(f, df)
+    e = iso.SparseGrid(list(shape)).populate_from_dense(torch.ones(shape, device="cuda"))
+    assert e.get_num_cells() == 0 and iso.marching_cubes(e) == (None, None)
+    with pytest.raises(RuntimeError):
+        iso.SparseGrid([8, 8, 8]).populate_from_dense(d)
+
+
+def test_populate_from_dense_1024_sphere_golden_count(iso):
+    """doc/grids.ipynb:307-309 of the reference: 2,416,778 active cells at 1024^3 -- here in one call."""
+    n = 1024
+    d = iso.UniformGrid([n] * 3)
+    ax = fields.axis(n).cuda()
+    view = d.values_view()
+    sdf = S.SphereSDF(0.7)
+    for a in range(0, n, 32):
+        view[a:a + 32] = sdf(torch.stack(torch.meshgrid(ax[a:a + 32], ax, ax, indexing="ij"), dim=-1))
+    g = iso.SparseGrid([n] * 3).populate_from_dense(d)
+    assert g.get_num_cells() == 2416778
+    v, f = iso.marching_cubes(g)
+    assert len(v) == 2416776
