@@ -86,7 +86,7 @@ size_t isoext_mc_dense_scratch_bytes(int64_t n_candidates);
 int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                           const float *aabb_min, const float *aabb_max, float level, int method,
                           int64_t emit_x_lo, int64_t emit_x_hi, void *workspace, size_t workspace_bytes,
-                          int64_t cap_entries, void *stream, int64_t *counts_out);
+                          int64_t cap_entries, const void *sdf_program, void *stream, int64_t *counts_out);
 
 /* Phase 2 (same arguments + the phase-1 workspace untouched in between).
  * V: capacity Vc x 3 f32, receives the welded vertices in the reference's order (lexicographic
@@ -98,7 +98,7 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
                          const float *aabb_min, const float *aabb_max, float level, int method,
                          int64_t emit_x_lo, int64_t emit_x_hi, void *workspace, size_t workspace_bytes,
                          int64_t cap_entries, void *scratch, size_t scratch_bytes, int64_t n_candidates, int64_t n_big,
-                         float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, void *stream,
+                         float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F, const void *sdf_program, void *stream,
                          int64_t *counts_out);
 
 /* ---- get_intersection on a UniformGrid  (src/its.cu:93-159, src/isoext_ext.cu:329-343) -------
@@ -112,20 +112,20 @@ size_t isoext_its_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t
 int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                            const float *aabb_min, const float *aabb_max, float level, void *workspace,
                            size_t workspace_bytes, int64_t cap_entries, void *entries, uint32_t *row_start,
-                           uint32_t *cellslot, uint32_t *its_off, void *stream, int64_t *counts_out);
+                           uint32_t *cellslot, uint32_t *its_off, const void *sdf_program, void *stream, int64_t *counts_out);
 /* Phase 2: points (I x 3), normals (I x 3; written only if compute_normals), isout (S bytes),
  * cell_offsets (n_cells+1 u32) and cell_indices (n_cells i64) as in include/its.cuh:9-12. */
 int isoext_its_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                           const float *aabb_min, const float *aabb_max, float level, int compute_normals,
                           const void *entries, int64_t n_entries, const uint32_t *cellslot, const uint32_t *its_off,
                           int64_t n_cells, int64_t n_its, float *points, float *normals, unsigned char *isout,
-                          uint32_t *cell_offsets, int64_t *cell_indices, void *stream);
+                          uint32_t *cell_offsets, int64_t *cell_indices, const void *sdf_program, void *stream);
 /* compute_intersection_normals (src/its.cu:270-284): trilinear central differences of each cell,
  * in the reference's float32 rounding pattern. */
 int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                              const float *aabb_min, const float *aabb_max, const void *entries, int64_t n_entries,
                              const uint32_t *cellslot, const uint32_t *its_off, const float *points, float *normals,
-                             void *stream);
+                             const void *sdf_program, void *stream);
 
 /* ---- dual_contouring on a UniformGrid  (src/dc.cu:161-218, src/isoext_ext.cu:345-378) --------
  * Phase 1: QEF (src/dc.cu:14-80) + pseudo-inverse solve (replaces src/batched_la.cu:104-179) + clip
@@ -141,8 +141,9 @@ size_t isoext_dc_dense_scratch_bytes(int64_t n_candidates);
  * isoext_its_dense_count (entries, cellslot; counts_out[1] = crossing cells); this is step 2: the ascending cell ids
  * and the (n_cells, 8) corner values in the corner order of include/utils.cuh:32-60. */
 int isoext_band_from_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
-                                const void *entries, int64_t n_entries, const uint32_t *cellslot, int64_t *d_cell_idx,
-                                float *d_values8, void *stream);
+                                const float *aabb_min, const float *aabb_max, const void *entries, int64_t n_entries,
+                                const uint32_t *cellslot, int64_t *d_cell_idx, float *d_values8, const void *sdf_program,
+                                void *stream);
 /* Slab support (no reference counterpart): emit_x_lo / emit_x_hi = local point planes [lo, hi) whose
  * sign-change edges emit their quad (0 .. X on one GPU); dual vertices of ALL cells of the slab are welded, and the
  * emit phase returns how many welded vertices lie below x_lo_threshold / x_hi_threshold (ownership by position,
@@ -241,7 +242,8 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
                         size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, int radix,
                         float x_lo_threshold, float x_hi_threshold, int64_t halo_planes_lo, int64_t halo_planes_hi,
-                        void *halo_event, float *V, int32_t *F, void *stream, int64_t *counts_out);
+                        void *halo_event, float *V, int32_t *F, const void *sdf_program, void *stream,
+                        int64_t *counts_out);
 
 /* Slab-local -> global vertex ids after the per-rank counts have been all-gathered (new capability;
  * the reference is single-GPU).  id < n_lo -> base_mine - (n_lo - id); n_lo <= id < n_hi ->
@@ -278,6 +280,17 @@ int isoext_peer_publish_counts(uint64_t *d_sync, uint64_t epoch, int64_t n_own, 
 int isoext_relabel_faces_peer(int32_t *d_F, int64_t n_ids, int64_t n_lo, int64_t n_hi, int64_t n_own,
                               const uint64_t *const *peer_syncs, int rank, uint64_t epoch, int64_t *d_bases_out,
                               uint32_t *err_mapped, void *stream);
+
+/* ---- analytic SDF programs (csrc/sdfprog.cuh) -------------------------------------
+ * The reference's workflow evaluates isoext.sdf objects with torch on grid.get_points(), stores the field and extracts
+ * it (src/isoext/sdf.py:69-221, tests/conftest.py:21-27).  For the built-in primitives and combinators the host layer
+ * compiles the object tree to a postfix program (isoext_sdf_program_bytes() bytes of device memory, layout of
+ * struct SdfProg) and every dense entry point above that takes `sdf_program` evaluates it wherever it would load a
+ * value: pass values = NULL and the field never exists in HBM (the volume pass becomes a compute pass with Lipschitz
+ * culling).  isoext_sdf_eval_dense materialises the field with the same device function (two-step path). */
+size_t isoext_sdf_program_bytes(void);
+int isoext_sdf_eval_dense(const void *sdf_program, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                          const float *aabb_min, const float *aabb_max, float *d_out, void *stream);
 
 /* ---- gaussian_smooth (src/isoext/utils.py:5-39 is a dense k^3 conv3d) ----------------
  * Separable: three 1-D passes with clamped indices (= replicate padding).  taps_host: the k normalised 1-D weights

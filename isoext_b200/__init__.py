@@ -11,12 +11,14 @@ if importlib.util.find_spec("torch") is None:  # same guard as the reference (sr
 
 from . import sdf, utils  # noqa: E402,F401
 from .dc import Intersection, dual_contouring, get_intersection  # noqa: E402,F401
-from .grid import Grid, UniformGrid  # noqa: E402,F401
+from .grid import Grid, ImplicitGrid, UniformGrid  # noqa: E402,F401
 from .mc import marching_cubes  # noqa: E402,F401
 from .sparse import SparseGrid  # noqa: E402,F401
-from .utils import gaussian_smooth, make_grid, write_obj  # noqa: E402,F401
+from .utils import gaussian_smooth, make_grid, write_obj, write_ply  # noqa: E402,F401
 
+# the reference's names, plus the extensions ImplicitGrid (analytic SDF evaluated in the kernels) and write_ply
 __all__ = [
+    "ImplicitGrid",
     "Intersection",
     "SparseGrid",
     "UniformGrid",
@@ -26,4 +28,5 @@ __all__ = [
     "marching_cubes",
     "make_grid",
     "write_obj",
+    "write_ply",
 ]

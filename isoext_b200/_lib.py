@@ -35,16 +35,18 @@ SIGNATURES = {
     "isoext_mc_dense_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "isoext_mc_dense_scratch_bytes": (_sz, [_i64]),
     "isoext_mc_dense_count": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
-                                     _vp, _sz, _i64, _vp, _pi64]),
+                                     _vp, _sz, _i64, _vp, _vp, _pi64]),
     "isoext_mc_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
-                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _pi64]),
+                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_its_dense_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "isoext_its_dense_count": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _vp, _sz, _i64, _vp, _vp, _vp, _vp,
-                                      _vp, _pi64]),
+                                      _vp, _vp, _pi64]),
     "isoext_its_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _vp, _i64, _vp, _vp, _i64, _i64,
-                                     _vp, _vp, _vp, _vp, _vp, _vp]),
-    "isoext_its_dense_normals": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "isoext_band_from_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "isoext_its_dense_normals": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "isoext_sdf_program_bytes": (_sz, []),
+    "isoext_sdf_eval_dense": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp]),
+    "isoext_band_from_dense_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "isoext_dc_dense_workspace_bytes": (_sz, [_i64, _i64]),
     "isoext_dc_dense_scratch_bytes": (_sz, [_i64]),
     "isoext_dc_dense_count": (_int, [_i64, _i64, _i64, _i64, _i64, _f3, _f3, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _f32,
@@ -73,7 +75,7 @@ SIGNATURES = {
     "isoext_dc_sparse_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i64, _vp, _vp, _vp,
                                      _vp, _pi64]),
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
-                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _pi64]),
+                                   _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "isoext_gaussian_smooth_separable": (_int, [_vp, _i64, _i64, _i64, _f3, _int, _vp, _vp, _vp]),
     "isoext_write_obj": (_int, [C.c_char_p, _vp, _i64, _vp, _i64]),

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_its_scan(u32 cap, u32 *__restrict__ cou
 // ---------------------------------------------------------------------------------------------
 // per active cell: crossing points in edge order 0..11 (src/its.cu:37-90), normals, is_out bits
 // ---------------------------------------------------------------------------------------------
-template <bool POINTS, bool NORMALS>
+template <bool POINTS, bool NORMALS, bool IMPLICIT = false>
 __global__ void __launch_bounds__(128) k_its_emit(const float *__restrict__ values, DenseParams p,
                                                   const uint2 *__restrict__ entries, u32 S, const u32 *__restrict__ cellslot,
                                                   const u32 *__restrict__ its_off, float *__restrict__ points,
@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(128) k_its_emit(const float *__restrict__ valu
             const u32 own = ent_own(w);
             u32 io = 0;
             if (own) {
-                const i64 n = (i64) r * Z + z;
-                const float v0 = __ldg(values + n);
-                if ((own & 1u) && v0 <= __ldg(values + n + 1)) io |= 1u;
-                if ((own & 2u) && v0 <= __ldg(values + n + Z)) io |= 2u;
-                if ((own & 4u) && v0 <= __ldg(values + n + p.YZ)) io |= 4u;
+                const u32 x = r / Y, y = r - x * Y;
+                const float v0 = field_value<IMPLICIT>(values, p, x, y, z);
+                if ((own & 1u) && v0 <= field_value<IMPLICIT>(values, p, x, y, z + 1)) io |= 1u;
+                if ((own & 2u) && v0 <= field_value<IMPLICIT>(values, p, x, y + 1, z)) io |= 2u;
+                if ((own & 4u) && v0 <= field_value<IMPLICIT>(values, p, x + 1, y, z)) io |= 4u;
             }
             isout[s] = (unsigned char) io;
         }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128) k_its_emit(const float *__restrict__ valu
             if (slot == n_cells - 1) cell_offsets[n_cells] = n_its;
         }
         CellData c;
-        load_cell(values, p, r, z, c);
+        load_cell<IMPLICIT>(values, p, r, z, c);
         const u32 status = edge_mask_of_case(ent_case(w));
 #pragma unroll
         for (int k = 0; k < 12; k++) {
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(128) k_its_emit(const float *__restrict__ valu
 // tests/conftest.py:39-61: get_potential_cell_indices -> get_points_by_cell_indices -> sdf -> filter_cell_indices ->
 // add_cells -> set_values): every crossing cell of the dense field becomes a sparse cell with its 8 corner values in
 // Morton corner order.  The ordered entry list already is the ascending cell list.
+template <bool IMPLICIT>
 __global__ void __launch_bounds__(256) k_band_emit(const float *__restrict__ values, DenseParams p, const uint2 *__restrict__ entries,
                                                    u32 S, const u32 *__restrict__ cellslot, i64 *__restrict__ cell_idx,
                                                    float *__restrict__ values8) {
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256) k_band_emit(const float *__restrict__ val
         const u32 x = r / Y, y = r - x * Y;
         cell_idx[slot] = ((i64) (x + (u32) p.g.x_off) * (Y - 1) + y) * (Z - 1) + z;
         CellData c;
-        load_cell_values(values, p, r, z, c);
+        load_cell_values<IMPLICIT>(values, p, r, z, c);
         float4 *o = reinterpret_cast<float4 *>(values8 + 8 * (size_t) slot);
         o[0] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
         o[1] = make_float4(c.v[4], c.v[5], c.v[6], c.v[7]);
@@ -478,12 +479,13 @@ size_t isoext_its_dense_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t
 int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                            const float *aabb_min, const float *aabb_max, float level, void *workspace, size_t workspace_bytes,
                            int64_t cap_entries, void *entries, uint32_t *row_start, uint32_t *cellslot, uint32_t *its_off,
-                           void *stream_, int64_t *counts_out) {
+                           const void *sdf_program, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, 0, X - 1, &p);
     if (rc != OK) return rc;
-    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
+    if (!p.sdf && (reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
     if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
     Carver c(workspace);
     ItsWs b;
@@ -497,7 +499,8 @@ int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z,
     ISX_CUDA(cudaMemsetAsync(b.descC, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descI, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     const int sms = device_sms();
-    launch_signbits(values, b.bits, p.P, level, stream);
+    if (p.sdf) launch_sdf_bits(p, b.bits, stream);
+    else launch_signbits(values, b.bits, p.P, level, stream);
     launch_compact(b.bits, p, ent, cap, row_start, b.descA, b.counters, b.span_cnt, b.heavy_list, stream);
     ISX_LAUNCH(k_its_scan, scan_blocks(sms), 256, 0, stream, cap, b.counters, ent, cellslot, its_off, b.descC, b.descI);
     ISX_CUDA(cudaGetLastError());
@@ -517,20 +520,21 @@ int isoext_its_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, 
                           const float *aabb_min, const float *aabb_max, float level, int compute_normals, const void *entries,
                           int64_t n_entries, const uint32_t *cellslot, const uint32_t *its_off, int64_t n_cells, int64_t n_its,
                           float *points, float *normals, unsigned char *isout, uint32_t *cell_offsets, int64_t *cell_indices,
-                          void *stream_) {
+                          const void *sdf_program, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, 0, X - 1, &p);
     if (rc != OK) return rc;
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
     if (n_entries <= 0) return OK;
     const uint2 *ent = static_cast<const uint2 *>(entries);
     const int sms = device_sms();
-    if (compute_normals)
-        ISX_LAUNCH((k_its_emit<true, true>), sms * 8, 128, 0, stream, values, p, ent, (u32) n_entries, cellslot, its_off, points,
-                   normals, isout, cell_offsets, cell_indices, (u32) n_cells, (u32) n_its);
-    else
-        ISX_LAUNCH((k_its_emit<true, false>), sms * 8, 128, 0, stream, values, p, ent, (u32) n_entries, cellslot, its_off, points,
-                   normals, isout, cell_offsets, cell_indices, (u32) n_cells, (u32) n_its);
+#define ISX_ITS_EMIT(N, I)                                                                                                     \
+    ISX_LAUNCH((k_its_emit<true, N, I>), sms * 8, 128, 0, stream, values, p, ent, (u32) n_entries, cellslot, its_off, points, normals, \
+               isout, cell_offsets, cell_indices, (u32) n_cells, (u32) n_its)
+    if (compute_normals) { if (p.sdf) ISX_ITS_EMIT(true, true); else ISX_ITS_EMIT(true, false); }
+    else { if (p.sdf) ISX_ITS_EMIT(false, true); else ISX_ITS_EMIT(false, false); }
+#undef ISX_ITS_EMIT
     ISX_CUDA(cudaGetLastError());
     return OK;
 }
@@ -539,14 +543,19 @@ int isoext_its_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, 
 int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                              const float *aabb_min, const float *aabb_max, const void *entries, int64_t n_entries,
                              const uint32_t *cellslot, const uint32_t *its_off, const float *points, float *normals,
-                             void *stream_) {
+                             const void *sdf_program, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, 0, X - 1, &p);
     if (rc != OK) return rc;
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
     if (n_entries <= 0) return OK;
-    ISX_LAUNCH((k_its_emit<false, true>), device_sms() * 8, 128, 0, stream, values, p, static_cast<const uint2 *>(entries),
-               (u32) n_entries, cellslot, its_off, const_cast<float *>(points), normals, nullptr, nullptr, nullptr, 0u, 0u);
+    if (p.sdf)
+        ISX_LAUNCH((k_its_emit<false, true, true>), device_sms() * 8, 128, 0, stream, values, p, static_cast<const uint2 *>(entries),
+                   (u32) n_entries, cellslot, its_off, const_cast<float *>(points), normals, nullptr, nullptr, nullptr, 0u, 0u);
+    else
+        ISX_LAUNCH((k_its_emit<false, true, false>), device_sms() * 8, 128, 0, stream, values, p, static_cast<const uint2 *>(entries),
+                   (u32) n_entries, cellslot, its_off, const_cast<float *>(points), normals, nullptr, nullptr, nullptr, 0u, 0u);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }
@@ -554,17 +563,40 @@ int isoext_its_dense_normals(const float *values, int64_t X, int64_t Y, int64_t 
 // Second step of the sparse population from a dense field (first step: isoext_its_dense_count, whose counts_out[1]
 // is the number of crossing cells): cell_idx (n_cells, ascending) and values8 (n_cells x 8).
 int isoext_band_from_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
-                                const void *entries, int64_t n_entries, const uint32_t *cellslot, int64_t *cell_idx,
-                                float *values8, void *stream_) {
+                                const float *aabb_min, const float *aabb_max, const void *entries, int64_t n_entries,
+                                const uint32_t *cellslot, int64_t *cell_idx, float *values8, const void *sdf_program, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DenseParams p;
-    const float z3[3] = {0, 0, 0}, o3[3] = {1, 1, 1};
-    int rc = make_dense_params(X, Y, Z, x_offset, X_global, z3, o3, 0.f, 0, X, &p);
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, 0, X, &p);
     if (rc != OK) return rc;
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
     if (n_entries <= 0) return OK;
     if ((reinterpret_cast<uintptr_t>(values8) & 15u) != 0) return fail(E_INVALID, "values8 must be 16-byte aligned");
-    ISX_LAUNCH(k_band_emit, device_sms() * 8, 256, 0, stream, values, p, static_cast<const uint2 *>(entries), (u32) n_entries, cellslot,
-               cell_idx, values8);
+    if (p.sdf)
+        ISX_LAUNCH(k_band_emit<true>, device_sms() * 8, 256, 0, stream, values, p, static_cast<const uint2 *>(entries), (u32) n_entries,
+                   cellslot, cell_idx, values8);
+    else
+        ISX_LAUNCH(k_band_emit<false>, device_sms() * 8, 256, 0, stream, values, p, static_cast<const uint2 *>(entries), (u32) n_entries,
+                   cellslot, cell_idx, values8);
+    ISX_CUDA(cudaGetLastError());
+    return OK;
+}
+
+// ---- analytic programs (sdfprog.cuh) ---------------------------------------------------------------
+size_t isoext_sdf_program_bytes(void) { return sizeof(SdfProg); }
+// Materialise the field of a program on a grid / slab: out = (X, Y, Z) f32.  The two-step path, and the reference point of the
+// fused path (same device function).
+int isoext_sdf_eval_dense(const void *sdf_program, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
+                          const float *aabb_min, const float *aabb_max, float *out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!sdf_program) return fail(E_INVALID, "no program");
+    DenseParams p;
+    int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, 0.f, 0, X, &p);
+    if (rc != OK) return rc;
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
+    i64 want = (p.P + 255) / 256;
+    const i64 cap = (i64) device_sms() * 32;
+    ISX_LAUNCH(k_sdf_fill, (int) (want > cap ? cap : want), 256, 0, stream, p, out);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }

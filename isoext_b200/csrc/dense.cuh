@@ -14,6 +14,7 @@
 //             (an edge shared by 4 cells is owned by exactly one entry; no hash pass, no dense map)
 #pragma once
 #include "common.cuh"
+#include "sdfprog.cuh"
 
 namespace isx {
 
@@ -55,7 +56,22 @@ struct DenseParams {
     // k_cell_tris fast path: an edge whose crossing parameter t lies in [eps2[a], 1 - eps2[a]] (a = axis of the edge:
     // 0 x, 1 y, 2 z) is provably more than an ulp away from both end points, see cell_is_plain()
     float eps2[3];
+    // implicit field (sdfprog.cuh): when set, no `values` array exists and every kernel that would load a value
+    // evaluates the program at the point's position instead
+    const SdfProg *sdf;
 };
+
+// value of the field at local point (x, y, z): a load, or an evaluation of the analytic program at the position
+// get_points() reports for that point
+// IMPLICIT is a template parameter of the kernels (not a run-time branch), so the explicit-field instances carry no
+// trace of the interpreter (no call, no stack frame, no spills).
+template <bool IMPLICIT>
+__device__ __forceinline__ float field_value(const float *__restrict__ values, const DenseParams &p, u32 x, u32 y, u32 z) {
+    if (IMPLICIT)
+        return sdf_eval(p.sdf, axis_pos(x + (u32) p.g.x_off, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]),
+                        axis_pos(y, (u32) p.g.Y - 1, p.g.amin[1], p.g.asize[1]), axis_pos(z, (u32) p.g.Z - 1, p.g.amin[2], p.g.asize[2]));
+    return __ldg(values + ((i64) x * (u32) p.g.Y + y) * (u32) p.g.Z + z);
+}
 __host__ __device__ __forceinline__ u32 sort_nsub(const DenseParams &p) { return p.gy + p.gx; }
 __host__ __device__ __forceinline__ u32 sort_buckets(const DenseParams &p) { return ((u32) p.g.X + 2) * (p.gy + p.gx); }
 
@@ -173,6 +189,64 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1 for implicit fields: sign bits straight from the analytic program, no field in HBM.  One thread per 32-bit
+// word of the flat bit array.  If the word's 32 points lie in one row, the program is evaluated ONCE at the middle of
+// the word: every supported operator is 1-Lipschitz, so when |f(mid) - level| exceeds (half the word's length) x L
+// plus a float-error margin all 32 points have the sign of the middle and the word is written without evaluating them
+// (> 95 % of the words of a typical volume).  Otherwise (and for words straddling two rows) the points are evaluated.
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__restrict__ bits) {
+    const i64 P = p.P, nwords = (P + 31) >> 5;
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 resx = (u32) p.g.Xg - 1, resy = Y - 1, resz = Z - 1;
+    const i64 nall = (i64) (((P >> 7) + 2) << 2);             // = signbits_words(P): the array is zero-padded to here
+    for (i64 w = (i64) blockIdx.x * blockDim.x + threadIdx.x; w < nall; w += (i64) gridDim.x * blockDim.x) {
+        if (w >= nwords) { bits[w] = 0u; continue; }          // padding words (readers may over-fetch, see signbits_tail)
+        const i64 n0 = w << 5;
+        const u32 z0 = (u32) (n0 % Z);
+        const i64 r = n0 / Z;
+        const u32 y = (u32) (r % Y), x = (u32) (r / Y);
+        u32 word = 0;
+        if (z0 + 32u <= Z) {
+            const float fx = axis_pos(x + (u32) p.g.x_off, resx, p.g.amin[0], p.g.asize[0]), fy = axis_pos(y, resy, p.g.amin[1], p.g.asize[1]);
+            const float za = axis_pos(z0, resz, p.g.amin[2], p.g.asize[2]), zb = axis_pos(z0 + 31u, resz, p.g.amin[2], p.g.asize[2]);
+            const float mid = 0.5f * (za + zb), half = 0.5f * fabsf(zb - za);
+            const float fm = sdf_eval(p.sdf, fx, fy, mid);
+            const float d = fabsf(fm - p.level);
+            // margin: evaluation error of f (a few ulp of its operands' magnitude) and of the positions
+            const float margin = 1e-4f * (1.0f + fabsf(fm) + fabsf(p.level) + fabsf(fx) + fabsf(fy) + fabsf(mid));
+            if (d > p.sdf->lipschitz * half + margin) {
+                word = (__fsub_rn(fm, p.level) < 0.0f) ? 0xffffffffu : 0u;
+            } else {
+                for (u32 k = 0; k < 32u; k++) {
+                    const float v = sdf_eval(p.sdf, fx, fy, axis_pos(z0 + k, resz, p.g.amin[2], p.g.asize[2]));
+                    word |= (u32) (__fsub_rn(v, p.level) < 0.0f) << k;
+                }
+            }
+        } else {
+            for (u32 k = 0; k < 32u && n0 + k < P; k++) {
+                const i64 n = n0 + k;
+                const u32 zz = (u32) (n % Z);
+                const i64 rr = n / Z;
+                const float v = field_value<true>(nullptr, p, (u32) (rr / Y), (u32) (rr % Y), zz);
+                word |= (u32) (__fsub_rn(v, p.level) < 0.0f) << k;
+            }
+        }
+        bits[w] = word;
+    }
+}
+
+// materialise the field of an implicit grid (the two-step path; parity reference of the fused path)
+static __global__ void __launch_bounds__(256) k_sdf_fill(DenseParams p, float *__restrict__ out) {
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    for (i64 n = (i64) blockIdx.x * blockDim.x + threadIdx.x; n < p.P; n += (i64) gridDim.x * blockDim.x) {
+        const u32 z = (u32) (n % Z);
+        const i64 r = n / Z;
+        out[n] = field_value<true>(nullptr, p, (u32) (r / Y), (u32) (r % Y), z);
+    }
+}
+
 int device_sms();
 extern int g_signbits_variant;   // tuning knob (api.cu); 0 = default
 // Launch the volume-streaming kernel (timed by the bench hooks).
@@ -196,6 +270,15 @@ static inline void launch_signbits(const float *values, u32 *bits, i64 P, float 
     stream_timer_mark(stream);
 }
 static inline size_t signbits_words(i64 P) { return (size_t) (((P >> 7) + 2) << 2); }
+// volume pass of an implicit field (timed like the streaming kernel)
+static inline void launch_sdf_bits(const DenseParams &p, u32 *bits, cudaStream_t stream) {
+    const i64 nwords = (i64) signbits_words(p.P);
+    i64 want = (nwords + 255) / 256;
+    const i64 cap = (i64) device_sms() * 32;
+    stream_timer_mark(stream);
+    ISX_LAUNCH(k_sdf_bits, (int) (want > cap ? cap : want), 256, 0, stream, p, bits);
+    stream_timer_mark(stream);
+}
 
 // bits n..n+31 -> b0 ; bits n+1..n+32 -> b1
 __device__ __forceinline__ void fetch33(const u32 *__restrict__ bits, i64 n, u32 &b0, u32 &b1) {
@@ -649,8 +732,23 @@ struct CellData {
     float px[2], py[2], pz[2];
 };
 
+// same, for call sites that already hold the flat index n of a base point: explicit fields load values[n + off]
+// exactly as before (no index arithmetic is added to the explicit-field instances)
+template <bool IMPLICIT>
+__device__ __forceinline__ float field_at(const float *__restrict__ values, const DenseParams &p, i64 n, i64 off, u32 x, u32 y, u32 z) {
+    if (IMPLICIT) return field_value<true>(values, p, x, y, z);
+    return __ldg(values + n + off);
+}
+
+template <bool IMPLICIT = false>
 __device__ __forceinline__ void load_cell_values(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, CellData &c) {
     const u32 Z = (u32) p.g.Z;
+    if (IMPLICIT) {
+        const u32 Y = (u32) p.g.Y, x = r / Y, y = r - x * Y;
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) c.v[k] = field_value<true>(values, p, x + ((k >> 2) & 1), y + ((k >> 1) & 1), z + (k & 1));
+        return;
+    }
     const i64 n = (i64) r * Z + z;
     c.v[0] = __ldg(values + n);
     c.v[1] = __ldg(values + n + 1);
@@ -692,25 +790,10 @@ __device__ __forceinline__ bool cell_is_plain(const CellData &c, u32 status, con
         }
     return plain;
 }
+template <bool IMPLICIT = false>
 __device__ __forceinline__ void load_cell(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, CellData &c) {
-    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
-    const u32 x = r / Y, y = r - x * Y;
-    const i64 n = (i64) r * Z + z;
-    c.v[0] = __ldg(values + n);
-    c.v[1] = __ldg(values + n + 1);
-    c.v[2] = __ldg(values + n + Z);
-    c.v[3] = __ldg(values + n + Z + 1);
-    c.v[4] = __ldg(values + n + p.YZ);
-    c.v[5] = __ldg(values + n + p.YZ + 1);
-    c.v[6] = __ldg(values + n + p.YZ + Z);
-    c.v[7] = __ldg(values + n + p.YZ + Z + 1);
-    const u32 xg = x + (u32) p.g.x_off;
-    c.px[0] = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
-    c.px[1] = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
-    c.py[0] = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
-    c.py[1] = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
-    c.pz[0] = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
-    c.pz[1] = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
+    load_cell_values<IMPLICIT>(values, p, r, z, c);
+    load_cell_positions(p, r, z, c);
 }
 
 // position of the iso-crossing on cell edge e (exact reference arithmetic, see common.cuh)

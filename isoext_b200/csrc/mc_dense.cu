@@ -125,31 +125,32 @@ __device__ __forceinline__ u32 sub_bucket(const DenseParams &p, i64 xb /* global
     return p.gy + k;
 }
 
+template <bool IMPLICIT>
 __device__ __forceinline__ u32 owned_buckets(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, u32 own) {
     if (!own) return 0u;
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
     const u32 x = r / Y, y = r - x * Y;
     const i64 n = (i64) r * Z + z;
     const u32 xg = x + (u32) p.g.x_off;
-    const float v0 = __ldg(values + n);
+    const float v0 = field_at<IMPLICIT>(values, p, n, 0, x, y, z);
     const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
     const float py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
     u32 out = 0;
     if (own & 1u) {
-        const float t = edge_t(v0, __ldg(values + n + 1), p.level);
+        const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, 1, x, y, z + 1), p.level);
         const float xv = lerp_ref(t, px0, px0);
         const u32 code = xv < px0 ? 0u : 1u;
         out |= code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py0), y) << 2);
     }
     if (own & 2u) {
-        const float t = edge_t(v0, __ldg(values + n + Z), p.level);
+        const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, Z, x, y + 1, z), p.level);
         const float xv = lerp_ref(t, px0, px0);
         const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
         const u32 code = xv < px0 ? 0u : 1u;
         out |= (code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py1), y) << 2)) << 8;
     }
     if (own & 4u) {
-        const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
+        const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, p.YZ, x + 1, y, z), p.level);
         const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
         const float xv = lerp_ref(t, px0, px1);
         const u32 code = xv >= px1 ? 2u : (xv < px0 ? 0u : 1u);
@@ -163,6 +164,7 @@ __device__ __forceinline__ u32 bucket_of(u32 x, u32 byte, u32 nsub) { return (x 
 // ---------------------------------------------------------------------------------------------
 // K3: one thread per entry that is a valid cell.
 // ---------------------------------------------------------------------------------------------
+template <bool IMPLICIT>
 __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ values, DenseParams p, int method,
                                                    const uint2 *__restrict__ entries, const u32 *__restrict__ row_start,
                                                    u32 cap, const u32 *__restrict__ counters, u32 *__restrict__ nb,
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const uint2 e = entries[s];
         const u32 w = e.y;
-        bdelta[s] = owned_buckets(values, p, e.x, ent_z(w), ent_own(w));
+        bdelta[s] = owned_buckets<IMPLICIT>(values, p, e.x, ent_z(w), ent_own(w));
         if (!ent_cell(w) || ent_case(w) == 0u || ent_case(w) == 255u) {
             ntri[s] = 0;
             trimask[s] = 0;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
         nb[3 * s + 2] = lbXY;
 
         CellData c;
-        load_cell_values(values, p, r, z, c);
+        load_cell_values<IMPLICIT>(values, p, r, z, c);
         const u32 status = edge_mask_of_case(cs);
         u32 slot[12];
         cell_edge_slots(entries, s, z, lbY, lbX, lbXY, S, slot);
@@ -413,6 +415,7 @@ __device__ __forceinline__ void emit_candidate(bool has, u32 b, u32 id, u32 kxv,
     }
 }
 
+template <bool IMPLICIT>
 __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
                                                   const u32 *__restrict__ cand_info, const u32 *__restrict__ bdelta,
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             x = r / Y;
             y = r - x * Y;
             n = (i64) r * Z + z;
-            v0 = __ldg(values + n);
+            v0 = field_at<IMPLICIT>(values, p, n, 0, x, y, z);
             xg = x + (u32) p.g.x_off;
             bd = bdelta[s];
             px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             const bool has = um & 1u;
             u32 a = 0, b2 = 0, c = 0;
             if (has) {
-                const float t = edge_t(v0, __ldg(values + n + 1), p.level);
+                const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, 1, x, y, z + 1), p.level);
                 const float pz1 = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
                 a = float_key(lerp_ref(t, px0, px0));
                 b2 = float_key(lerp_ref(t, py0, py0));
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             const bool has = um & 2u;
             u32 a = 0, b2 = 0, c = 0;
             if (has) {
-                const float t = edge_t(v0, __ldg(values + n + Z), p.level);
+                const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, Z, x, y + 1, z), p.level);
                 const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
                 a = float_key(lerp_ref(t, px0, px0));
                 b2 = float_key(lerp_ref(t, py0, py1));
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             const bool has = um & 4u;
             u32 a = 0, b2 = 0, c = 0;
             if (has) {
-                const float t = edge_t(v0, __ldg(values + n + p.YZ), p.level);
+                const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, p.YZ, x + 1, y, z), p.level);
                 const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
                 a = float_key(lerp_ref(t, px0, px1));
                 b2 = float_key(lerp_ref(t, py0, py0));
@@ -546,6 +549,7 @@ int make_dense_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin,
     p.NQ = (u32) nq;
     p.R = (u32) (X * Y);
     p.level = level;
+    p.sdf = nullptr;
     p.emit_lo = (u32) (emit_lo < 0 ? 0 : emit_lo);
     p.emit_hi = (u32) (emit_hi < 0 ? 0 : emit_hi);
     // sort buckets: a layer holds ~ (2..8) * max(Y,Z) vertices and a bucket must stay below SEG_CAP = 4096 for
@@ -624,6 +628,11 @@ static int enqueue_zero(const McBuffers &b, cudaStream_t stream) {
 struct HaloSplit { i64 lo = 0, hi = 0; cudaEvent_t event = nullptr; };
 static int enqueue_signbits(const float *values, const DenseParams &p, const McBuffers &b, cudaStream_t stream, const HaloSplit &h = HaloSplit()) {
     const i64 plane = p.YZ;
+    if (p.sdf) {                       // implicit field: compute pass with Lipschitz culling, nothing to wait for
+        if (h.event) ISX_CUDA(cudaStreamWaitEvent(stream, h.event, 0));
+        launch_sdf_bits(p, b.bits, stream);
+        return OK;
+    }
     if (!h.event) {
         launch_signbits(values, b.bits, p.P, p.level, stream);
         return OK;
@@ -646,8 +655,12 @@ static void enqueue_compact(const DenseParams &p, const McBuffers &b, u32 cap, c
 static int enqueue_analysis(const float *values, const DenseParams &p, int method, const McBuffers &b, u32 cap, cudaStream_t stream) {
     const int sms = device_sms();
     const u32 nb = sort_buckets(p);
-    ISX_LAUNCH(k_cell_tris, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
-               b.trimask, b.used, b.bdelta);
+    if (p.sdf)
+        ISX_LAUNCH(k_cell_tris<true>, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+                   b.trimask, b.used, b.bdelta);
+    else
+        ISX_LAUNCH(k_cell_tris<false>, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+                   b.trimask, b.used, b.bdelta);
     ISX_LAUNCH(k_scan_entries, scan_blocks(sms), 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
                b.entries, b.bdelta, (u32) p.g.Y, sort_nsub(p), b.seg.count, nb, b.seg);
     ISX_CUDA(cudaGetLastError());
@@ -684,7 +697,10 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const u32 grid_n = device_counts ? cand_cap : host_nc;
     const CandOut co{s.kx, s.ky, s.kz, s.seg.perm0, s.seg.cbucket, b.seg.count, b.seg.start, b.seg.bigoff, b.seg.cursor,
                      s.seg.bkx, s.seg.bky, s.seg.bkz, s.seg.bid, b.seg.xinvmin, b.seg.xmax};
-    ISX_LAUNCH(k_cand_pos, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
+    if (p.sdf)
+        ISX_LAUNCH(k_cand_pos<true>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
+    else
+        ISX_LAUNCH(k_cand_pos<false>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg,
                           SegGeom{p.g.amin[0], p.g.asize[0], p.g.amin[1], p.g.asize[1], p.g.amin[2], p.g.asize[2], (u32) p.g.Xg, (u32) p.g.Y,
@@ -713,13 +729,14 @@ static int read_counters(const McBuffers &b, u32 *h, cudaStream_t stream) {
 int isoext_mc_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int64_t X_global,
                           const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                           int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries,
-                          void *stream_, int64_t *counts_out) {
+                          const void *sdf_program, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
-    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
+    if (!p.sdf && (reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
     if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
     Carver c(workspace);
     McBuffers b;
@@ -747,12 +764,13 @@ int isoext_mc_dense_emit(const float *values, int64_t X, int64_t Y, int64_t Z, i
                          const float *aabb_min, const float *aabb_max, float level, int method, int64_t emit_x_lo,
                          int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
                          size_t scratch_bytes, int64_t n_candidates, int64_t n_big, float x_lo_threshold, float x_hi_threshold,
-                         float *V, int32_t *F, void *stream_, int64_t *counts_out) {
+                         float *V, int32_t *F, const void *sdf_program, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
     Carver c(workspace);
     McBuffers b;
     if (carve_mc(c, p, (size_t) cap_entries, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
@@ -787,13 +805,14 @@ int isoext_mc_dense_run(const float *values, int64_t X, int64_t Y, int64_t Z, in
                         int64_t emit_x_hi, void *workspace, size_t workspace_bytes, int64_t cap_entries, void *scratch,
                         size_t scratch_bytes, int64_t cand_cap, int64_t tri_cap, int64_t big_cap, int radix, float x_lo_threshold,
                         float x_hi_threshold, int64_t halo_planes_lo, int64_t halo_planes_hi, void *halo_event, float *V, int32_t *F,
-                        void *stream_, int64_t *counts_out) {
+                        const void *sdf_program, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (method != 0 && method != 1) return fail(E_METHOD, "Unknown method");
     DenseParams p;
     int rc = make_dense_params(X, Y, Z, x_offset, X_global, aabb_min, aabb_max, level, emit_x_lo, emit_x_hi, &p);
     if (rc != OK) return rc;
-    if ((reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
+    p.sdf = static_cast<const SdfProg *>(sdf_program);
+    if (!p.sdf && (reinterpret_cast<uintptr_t>(values) & 31u) != 0) return fail(E_INVALID, "values must be 32-byte aligned");
     if (cap_entries < 1 || cap_entries >= ((i64) 1 << 29)) return fail(E_INVALID, "cap_entries out of range");
     if (cand_cap < 1 || cand_cap >= ((i64) 1 << 29) || tri_cap < 1) return fail(E_INVALID, "capacities out of range");
     Carver c(workspace);

@@ -59,15 +59,17 @@ class Intersection:
         return Intersection._make(**d)
 
 
-def its_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level: float, compute_normals: bool, ws, cap_hint=0,
-                  x_offset=0, x_global=None):
+def its_dense_raw(values, shape, aabb_min, aabb_max, level: float, compute_normals: bool, ws, cap_hint=0,
+                  x_offset=0, x_global=None, sdf_prog=None):
     """Intersections of a dense (X, Y, Z) float32 CUDA field (a whole grid, or the extended slab of a sharded grid:
     ``x_offset`` = global index of local plane 0, ``x_global`` = points along x of the whole grid).
     Returns ``(Intersection, entry capacity used)``."""
     lib = _lib.lib()
     X, Y, Z = shape
     xg = X if x_global is None else int(x_global)
-    dev = values.device
+    dev = values.device if values is not None else sdf_prog.device
+    vptr = values.data_ptr() if values is not None else None
+    sptr = sdf_prog.data_ptr() if sdf_prog is not None else None
     amin, amax = _lib.f3(aabb_min), _lib.f3(aabb_max)
     stream = _stream_ptr()
     counts = (C.c_int64 * 4)()
@@ -81,9 +83,9 @@ def its_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level: float,
         entries = torch.empty((cap + 1, 2), dtype=torch.int32, device=dev)
         cellslot = torch.empty(cap, dtype=torch.int32, device=dev)
         its_off = torch.empty(cap, dtype=torch.int32, device=dev)
-        rc = lib.isoext_its_dense_count(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), wsbuf.data_ptr(),
+        rc = lib.isoext_its_dense_count(vptr, X, Y, Z, x_offset, xg, amin, amax, float(level), wsbuf.data_ptr(),
                                         wsbuf.numel(), cap, entries.data_ptr(), row_start.data_ptr(), cellslot.data_ptr(),
-                                        its_off.data_ptr(), stream, counts)
+                                        its_off.data_ptr(), sptr, stream, counts)
         if rc == _lib.E_CAPACITY:
             cap = int(counts[0]) + 1024
             continue
@@ -96,10 +98,10 @@ def its_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level: float,
     isout = torch.empty(max(S, 1), dtype=torch.uint8, device=dev)
     cell_offsets = torch.zeros(n_cells + 1, dtype=torch.int32, device=dev)
     cell_indices = torch.empty(n_cells, dtype=torch.int64, device=dev)
-    _lib.check(lib.isoext_its_dense_emit(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level),
+    _lib.check(lib.isoext_its_dense_emit(vptr, X, Y, Z, x_offset, xg, amin, amax, float(level),
                                          int(bool(compute_normals)), entries.data_ptr(), S, cellslot.data_ptr(),
                                          its_off.data_ptr(), n_cells, n_its, points.data_ptr(), normals.data_ptr(),
-                                         isout.data_ptr(), cell_offsets.data_ptr(), cell_indices.data_ptr(), stream))
+                                         isout.data_ptr(), cell_offsets.data_ptr(), cell_indices.data_ptr(), sptr, stream))
     its = Intersection._make(kind="dense", shape=tuple(shape), aabb_min=aabb_min, aabb_max=aabb_max, level=float(level),
                              entries=entries, row_start=row_start, cellslot=cellslot, its_off=its_off, isout=isout,
                              n_entries=S, n_cells=n_cells, points=points, normals=normals, cell_offsets=cell_offsets,
@@ -107,16 +109,17 @@ def its_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level: float,
     return its, max(cap, S)
 
 
-def _its_dense(grid: UniformGrid, level: float, compute_normals: bool) -> Intersection:
+def _its_dense(grid, level: float, compute_normals: bool) -> Intersection:
     its, cap = its_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, compute_normals, grid._ws,
-                             cap_hint=grid._cap_hint)
+                             cap_hint=grid._cap_hint, sdf_prog=getattr(grid, "_prog", None))
     grid._cap_hint = cap
     return its
 
 
 def get_intersection(grid, level: float = 0.0, compute_normals: bool = False) -> Intersection:
     """Edge/iso-surface crossings of every active cell (src/isoext_ext.cu:329-343, src/its.cu:93-159)."""
-    if isinstance(grid, UniformGrid):
+    from .grid import ImplicitGrid
+    if isinstance(grid, (UniformGrid, ImplicitGrid)):
         with torch.cuda.device(grid.device):
             return _its_dense(grid, level, compute_normals)
     from .sparse import SparseGrid, its_sparse
@@ -125,12 +128,15 @@ def get_intersection(grid, level: float = 0.0, compute_normals: bool = False) ->
     raise TypeError("get_intersection: grid must be a UniformGrid or SparseGrid")
 
 
-def _normals_dense(grid: UniformGrid, its: Intersection) -> None:
+def _normals_dense(grid, its: Intersection) -> None:
     X, Y, Z = grid.shape
-    _lib.check(_lib.lib().isoext_its_dense_normals(grid._values.data_ptr(), X, Y, Z, its.x_offset, its.x_global, _lib.f3(grid.aabb_min),
+    prog = getattr(grid, "_prog", None)
+    _lib.check(_lib.lib().isoext_its_dense_normals(grid._values.data_ptr() if grid._values is not None else None, X, Y, Z,
+                                                   its.x_offset, its.x_global, _lib.f3(grid.aabb_min),
                                                    _lib.f3(grid.aabb_max), its.entries.data_ptr(), its.n_entries,
                                                    its.cellslot.data_ptr(), its.its_off.data_ptr(), its.points.data_ptr(),
-                                                   its.normals.data_ptr(), _stream_ptr()))
+                                                   its.normals.data_ptr(), prog.data_ptr() if prog is not None else None,
+                                                   _stream_ptr()))
     its._has_normals = True
 
 
@@ -190,7 +196,8 @@ def dual_contouring(grid, level: float = 0.0, intersection: Intersection | None 
     normals they are computed from the grid values (trilinear central differences).
     Deviation: quads with a neighbour cell outside the grid are skipped on the upper faces as well
     (the reference only checks the lower faces, include/utils.cuh:128-135, and reads out of bounds)."""
-    if isinstance(grid, UniformGrid):
+    from .grid import ImplicitGrid
+    if isinstance(grid, (UniformGrid, ImplicitGrid)):
         with torch.cuda.device(grid.device):
             its = intersection._copy() if intersection is not None else _its_dense(grid, level, True)
             if its.kind != "dense" or tuple(its.shape) != tuple(grid.shape):

@@ -145,3 +145,61 @@ class UniformGrid(Grid):
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().isoext_grid_cells_dense(X, Y, Z, int(wide), out.data_ptr(), _stream_ptr()))
         return out
+
+
+class ImplicitGrid(Grid):
+    """A uniform lattice whose values are an analytic SDF evaluated INSIDE the extraction kernels (extension,
+    SURVEY.md 8f-1): ``marching_cubes`` / ``get_intersection`` / ``dual_contouring`` accept it like a ``UniformGrid``,
+    but no (X, Y, Z) field is ever allocated, written or read -- where a kernel would load a value it evaluates the
+    compiled program (csrc/sdfprog.cuh) at the position ``get_points()`` reports for that point, and the volume pass
+    skips every 32-point word that the 1-Lipschitz bound proves to be far from the surface.
+
+    ``sdf``: a tree of the built-in classes of ``isoext_b200.sdf`` (``compile_sdf``).  ``materialize()`` returns the
+    equivalent ``UniformGrid`` (field written by the same device function): extracting that grid gives the same mesh
+    bit for bit -- the parity contract of the fused path."""
+
+    def __init__(self, shape, sdf, aabb_min=(-1.0, -1.0, -1.0), aabb_max=(1.0, 1.0, 1.0), device=None):
+        from .sdf import SdfProgram, compile_sdf
+        shape = [int(s) for s in shape]
+        if len(shape) != 3 or len(aabb_min) != 3 or len(aabb_max) != 3:
+            raise TypeError("shape, aabb_min and aabb_max must have three elements")
+        if min(shape) < 1:
+            raise RuntimeError("Grid shape must be positive")
+        self.shape = tuple(shape)
+        self.aabb_min = tuple(float(v) for v in aabb_min)
+        self.aabb_max = tuple(float(v) for v in aabb_max)
+        _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.program = sdf if isinstance(sdf, SdfProgram) else compile_sdf(sdf)
+        self._prog = self.program.device(self.device)
+        self._values = None
+        self._ws = _Workspace()
+        self._cap_hint = 0
+        self._hints = {}
+
+    def get_num_cells(self) -> int:
+        X, Y, Z = self.shape
+        return (X - 1) * (Y - 1) * (Z - 1)
+
+    def get_num_points(self) -> int:
+        X, Y, Z = self.shape
+        return X * Y * Z
+
+    get_points = UniformGrid.get_points
+
+    def eval_slab(self, x0: int, x1: int) -> torch.Tensor:
+        """(x1 - x0, Y, Z) float32 values of point planes [x0, x1) (kernel evaluation of the program)."""
+        X, Y, Z = self.shape
+        out = torch.empty((x1 - x0, Y, Z), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().isoext_sdf_eval_dense(self._prog.data_ptr(), x1 - x0, Y, Z, x0, X, _lib.f3(self.aabb_min),
+                                                        _lib.f3(self.aabb_max), out.data_ptr(), _stream_ptr()))
+        return out
+
+    def get_values(self) -> torch.Tensor:
+        return self.eval_slab(0, self.shape[0])
+
+    def materialize(self) -> UniformGrid:
+        g = UniformGrid(list(self.shape), self.aabb_min, self.aabb_max, device=self.device)
+        g._values = self.get_values()
+        return g

@@ -25,7 +25,7 @@ def _initial_cap(shape) -> int:
 
 
 def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_id, ws, cap_hint=0, x_offset=0,
-                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf), hints=None, halo=None):
+                 x_global=None, emit_range=None, x_thresholds=(-math.inf, math.inf), hints=None, halo=None, sdf_prog=None):
     """Run the dense pipeline on a (X,Y,Z) float32 CUDA tensor.
 
     Returns ``(V_own, F, n_lo, n_hi, cap_used)``: ``V_own`` the position-sorted welded vertices OWNED by
@@ -38,6 +38,9 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     With hints the single-call fast path (``isoext_mc_dense_run``: one stream sync, no host round trip
     between the phases) is tried first; any capacity miss falls back to count + emit.
 
+    ``sdf_prog``: device image of an analytic program (``sdf.SdfProgram.device``); ``values`` is then ``None`` and the
+    kernels evaluate the program instead of loading values (``grid.ImplicitGrid``).
+
     ``halo``: ``(planes_lo, planes_hi, event)`` -- the first / last x planes of ``values`` are still being written on
     another stream that records ``event`` (a ``torch.cuda.Event``) when done; the fast path starts streaming the planes
     in between at once (slab halo pull overlapped with the volume stream), every other path waits for the event first.
@@ -47,7 +50,9 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     xg = X if x_global is None else x_global
     lo, hi = (0, X - 1) if emit_range is None else emit_range
     amin, amax = _lib.f3(aabb_min), _lib.f3(aabb_max)
-    dev = values.device
+    dev = values.device if values is not None else sdf_prog.device
+    vptr = values.data_ptr() if values is not None else None
+    sptr = sdf_prog.data_ptr() if sdf_prog is not None else None
     stream = _stream_ptr()
     counts = (C.c_int64 * 8)()
     cap = max(int(cap_hint), _initial_cap(shape))
@@ -64,10 +69,10 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         F = torch.empty((tri_cap, 3), dtype=torch.int32, device=dev)
         h_lo, h_hi, h_ev = (0, 0, None) if halo is None else (int(halo[0]), int(halo[1]), halo[2].cuda_event)
         halo = None      # consumed: whatever follows this call runs behind the event
-        rc = lib.isoext_mc_dense_run(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
+        rc = lib.isoext_mc_dense_run(vptr, X, Y, Z, x_offset, xg, amin, amax, float(level), method_id, lo, hi,
                                      wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(), cand_cap, tri_cap,
                                      big_cap, 1 if hints.get("radix") else 0, thr_lo, thr_hi, h_lo, h_hi, h_ev, V.data_ptr(),
-                                     F.data_ptr(), stream, counts)
+                                     F.data_ptr(), sptr, stream, counts)
         hints["radix"] = int(counts[7]) > 0     # the sort's radix last resort is only enqueued when it was needed last time
         if rc == 0:
             S, T, Vc = int(counts[0]), int(counts[1]), int(counts[2])
@@ -88,8 +93,8 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         if nbytes == 0:
             raise RuntimeError(_lib.last_error())
         wsbuf = ws.get("mc_ws", nbytes, dev)
-        rc = lib.isoext_mc_dense_count(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
-                                       lo, hi, wsbuf.data_ptr(), wsbuf.numel(), cap, stream, counts)
+        rc = lib.isoext_mc_dense_count(vptr, X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
+                                       lo, hi, wsbuf.data_ptr(), wsbuf.numel(), cap, sptr, stream, counts)
         if rc == _lib.E_CAPACITY:
             cap = int(counts[0]) + 1024
             continue
@@ -105,9 +110,9 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
     F = torch.empty((T, 3), dtype=torch.int32, device=dev)
     out = (C.c_int64 * 4)()
-    _lib.check(lib.isoext_mc_dense_emit(values.data_ptr(), X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
+    _lib.check(lib.isoext_mc_dense_emit(vptr, X, Y, Z, x_offset, xg, amin, amax, float(level), method_id,
                                         lo, hi, wsbuf.data_ptr(), wsbuf.numel(), cap, scratch.data_ptr(), scratch.numel(),
-                                        Vc, n_big, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(),
+                                        Vc, n_big, thr_lo, thr_hi, V.data_ptr(), F.data_ptr(), sptr,
                                         stream, out))
     n_lo, n_hi = int(out[1]), int(out[2])
     return V[n_lo:n_hi], F, n_lo, n_hi, max(cap, S)
@@ -121,10 +126,11 @@ def marching_cubes(grid, level: float = 0.0, method: str = "nagae"):
     LUT order -- or ``(None, None)`` when no triangle exists (src/isoext_ext.cu:47-49).
     """
     mid = _method_id(method)
-    if isinstance(grid, UniformGrid):
+    from .grid import ImplicitGrid
+    if isinstance(grid, (UniformGrid, ImplicitGrid)):
         with torch.cuda.device(grid.device):
             v, f, _, _, cap = mc_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, mid, grid._ws,
-                                           cap_hint=grid._cap_hint, hints=grid._hints)
+                                           cap_hint=grid._cap_hint, hints=grid._hints, sdf_prog=getattr(grid, "_prog", None))
         grid._cap_hint = cap
         if f is None or f.shape[0] == 0:
             return None, None   # src/isoext_ext.cu:47-49: empty arrays become None

@@ -15,6 +15,7 @@ import torch.nn.functional as F
 __all__ = [
     "SDF", "SDFProtocol", "SphereSDF", "TorusSDF", "CuboidSDF", "UnionOp", "SmoothUnionOp",
     "IntersectionOp", "NegationOp", "TranslationOp", "RotationOp", "get_sdf_grad", "get_sdf_normal",
+    "compile_sdf", "SdfProgram",
 ]
 
 # Anything callable on a (..., 3) tensor returning (...) distances (src/isoext/sdf.py:8-21).
@@ -157,3 +158,95 @@ class RotationOp(SDF):
 
     def __call__(self, p):
         return self.sdf(p @ self.R.to(p))
+
+
+# ---- analytic programs for the fused path (extension; csrc/sdfprog.cuh) ----------------------------------------
+_OP = dict(END=0, RESET=1, TRANSLATE=2, ROTATE=3, SPHERE=4, TORUS=5, CUBOID=6, UNION=7, INTER=8, SMOOTH=9, NEG=10)
+_MAX_OPS, _MAX_CONSTS, _MAX_STACK = 240, 256, 12
+
+
+def _f32(x) -> float:
+    return float(torch.tensor(x, dtype=torch.float32))
+
+
+class SdfProgram:
+    """A tree of the built-in SDF classes compiled to the postfix program the extraction kernels interpret
+    (csrc/sdfprog.cuh).  ``blob`` is the host image of ``struct SdfProg``; ``device(dev)`` uploads it once per device.
+
+    Every leaf carries the chain of point transforms above it (outermost first, exactly the order in which the
+    torch expressions of this module apply them), combinators work on a small value stack.  Constants are the
+    float32 values the torch expressions use (e.g. ``size / 2`` of a cuboid and the rotation matrix are computed
+    with torch, in float32)."""
+
+    def __init__(self, ops: list, consts: list):
+        import struct
+        if len(ops) > _MAX_OPS or len(consts) > _MAX_CONSTS:
+            raise RuntimeError("SDF tree too large for a device program")
+        self.ops, self.consts = list(ops), list(consts)
+        self.blob = (struct.pack("<IIfI", len(ops), len(consts), 1.0 + 1e-3, 0) + bytes(ops) + bytes(_MAX_OPS - len(ops))
+                     + struct.pack(f"<{_MAX_CONSTS}f", *(list(consts) + [0.0] * (_MAX_CONSTS - len(consts)))))
+        self._dev = {}
+
+    def device(self, device) -> torch.Tensor:
+        device = torch.device(device)
+        t = self._dev.get(device)
+        if t is None:
+            from . import _lib
+            assert len(self.blob) == _lib.lib().isoext_sdf_program_bytes(), "SdfProg layout mismatch"
+            t = torch.frombuffer(bytearray(self.blob), dtype=torch.uint8).to(device)
+            self._dev[device] = t
+        return t
+
+
+def compile_sdf(sdf) -> SdfProgram:
+    """Compile a tree of SphereSDF / TorusSDF / CuboidSDF / UnionOp / SmoothUnionOp / IntersectionOp / NegationOp /
+    TranslationOp / RotationOp to an :class:`SdfProgram`.  Raises ``TypeError`` for anything else (arbitrary callables
+    cannot run inside a kernel: evaluate them with torch and use ``set_values``)."""
+    ops, consts = [], []
+    depth = [0, 0]   # current / maximum value-stack depth
+
+    def push():
+        depth[0] += 1
+        depth[1] = max(depth[1], depth[0])
+
+    def leaf_prefix(chain):
+        ops.append(_OP["RESET"])
+        for kind, data in chain:
+            ops.append(_OP[kind])
+            consts.extend(data)
+
+    def walk(node, chain):
+        if isinstance(node, SphereSDF):
+            leaf_prefix(chain); ops.append(_OP["SPHERE"]); consts.append(_f32(node.radius)); push()
+        elif isinstance(node, TorusSDF):
+            leaf_prefix(chain); ops.append(_OP["TORUS"]); consts.extend([_f32(node.R), _f32(node.r)]); push()
+        elif isinstance(node, CuboidSDF):
+            half = (torch.tensor(node.size, dtype=torch.float32) / 2).tolist()
+            if len(half) != 3:
+                raise TypeError("CuboidSDF.size must have three elements")
+            leaf_prefix(chain); ops.append(_OP["CUBOID"]); consts.extend(half); push()
+        elif isinstance(node, (UnionOp, IntersectionOp, SmoothUnionOp)):
+            kids = list(node.sdf_list)
+            if not 1 <= len(kids) <= _MAX_STACK - 2:
+                raise TypeError("combinators take between 1 and 10 children in a device program")
+            for k in kids:
+                walk(k, chain)
+            if isinstance(node, SmoothUnionOp):
+                ops.extend([_OP["SMOOTH"], len(kids)]); consts.append(_f32(node.k))
+            else:
+                ops.extend([_OP["UNION" if isinstance(node, UnionOp) else "INTER"], len(kids)])
+            depth[0] -= len(kids) - 1
+        elif isinstance(node, NegationOp):
+            walk(node.sdf, chain); ops.append(_OP["NEG"])
+        elif isinstance(node, TranslationOp):
+            off = torch.tensor(node.offset).to(torch.float32).tolist()
+            walk(node.sdf, chain + [("TRANSLATE", off)])
+        elif isinstance(node, RotationOp):
+            walk(node.sdf, chain + [("ROTATE", node.R.to(torch.float32).reshape(-1).tolist())])
+        else:
+            raise TypeError(f"compile_sdf: {type(node).__name__} is not one of the built-in SDF classes")
+
+    walk(sdf, [])
+    if depth[1] > _MAX_STACK:
+        raise RuntimeError("SDF tree too deep for a device program")
+    return SdfProgram(ops, consts)

@@ -164,28 +164,39 @@ class SparseGrid(Grid):
         (tests/conftest.py:39-61 of the reference: potential ids -> points -> sdf -> filter -> add_cells -> set_values)
         in one pass over the field instead of a Python loop over chunks.
 
-        ``values``: a UniformGrid of the same shape and AABB, or an (X, Y, Z) float32 CUDA tensor.  ``x_chunk``: planes
-        per pass (default: all); chunks bound the sign-bit workspace for very large fields."""
+        ``values``: a UniformGrid of the same shape and AABB, an (X, Y, Z) float32 CUDA tensor, or an ``ImplicitGrid``
+        (analytic SDF evaluated in the kernels: nothing of size X*Y*Z floats is ever allocated, which is what makes a
+        4096^3-equivalent band possible).  ``x_chunk``: planes per pass (default: all); chunks bound the sign-bit
+        workspace (X*Y*Z/8 bytes unchunked) for very large grids."""
         from .dc import its_dense_raw
-        from .grid import UniformGrid
-        vals = values._values if isinstance(values, UniformGrid) else values
-        _expect_cuda(vals, torch.float32, ndim=3, what="values")
-        if tuple(vals.shape) != self.shape:
-            raise RuntimeError("Cannot set values with different shapes")
+        from .grid import ImplicitGrid, UniformGrid
+        prog = None
+        if isinstance(values, ImplicitGrid):
+            if values.shape != self.shape or values.aabb_min != self.aabb_min or values.aabb_max != self.aabb_max:
+                raise RuntimeError("Cannot set values with different shapes")
+            vals, prog = None, values.program.device(self.device)
+        else:
+            vals = values._values if isinstance(values, UniformGrid) else values
+            _expect_cuda(vals, torch.float32, ndim=3, what="values")
+            if tuple(vals.shape) != self.shape:
+                raise RuntimeError("Cannot set values with different shapes")
         lib = _lib.lib()
         X, Y, Z = self.shape
+        amin, amax = _lib.f3(self.aabb_min), _lib.f3(self.aabb_max)
         step = X if not x_chunk else max(2, int(x_chunk))
         cells, vals8 = [], []
         with torch.cuda.device(self.device):
             for x0 in range(0, X - 1, step - 1 if step < X else X):
                 x1 = min(X, x0 + step)                      # planes [x0, x1): cell layers [x0, x1 - 1)
-                sub = vals[x0:x1]
-                its, _ = its_dense_raw(sub, (x1 - x0, Y, Z), self.aabb_min, self.aabb_max, level, False, self._ws, x_offset=x0, x_global=X)
+                sub = vals[x0:x1] if vals is not None else None
+                its, _ = its_dense_raw(sub, (x1 - x0, Y, Z), self.aabb_min, self.aabb_max, level, False, self._ws, x_offset=x0,
+                                       x_global=X, sdf_prog=prog)
                 n = its.n_cells
                 ci = torch.empty(n, dtype=torch.int64, device=self.device)
                 v8 = torch.empty((n, 8), dtype=torch.float32, device=self.device)
-                _lib.check(lib.isoext_band_from_dense_emit(sub.data_ptr(), x1 - x0, Y, Z, x0, X, its.entries.data_ptr(), its.n_entries,
-                                                           its.cellslot.data_ptr(), ci.data_ptr(), v8.data_ptr(), _stream_ptr()))
+                _lib.check(lib.isoext_band_from_dense_emit(sub.data_ptr() if sub is not None else None, x1 - x0, Y, Z, x0, X, amin, amax,
+                                                           its.entries.data_ptr(), its.n_entries, its.cellslot.data_ptr(), ci.data_ptr(),
+                                                           v8.data_ptr(), prog.data_ptr() if prog is not None else None, _stream_ptr()))
                 cells.append(ci); vals8.append(v8)
                 if x1 >= X:
                     break
