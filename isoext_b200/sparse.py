@@ -189,6 +189,8 @@ class SparseGrid(Grid):
             for x0 in range(0, X - 1, step - 1 if step < X else X):
                 x1 = min(X, x0 + step)                      # planes [x0, x1): cell layers [x0, x1 - 1)
                 sub = vals[x0:x1] if vals is not None else None
+                if sub is not None and sub.data_ptr() % 32:      # the volume stream reads 256-bit words
+                    sub = sub.clone()
                 its, _ = its_dense_raw(sub, (x1 - x0, Y, Z), self.aabb_min, self.aabb_max, level, False, self._ws, x_offset=x0,
                                        x_global=X, sdf_prog=prog)
                 n = its.n_cells
