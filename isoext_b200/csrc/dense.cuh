@@ -197,43 +197,78 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
 // (> 95 % of the words of a typical volume).  Otherwise (and for words straddling two rows) the points are evaluated.
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__restrict__ bits) {
+    // Two phases per block of 256 consecutive words.  Phase 1, thread per word: one evaluation at the middle of the
+    // word decides it if the surface is provably farther than half a word (1-Lipschitz bound + float margin);
+    // undecided words go to a shared list.  Phase 2, warp per listed word: the 32 lanes evaluate the 32 points at
+    // once and a ballot assembles the word (a thread-per-word loop over 32 evaluations left 31 lanes of most warps
+    // idle: 2.2 ms instead of 0.x ms at 1024^3).
+    __shared__ u32 s_n;
+    __shared__ u32 s_list[256];
     const i64 P = p.P, nwords = (P + 31) >> 5;
+    const i64 nall = (i64) (((P >> 7) + 2) << 2);             // = signbits_words(P): the array is zero-padded to here
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
     const u32 resx = (u32) p.g.Xg - 1, resy = Y - 1, resz = Z - 1;
-    const i64 nall = (i64) (((P >> 7) + 2) << 2);             // = signbits_words(P): the array is zero-padded to here
-    for (i64 w = (i64) blockIdx.x * blockDim.x + threadIdx.x; w < nall; w += (i64) gridDim.x * blockDim.x) {
-        if (w >= nwords) { bits[w] = 0u; continue; }          // padding words (readers may over-fetch, see signbits_tail)
-        const i64 n0 = w << 5;
-        const u32 z0 = (u32) (n0 % Z);
-        const i64 r = n0 / Z;
-        const u32 y = (u32) (r % Y), x = (u32) (r / Y);
-        u32 word = 0;
-        if (z0 + 32u <= Z) {
-            const float fx = axis_pos(x + (u32) p.g.x_off, resx, p.g.amin[0], p.g.asize[0]), fy = axis_pos(y, resy, p.g.amin[1], p.g.asize[1]);
-            const float za = axis_pos(z0, resz, p.g.amin[2], p.g.asize[2]), zb = axis_pos(z0 + 31u, resz, p.g.amin[2], p.g.asize[2]);
-            const float mid = 0.5f * (za + zb), half = 0.5f * fabsf(zb - za);
-            const float fm = sdf_eval(p.sdf, fx, fy, mid);
-            const float d = fabsf(fm - p.level);
-            // margin: evaluation error of f (a few ulp of its operands' magnitude) and of the positions
-            const float margin = 1e-4f * (1.0f + fabsf(fm) + fabsf(p.level) + fabsf(fx) + fabsf(fy) + fabsf(mid));
-            if (d > p.sdf->lipschitz * half + margin) {
-                word = (__fsub_rn(fm, p.level) < 0.0f) ? 0xffffffffu : 0u;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rows made of whole words (Z % 32 == 0, nwords < 2^32): 32-bit index arithmetic, one division per word
+    const bool aligned = (Z & 31u) == 0u && nwords < ((i64) 1 << 32);
+    const u32 wpr = Z >> 5;
+    for (i64 base = (i64) blockIdx.x * 256; base < nall; base += (i64) gridDim.x * 256) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const i64 w = base + threadIdx.x;
+        if (w < nall) {
+            if (w >= nwords) {
+                bits[w] = 0u;                                  // padding words (readers may over-fetch, see signbits_tail)
             } else {
-                for (u32 k = 0; k < 32u; k++) {
-                    const float v = sdf_eval(p.sdf, fx, fy, axis_pos(z0 + k, resz, p.g.amin[2], p.g.asize[2]));
-                    word |= (u32) (__fsub_rn(v, p.level) < 0.0f) << k;
+                u32 x, y, z0;
+                bool inrow;
+                if (aligned) {
+                    const u32 r = (u32) w / wpr;
+                    z0 = ((u32) w - r * wpr) << 5;
+                    x = r / Y; y = r - x * Y;
+                    inrow = true;
+                } else {
+                    const i64 n0 = w << 5, r = n0 / Z;
+                    z0 = (u32) (n0 - r * Z);
+                    y = (u32) (r % Y); x = (u32) (r / Y);
+                    inrow = z0 + 32u <= Z;
                 }
-            }
-        } else {
-            for (u32 k = 0; k < 32u && n0 + k < P; k++) {
-                const i64 n = n0 + k;
-                const u32 zz = (u32) (n % Z);
-                const i64 rr = n / Z;
-                const float v = field_value<true>(nullptr, p, (u32) (rr / Y), (u32) (rr % Y), zz);
-                word |= (u32) (__fsub_rn(v, p.level) < 0.0f) << k;
+                bool decided = false;
+                if (inrow) {                                   // the word lies in one row
+                    const float fx = axis_pos(x + (u32) p.g.x_off, resx, p.g.amin[0], p.g.asize[0]), fy = axis_pos(y, resy, p.g.amin[1], p.g.asize[1]);
+                    const float za = axis_pos(z0, resz, p.g.amin[2], p.g.asize[2]), zb = axis_pos(z0 + 31u, resz, p.g.amin[2], p.g.asize[2]);
+                    const float mid = 0.5f * (za + zb), half = 0.5f * fabsf(zb - za);
+                    const float fm = sdf_eval(p.sdf, fx, fy, mid);
+                    // margin: evaluation error of f (a few ulp of its operands' magnitude) and of the positions
+                    const float margin = 1e-4f * (1.0f + fabsf(fm) + fabsf(p.level) + fabsf(fx) + fabsf(fy) + fabsf(mid));
+                    if (fabsf(fm - p.level) > p.sdf->lipschitz * half + margin) {
+                        bits[w] = (__fsub_rn(fm, p.level) < 0.0f) ? 0xffffffffu : 0u;
+                        decided = true;
+                    }
+                }
+                if (!decided) s_list[atomicAdd(&s_n, 1u)] = threadIdx.x;
             }
         }
-        bits[w] = word;
+        __syncthreads();
+        const u32 nlist = s_n;
+        for (u32 i = warp; i < nlist; i += 8) {
+            const i64 ww = base + s_list[i];
+            bool neg = false;
+            if (aligned) {
+                const u32 r = (u32) ww / wpr;
+                const u32 z0 = ((u32) ww - r * wpr) << 5, x = r / Y, y = r - x * Y;
+                neg = __fsub_rn(field_value<true>(nullptr, p, x, y, z0 + lane), p.level) < 0.0f;
+            } else {
+                const i64 n = (ww << 5) + lane;
+                if (n < P) {
+                    const i64 rr = n / Z;
+                    neg = __fsub_rn(field_value<true>(nullptr, p, (u32) (rr / Y), (u32) (rr % Y), (u32) (n - rr * Z)), p.level) < 0.0f;
+                }
+            }
+            const u32 word = __ballot_sync(0xffffffffu, neg);
+            if (lane == 0) bits[ww] = word;
+        }
+        __syncthreads();
     }
 }
 
@@ -274,7 +309,7 @@ static inline size_t signbits_words(i64 P) { return (size_t) (((P >> 7) + 2) << 
 static inline void launch_sdf_bits(const DenseParams &p, u32 *bits, cudaStream_t stream) {
     const i64 nwords = (i64) signbits_words(p.P);
     i64 want = (nwords + 255) / 256;
-    const i64 cap = (i64) device_sms() * 32;
+    const i64 cap = (i64) device_sms() * 64;
     stream_timer_mark(stream);
     ISX_LAUNCH(k_sdf_bits, (int) (want > cap ? cap : want), 256, 0, stream, p, bits);
     stream_timer_mark(stream);
