@@ -77,7 +77,9 @@ class UniformGrid(Grid):
     (src/grid/uniform.cu:8-20; 64^3 -> 250,047 cells / 262,144 points).
 
     Extension over the reference: grids with more than INT_MAX points are accepted (the reference
-    throws, src/grid/uniform.cu:13-17) as long as X*Y*ceil(Z/32) < 2^31 and Z <= 65535.
+    throws, src/grid/uniform.cu:13-17).  Limits of one extraction call: Z <= 65,535 points along the last axis,
+    X*Y < 2^31 rows, X*Y*ceil(Z/32) < 2^31, fewer than 2^29 surface entries and vertex candidates; the field
+    storage must be 32-byte aligned (torch allocations are).  Larger grids: ``isoext_b200.dist.SlabGrid``.
     """
 
     def __init__(self, shape, aabb_min=(-1.0, -1.0, -1.0), aabb_max=(1.0, 1.0, 1.0), default_value=FLT_MAX,
