@@ -194,8 +194,13 @@ def dual_contouring(grid, level: float = 0.0, intersection: Intersection | None 
     Returns ``(v, f)``: (V, 3) float32 in lexicographic position order and (2Q, 3) int32, or
     ``(None, None)`` if there is no quad.  A passed ``intersection`` is not modified; if it carries no
     normals they are computed from the grid values (trilinear central differences).
-    Deviation: quads with a neighbour cell outside the grid are skipped on the upper faces as well
-    (the reference only checks the lower faces, include/utils.cuh:128-135, and reads out of bounds)."""
+    Deviations: (1) quads with a neighbour cell outside the grid are skipped on the upper faces as well (the
+    reference only checks the lower faces, include/utils.cuh:128-135, and reads out of bounds).  (2) On a SparseGrid
+    whose neighbouring cells carry INCONSISTENT values for a shared corner (``set_values`` allows it), the existence
+    and orientation of the quad of an edge are taken from the cell whose corner 0 is the edge origin; the reference
+    collects the sign-change edges of all cells around the edge and takes ``is_out`` from the first in sorted order
+    (src/its.cu get_its_op + src/grid/sparse.cu:181-246).  With consistent values -- every field sampled from one
+    function -- the two are identical (tested); marching cubes welds by position and has no such caveat."""
     from .grid import ImplicitGrid
     if isinstance(grid, (UniformGrid, ImplicitGrid)):
         with torch.cuda.device(grid.device):

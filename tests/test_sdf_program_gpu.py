@@ -101,6 +101,10 @@ def test_populate_4096_equivalent_band_from_sdf(iso):
     v, f = iso.marching_cubes(g)
     assert len(v) == 38720856 and len(f) == 77441708
     assert float((v[::97].double().norm(dim=-1) - 0.7).abs().max()) < 1e-5
+    del v, f
+    dv, df = iso.dual_contouring(g)                      # one dual vertex per band cell, two triangles per sign-change edge
+    assert len(dv) == 38720858 and len(df) == 77441712
+    assert float((dv[::97].double().norm(dim=-1) - 0.7).abs().max()) < 2e-4
 
 
 def test_compile_sdf_rejects_arbitrary_callables(iso):
