@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
         const u32 lbY = row_lower_bound(entries, row_start[r + 1], row_start[r + 2], z);
         const u32 lbX = row_lower_bound(entries, row_start[r + Y], row_start[r + Y + 1], z);
         const u32 lbXY = row_lower_bound(entries, row_start[r + Y + 1], row_start[r + Y + 2], z);
-        nb[3 * s + 0] = lbY;
-        nb[3 * s + 1] = lbX;
-        nb[3 * s + 2] = lbXY;
+        nb[s] = lbY;                    // structure of arrays (three planes of `cap` entries): coalesced 4-byte accesses
+        nb[cap + s] = lbX;
+        nb[2 * (size_t) cap + s] = lbXY;
 
         CellData c;
         load_cell_values<IMPLICIT>(values, p, r, z, c);
@@ -497,31 +497,47 @@ __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, c
                                                     const unsigned char *__restrict__ trimask, const u32 *__restrict__ tri_off,
                                                     const u32 *__restrict__ cand_info, const u32 *__restrict__ cand_rank,
                                                     int *__restrict__ F, u32 cand_cap, u32 tri_cap, u32 entry_cap) {
+    // The triangles of 128 consecutive entries are consecutive in F (tri_off is the exclusive scan in entry order):
+    // they are assembled in shared memory and copied out with coalesced stores instead of 3..15 scalar stores per thread.
+    __shared__ int sF[128 * 15];
+    __shared__ u32 s_first, s_end;
     const u32 S = counters[C_S];
     if (S > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap || counters[C_ABORT]) return;
-    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-        const u32 mask = trimask[s];
-        if (!mask) continue;
-        const uint2 e = entries[s];
-        const u32 z = ent_z(e.y), cs = ent_case(e.y);
-        u32 slot[12];
-        cell_edge_slots(entries, s, z, nb[3 * s], nb[3 * s + 1], nb[3 * s + 2], S, slot);
-        const u64 word = tri_word(method, cs);
-        const u32 nt = (u32) (word >> 60);
-        size_t o = 3 * (size_t) tri_off[s];
-        for (u32 k = 0; k < nt; k++) {
-            if (!((mask >> k) & 1u)) continue;
+    for (u32 base = blockIdx.x * 128u; base < S; base += gridDim.x * 128u) {   // block-uniform loop
+        const u32 s = base + threadIdx.x;
+        const bool in = s < S;
+        const u32 mask = in ? trimask[s] : 0u;
+        const u32 toff = in ? tri_off[s] : 0u;
+        if (threadIdx.x == 0) s_first = toff;
+        if (s == min(base + 127u, S - 1u)) s_end = toff + __popc(mask);
+        __syncthreads();
+        const u32 first = s_first, total = s_end - first;
+        if (mask) {
+            const uint2 e = entries[s];
+            const u32 z = ent_z(e.y), cs = ent_case(e.y);
+            u32 slot[12];
+            cell_edge_slots(entries, s, z, nb[s], nb[entry_cap + s], nb[2 * (size_t) entry_cap + s], S, slot);
+            const u64 word = tri_word(method, cs);
+            const u32 nt = (u32) (word >> 60);
+            u32 o = 3 * (toff - first);
+            for (u32 k = 0; k < nt; k++) {
+                if (!((mask >> k) & 1u)) continue;
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const u32 edge = (u32) (word >> (12 * k + 4 * j)) & 15u;
-                const u32 sl = slot[edge];
-                const u32 ent = sl / 3, axis = sl - 3 * ent;
-                const u32 ci = cand_info[ent];
-                const u32 cand = (ci & 0x1fffffffu) + __popc((ci >> 29) & ((1u << axis) - 1u));
-                F[o + j] = (int) cand_rank[cand];
+                for (int j = 0; j < 3; j++) {
+                    const u32 edge = (u32) (word >> (12 * k + 4 * j)) & 15u;
+                    const u32 sl = slot[edge];
+                    const u32 ent = sl / 3, axis = sl - 3 * ent;
+                    const u32 ci = cand_info[ent];
+                    const u32 cand = (ci & 0x1fffffffu) + __popc((ci >> 29) & ((1u << axis) - 1u));
+                    sF[o + j] = (int) cand_rank[cand];
+                }
+                o += 3;
             }
-            o += 3;
         }
+        __syncthreads();
+        int *dst = F + 3 * (size_t) first;
+        for (u32 i = threadIdx.x; i < 3 * total; i += 128u) dst[i] = sF[i];
+        __syncthreads();
     }
 }
 
