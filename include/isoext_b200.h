@@ -192,7 +192,7 @@ int isoext_vertex_layer_histogram(const float *V, int64_t n, float aabb_min_x, f
                                   uint32_t *d_hist, void *stream);
 /* marching_cubes on a SparseGrid: phase 1 counts_out[0..1] = T, Vc; phase 2 counts_out[0] = V */
 size_t isoext_mc_sparse_workspace_bytes(int64_t n);
-size_t isoext_sparse_scratch_bytes(int64_t n_candidates);
+size_t isoext_sparse_scratch_bytes(int64_t n_candidates, int64_t X, int64_t Y);
 /* Slab support (the sorted cell list is partitioned by x layer): only the cells [emit_begin, emit_end) of
  * the list emit triangles (0 .. n on one GPU); the vertices of ALL cells are welded, and the emit phase returns
  * counts_out = {V, # with x < x_lo_threshold, # with x < x_hi_threshold} (ownership by position). */
@@ -214,7 +214,7 @@ int isoext_its_sparse_emit(const float *values8, const int64_t *cell_idx, int64_
                            float *normals, uint32_t *cell_offsets, int64_t *cell_indices, void *stream);
 /* dual_contouring on a SparseGrid: neighbour cells by binary search in cell_idx (replaces the dense
  * X*Y*Z idx_map of src/grid/sparse.cu:223-243).  Phase 1 counts_out[0..1] = Q, Vc; phase 2 [0] = V. */
-size_t isoext_dc_sparse_workspace_bytes(int64_t n);
+size_t isoext_dc_sparse_workspace_bytes(int64_t n, int64_t X);
 int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
                            const float *aabb_min, const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot,
                            const uint32_t *its_off, const float *points, const float *normals, float reg, float svd_tol,

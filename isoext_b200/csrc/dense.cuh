@@ -41,6 +41,21 @@ enum Counter : int {
     C_COUNT = 20
 };
 
+// Single-sync paths: the kernels behind the sort decide for themselves whether its output is complete (they do nothing
+// otherwise and the host falls back): a capacity was exceeded, there are more candidates in oversized buckets than the
+// second bucket level was sized for, or the radix last resort was needed but not enqueued.
+struct Gate {
+    u32 entry_cap = 0xffffffffu, cand_cap = 0xffffffffu, tri_cap = 0xffffffffu, big_cap = 0xffffffffu;
+    int allow_radix = 1;
+    int on = 0;
+};
+__device__ __forceinline__ bool gate_bad(const u32 *__restrict__ counters, const Gate &g) {
+    if (counters[C_ABORT]) return true;
+    if (!g.on) return false;
+    return counters[C_S] > g.entry_cap || counters[C_VC] > g.cand_cap || counters[C_T] > g.tri_cap || counters[C_NBIG] > g.big_cap ||
+           (counters[C_RADIX] > 0u && !g.allow_radix);
+}
+
 struct DenseParams {
     Geom g;
     i64 P;       // X*Y*Z

@@ -380,41 +380,7 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
 // ---------------------------------------------------------------------------------------------
 // K5: positions (as sortable keys) of the used edge slots, computed once by the owning entry.
 // ---------------------------------------------------------------------------------------------
-// Where the candidates go: straight to their place in the bucket-grouped arrays of the segmented sort (the bucket
-// offsets were scanned in phase 1), so no separate scatter pass and the sort reads its keys contiguously.  Elements of
-// oversized buckets go to the compacted big list instead and feed the x range of their bucket (segsort.cuh).
-struct CandOut {
-    u32 *gkx, *gky, *gkz, *gid;        // grouped by bucket: keys + candidate id
-    u32 *cbucket;                      // bucket of every candidate (candidate order)
-    const u32 *count, *start, *bigoff;
-    u32 *cursor;
-    u32 *bkx, *bky, *bkz, *bid, *xinvmin, *xmax;
-};
-// executed by all 32 lanes; `has` = this lane emits a candidate
-__device__ __forceinline__ void emit_candidate(bool has, u32 b, u32 id, u32 kxv, u32 kyv, u32 kzv, const CandOut &o) {
-    const u32 lane = threadIdx.x & 31;
-    const u32 act = __ballot_sync(0xffffffffu, has);
-    if (!has) return;
-    const u32 peers = __match_any_sync(act, b);
-    const u32 leader = __ffs(peers) - 1;
-    u32 off = 0;
-    if (lane == leader) off = atomicAdd(&o.cursor[b], (u32) __popc(peers));
-    off = __shfl_sync(peers, off, leader) + __popc(peers & ((1u << lane) - 1u));
-    o.cbucket[id] = b;
-    if (o.count[b] > (u32) SEG_CAP) {
-        const u32 q = o.bigoff[b] + off;
-        o.bkx[q] = kxv; o.bky[q] = kyv; o.bkz[q] = kzv; o.bid[q] = id;
-        const u32 mx = __reduce_max_sync(peers, kxv), mn = __reduce_max_sync(peers, ~kxv);
-        if (lane == leader) {
-            atomicMax(&o.xmax[b], mx);
-            atomicMax(&o.xinvmin[b], mn);
-        }
-    } else {
-        const u32 q = o.start[b] + off;
-        o.gkx[q] = kxv; o.gky[q] = kyv; o.gkz[q] = kzv; o.gid[q] = id;
-    }
-}
-
+// (CandOut / emit_candidate: segsort.cuh)
 template <bool IMPLICIT>
 __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
@@ -491,53 +457,38 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
 
 // ---------------------------------------------------------------------------------------------
 // K7: faces.  One thread per emitting cell; triangle k of the LUT row goes to tri_off[s] + (#kept before k).
+// (Assembling the triangles of 128 entries in shared memory for coalesced stores was measured slower: 56 vs 48 us at 1024^3.)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, const uint2 *__restrict__ entries,
                                                     const u32 *__restrict__ counters, const u32 *__restrict__ nb,
                                                     const unsigned char *__restrict__ trimask, const u32 *__restrict__ tri_off,
                                                     const u32 *__restrict__ cand_info, const u32 *__restrict__ cand_rank,
-                                                    int *__restrict__ F, u32 cand_cap, u32 tri_cap, u32 entry_cap) {
-    // The triangles of 128 consecutive entries are consecutive in F (tri_off is the exclusive scan in entry order):
-    // they are assembled in shared memory and copied out with coalesced stores instead of 3..15 scalar stores per thread.
-    __shared__ int sF[128 * 15];
-    __shared__ u32 s_first, s_end;
+                                                    int *__restrict__ F, u32 entry_cap, Gate gate) {
     const u32 S = counters[C_S];
-    if (S > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap || counters[C_ABORT]) return;
-    for (u32 base = blockIdx.x * 128u; base < S; base += gridDim.x * 128u) {   // block-uniform loop
-        const u32 s = base + threadIdx.x;
-        const bool in = s < S;
-        const u32 mask = in ? trimask[s] : 0u;
-        const u32 toff = in ? tri_off[s] : 0u;
-        if (threadIdx.x == 0) s_first = toff;
-        if (s == min(base + 127u, S - 1u)) s_end = toff + __popc(mask);
-        __syncthreads();
-        const u32 first = s_first, total = s_end - first;
-        if (mask) {
-            const uint2 e = entries[s];
-            const u32 z = ent_z(e.y), cs = ent_case(e.y);
-            u32 slot[12];
-            cell_edge_slots(entries, s, z, nb[s], nb[entry_cap + s], nb[2 * (size_t) entry_cap + s], S, slot);
-            const u64 word = tri_word(method, cs);
-            const u32 nt = (u32) (word >> 60);
-            u32 o = 3 * (toff - first);
-            for (u32 k = 0; k < nt; k++) {
-                if (!((mask >> k) & 1u)) continue;
+    if (S > entry_cap || gate_bad(counters, gate)) return;
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const u32 mask = trimask[s];
+        if (!mask) continue;
+        const uint2 e = entries[s];
+        const u32 z = ent_z(e.y), cs = ent_case(e.y);
+        u32 slot[12];
+        cell_edge_slots(entries, s, z, nb[s], nb[entry_cap + s], nb[2 * (size_t) entry_cap + s], S, slot);
+        const u64 word = tri_word(method, cs);
+        const u32 nt = (u32) (word >> 60);
+        size_t o = 3 * (size_t) tri_off[s];
+        for (u32 k = 0; k < nt; k++) {
+            if (!((mask >> k) & 1u)) continue;
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const u32 edge = (u32) (word >> (12 * k + 4 * j)) & 15u;
-                    const u32 sl = slot[edge];
-                    const u32 ent = sl / 3, axis = sl - 3 * ent;
-                    const u32 ci = cand_info[ent];
-                    const u32 cand = (ci & 0x1fffffffu) + __popc((ci >> 29) & ((1u << axis) - 1u));
-                    sF[o + j] = (int) cand_rank[cand];
-                }
-                o += 3;
+            for (int j = 0; j < 3; j++) {
+                const u32 edge = (u32) (word >> (12 * k + 4 * j)) & 15u;
+                const u32 sl = slot[edge];
+                const u32 ent = sl / 3, axis = sl - 3 * ent;
+                const u32 ci = cand_info[ent];
+                const u32 cand = (ci & 0x1fffffffu) + __popc((ci >> 29) & ((1u << axis) - 1u));
+                F[o + j] = (int) cand_rank[cand];
             }
+            o += 3;
         }
-        __syncthreads();
-        int *dst = F + 3 * (size_t) first;
-        for (u32 i = threadIdx.x; i < 3 * total; i += 128u) dst[i] = sF[i];
-        __syncthreads();
     }
 }
 
@@ -692,16 +643,6 @@ static int enqueue_phase1(const float *values, const DenseParams &p, int method,
     return enqueue_analysis(values, p, method, b, cap, stream);
 }
 
-// Single-call path: after the sort was enqueued, decide on the device whether its output is complete.  It is not if
-// a capacity was exceeded, if there are candidates in oversized buckets beyond what the second bucket level was
-// sized for (big_cap; 0 = not enqueued), or if the radix last resort was needed but not enqueued.  The weld and
-// face kernels then do nothing and the host falls back to count + emit (same conditions as in isoext_mc_dense_run).
-__global__ void k_phase2_gate(u32 *__restrict__ counters, u32 entry_cap, u32 cand_cap, u32 tri_cap, u32 big_cap, int allow_radix) {
-    const bool bad = counters[C_S] > entry_cap || counters[C_VC] > cand_cap || counters[C_T] > tri_cap ||
-                     counters[C_NBIG] > big_cap || (counters[C_RADIX] > 0u && !allow_radix);
-    counters[C_ABORT] = bad ? 1u : 0u;
-}
-
 // host_nc: number of candidates if the host knows it (two-phase path), else 0 with device_counts = true:
 // the kernels then read the counts from the counter block and do nothing if a capacity is exceeded.
 static int enqueue_phase2(const float *values, const DenseParams &p, int method, const McBuffers &b, const McScratch &s,
@@ -723,13 +664,18 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
                                   (u32) p.g.Z, p.g.x_off, p.gy, p.gx, p.ystep,
                                   p.ystep + 2 <= (u32) SEG_GROUPS && !getenv("ISX_SORT_NO_GROUPS")},
                           allow_radix, b.counters + C_RADIX, stream));
-    if (device_counts)
-        ISX_LAUNCH(k_phase2_gate, 1, 1, 0, stream, b.counters, entry_cap, cand_cap, tri_cap, big_cap, allow_radix ? 1 : 0);
+    // single-sync path: the weld and face kernels check the capacities / sort completeness themselves (dense.cuh: Gate)
+    Gate gate;
+    if (device_counts) {
+        gate.entry_cap = entry_cap; gate.cand_cap = cand_cap; gate.tri_cap = tri_cap; gate.big_cap = big_cap;
+        gate.allow_radix = allow_radix ? 1 : 0;
+        gate.on = 1;
+    }
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
-               b.descV, klo, khi, n_dev, cand_cap, true);
+               b.descV, klo, khi, n_dev, cand_cap, true, gate);
     ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
-               s.cand_rank, F, cand_cap, tri_cap, entry_cap);
+               s.cand_rank, F, entry_cap, gate);
     ISX_CUDA(cudaGetLastError());
     return OK;
 }

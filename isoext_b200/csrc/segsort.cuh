@@ -21,6 +21,7 @@
 // 4 launches instead of 14 in the common case.
 #pragma once
 #include "common.cuh"
+#include "dense.cuh"   // Counter
 #include "radix.cuh"
 
 namespace isx {
@@ -304,17 +305,37 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
         __syncthreads();
         u32 cur = 0;
         bool grouped = false;
-        if (!LEVEL2 && geom.grouped && b >= geom.gy + geom.gx) {   // (layer 0 = below the first plane: radix passes)
+        // Group stage: first-level buckets of a grid layer, and second-level pieces whose keys all share x (the cut of an
+        // axis-aligned face by y plane: k_big_sub) -- there the y-plane index relative to the piece's lowest y is the index.
+        bool piece_const_x = false;
+        int j0_piece = 0;
+        if (LEVEL2 && geom.grouped && vary[2] == 0u) {          // block-uniform
+            // lowest / highest y key of the piece -> its first y plane; NaN keys have no plane: radix passes
+            if (tid == 0) { dbase[0] = 0xffffffffu; dbase[1] = 0u; }
+            __syncthreads();
+            u32 mn = 0xffffffffu, mx = 0u;
+            for (u32 i = tid; i < n; i += THREADS) { mn = min(mn, sk[CAP + i]); mx = max(mx, sk[CAP + i]); }
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0) { atomicMin(&dbase[0], mn); atomicMax(&dbase[1], mx); }
+            __syncthreads();
+            mn = dbase[0]; mx = dbase[1];
+            __syncthreads();
+            piece_const_x = mn >= 0x007fffffu && mx <= 0xff800000u;   // float_key(-inf) .. float_key(+inf)
+            if (piece_const_x) j0_piece = (int) yplane_of(key_float(mn), geom) - 1;
+        }
+        if (geom.grouped && (LEVEL2 ? piece_const_x : b >= geom.gy + geom.gx)) {   // (layer 0 = below the first plane: radix passes)
             const u32 nsub = geom.gy + geom.gx;
-            const u32 L = b / nsub, sub = b - L * nsub;
-            const u32 xb = (u32) ((i64) L - 1 + geom.x_off);    // global index of the layer's lower plane
+            const u32 L = b / nsub, sub = LEVEL2 ? 0u : b - L * nsub;
+            const u32 xb = (u32) ((i64) L - 1 + geom.x_off);    // global index of the layer's lower plane (first level only)
             u32 *gtab = cnt;                                    // [SEG_GROUPS + 1]: counts -> starts -> ends
             unsigned short *gid = ord + CAP;                    // group of every element (second half of ord as temp)
+            constexpr u32 ngroups = (u32) SEG_GROUPS;
             for (u32 i = tid; i < (u32) SEG_GROUPS + 2; i += THREADS) gtab[i] = 0;
             if (tid == 0) vary[3] = 0;
             __syncthreads();
             if (sub < geom.gy) {          // all keys share x: groups by y plane
-                const int j0 = (int) (sub * geom.ystep) - 1;
+                const int j0 = LEVEL2 ? j0_piece : (int) (sub * geom.ystep) - 1;
                 for (u32 i = tid; i < n; i += THREADS) {
                     int g = (int) yplane_of(key_float(sk[CAP + i]), geom) - j0;
                     g = g < 0 ? 0 : (g > SEG_GROUPS - 1 ? SEG_GROUPS - 1 : g);
@@ -340,7 +361,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
 #pragma unroll
                 for (int q = 0; q < GPT; q++) {
                     const u32 g = tid * GPT + q;
-                    c[q] = g < (u32) SEG_GROUPS ? gtab[g] : 0u;
+                    c[q] = g < ngroups ? gtab[g] : 0u;
                     sum += c[q];
                     mx = c[q] > mx ? c[q] : mx;
                 }
@@ -350,7 +371,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
 #pragma unroll
                 for (int q = 0; q < GPT; q++) {
                     const u32 g = tid * GPT + q;
-                    if (g < (u32) SEG_GROUPS) gtab[g] = ex;
+                    if (g < ngroups) gtab[g] = ex;
                     ex += c[q];
                 }
             }
@@ -389,7 +410,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                     }
                 }
                 if (vary[3]) {   // list the large groups
-                    for (u32 g = tid; g < (u32) SEG_GROUPS; g += THREADS) {
+                    for (u32 g = tid; g < ngroups; g += THREADS) {
                         const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
                         if (e1 - s1 > (u32) SEG_GROUP_MAX) {
                             const u32 k = atomicAdd(s_nl, 1u);
@@ -715,6 +736,42 @@ static __global__ void __launch_bounds__(256) k_seg_big_scatter(u32 n_big, const
     }
 }
 
+// Where the candidates go: straight to their place in the bucket-grouped arrays of the segmented sort (the bucket
+// offsets were scanned in phase 1), so no separate scatter pass and the sort reads its keys contiguously.  Elements of
+// oversized buckets go to the compacted big list instead and feed the x range of their bucket (segsort.cuh).
+struct CandOut {
+    u32 *gkx, *gky, *gkz, *gid;        // grouped by bucket: keys + candidate id
+    u32 *cbucket;                      // bucket of every candidate (candidate order)
+    const u32 *count, *start, *bigoff;
+    u32 *cursor;
+    u32 *bkx, *bky, *bkz, *bid, *xinvmin, *xmax;
+};
+// executed by all 32 lanes; `has` = this lane emits a candidate
+__device__ __forceinline__ void emit_candidate(bool has, u32 b, u32 id, u32 kxv, u32 kyv, u32 kzv, const CandOut &o) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 act = __ballot_sync(0xffffffffu, has);
+    if (!has) return;
+    const u32 peers = __match_any_sync(act, b);
+    const u32 leader = __ffs(peers) - 1;
+    u32 off = 0;
+    if (lane == leader) off = atomicAdd(&o.cursor[b], (u32) __popc(peers));
+    off = __shfl_sync(peers, off, leader) + __popc(peers & ((1u << lane) - 1u));
+    o.cbucket[id] = b;
+    if (o.count[b] > (u32) SEG_CAP) {
+        const u32 q = o.bigoff[b] + off;
+        o.bkx[q] = kxv; o.bky[q] = kyv; o.bkz[q] = kzv; o.bid[q] = id;
+        const u32 mx = __reduce_max_sync(peers, kxv), mn = __reduce_max_sync(peers, ~kxv);
+        if (lane == leader) {
+            atomicMax(&o.xmax[b], mx);
+            atomicMax(&o.xinvmin[b], mn);
+        }
+    } else {
+        const u32 q = o.start[b] + off;
+        o.gkx[q] = kxv; o.gky[q] = kyv; o.gkz[q] = kzv; o.gid[q] = id;
+    }
+}
+
+
 // Phase-2 part of the segmented sort: group by bucket, sort the small buckets in shared memory, and run the
 // radix fallback for the oversized buckets.  The histogram (h.count) and its scan (h.start / h.bigoff) were
 // produced in phase 1.
@@ -800,6 +857,145 @@ static inline cudaError_t seg_sort_run(const u32 *kx, const u32 *ky, const u32 *
     }
     if ((ef = cudaStreamWaitEvent(stream, ev_join, 0)) != cudaSuccess) return ef;
     return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Generic front end: segmented sort of ANY set of 96-bit position keys that lie on / inside the grid (dual
+// vertices of dual contouring, the per-(cell, edge) vertices of sparse marching cubes).  The marching-cubes path
+// derives the bucket of a vertex from the edge that owns it while it scans its entries; here the bucket comes from
+// the key itself:
+//     layer  L = (index of the last x plane at or below x) - x_off + 1      (exact float compares, monotone in x)
+//     sub      = y-plane index / ystep           if x == px[L-1] exactly     (gy pieces, monotone in y)
+//              = gy + floor((x - pb) * gx / (pb1 - pb))  otherwise           (gx pieces, monotone in x)
+// which is what the group stage of k_seg_sort assumes about a first-level bucket.  Three extra passes over the
+// candidates (bucket ids + histogram, one-block scan, grouping) replace the 14-launch global radix sort.
+// NaN keys have no place in this order: they raise *radix_needed and the caller falls back to radix_sort96.
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) k_gen_bucket(const u32 *__restrict__ kx, const u32 *__restrict__ ky, u32 n, SegGeom g,
+                                                           u32 x_planes /* local point planes */, u32 *__restrict__ cbucket,
+                                                           u32 *__restrict__ count, u32 *__restrict__ nan_count) {
+    const u32 lane = threadIdx.x & 31, nsub = g.gy + g.gx;
+    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const u32 i = base + lane;
+        const bool valid = i < n;
+        const u32 active = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const float x = key_float(kx[i]), y = key_float(ky[i]);
+        u32 b;
+        if (x != x || y != y) {
+            atomicAdd(nan_count, 1u);
+            b = 0;
+        } else {
+            const u32 resx = g.Xg - 1;
+            const i64 j = (i64) plane_index(x, g.amin_x, g.asize_x, resx);        // global plane index (0 if below all planes)
+            const bool below = !(axis_pos(0u, resx, g.amin_x, g.asize_x) <= x);
+            i64 L = below ? 0 : j - g.x_off + 1;
+            L = L < 0 ? 0 : (L > (i64) x_planes ? (i64) x_planes : L);
+            u32 sub = 0;
+            if (L >= 1) {
+                const u32 xb = (u32) (L - 1 + g.x_off);
+                const float pb = axis_pos(xb, resx, g.amin_x, g.asize_x);
+                if (x == pb) {
+                    sub = yplane_of(y, g) / g.ystep;
+                    sub = sub > g.gy - 1 ? g.gy - 1 : sub;
+                } else {
+                    u32 k = 0;
+                    if (g.gx > 1 && xb < resx) {
+                        const float pb1 = axis_pos(xb + 1, resx, g.amin_x, g.asize_x);
+                        const float f = __fmul_rn(__fsub_rn(x, pb), __fdiv_rn((float) g.gx, __fsub_rn(pb1, pb)));
+                        k = f > 0.f ? (u32) f : 0u;
+                        k = k > g.gx - 1 ? g.gx - 1 : k;
+                    }
+                    sub = g.gy + k;
+                }
+            }
+            b = (u32) L * nsub + sub;
+        }
+        cbucket[i] = b;
+        const u32 peers = __match_any_sync(active, b);
+        if (lane == (u32) (__ffs(peers) - 1)) atomicAdd(&count[b], (u32) __popc(peers));
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_gen_group(const u32 *__restrict__ kx, const u32 *__restrict__ ky, const u32 *__restrict__ kz,
+                                                          u32 n, const u32 *__restrict__ cbucket_in, CandOut out) {
+    const u32 lane = threadIdx.x & 31;
+    for (u32 base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform
+        const u32 i = base + lane;
+        const bool has = i < n;
+        emit_candidate(has, has ? cbucket_in[i] : 0u, i, has ? kx[i] : 0u, has ? ky[i] : 0u, has ? kz[i] : 0u, out);
+    }
+}
+
+// scratch of the generic sort for n candidates on a grid with x_planes local point planes
+struct GenSort {
+    SegHead head;
+    SegScratch seg;
+    u32 *gkx, *gky, *gkz;    // keys grouped by bucket
+    u32 *cb;                 // bucket of every candidate (k_gen_bucket -> k_gen_group; emit_candidate rewrites seg.cbucket)
+    u32 nb;
+    static u32 pick_groups(u32 n, u32 x_planes, u32 Y) {
+        // pieces per layer so that a bucket holds ~1-2 k elements, and few enough y planes per piece for the group stage
+        if (g_tuning[3] > 0 && g_tuning[3] < 100) return (u32) g_tuning[3];
+        u32 g = 1;
+        const u64 per_layer = (u64) n / (x_planes ? x_planes : 1u);
+        while (g < 16 && (u64) g * 1536u < per_layer) g *= 2;
+        while (g < 32 && (Y + g - 1) / g + 2 > (u32) SEG_GROUPS) g *= 2;
+        return g;
+    }
+    static size_t carve(Carver &c, size_t n, u32 x_planes, u32 Y, GenSort *out) {
+        GenSort s;
+        const u32 g = pick_groups((u32) n, x_planes, Y);
+        s.nb = (x_planes + 2) * (2 * g);
+        SegHead::carve(c, s.nb, &s.head);
+        SegScratch::carve(c, n, &s.seg);
+        s.gkx = c.take<u32>(n);
+        s.gky = c.take<u32>(n);
+        s.gkz = c.take<u32>(n);
+        s.cb = c.take<u32>(n);
+        if (out) *out = s;
+        return c.bytes();
+    }
+};
+
+// Sorts n candidates (keys kx/ky/kz in candidate order).  Result: s.seg.perm (candidate ids in sorted order) and
+// s.seg.skx/sky/skz (their keys), ready for k_unique(..., keys_sorted = true).  counters: the caller's counter block
+// (C_NBIG, C_MAXB, C_RADIX, C_ABORT are used); counters[C_ABORT] or counters[C_RADIX] != 0 afterwards means the result is incomplete (NaN keys,
+// or a piece that the two bucket levels could not cut below SEG_CAP) and the caller must use radix_sort96 instead.
+static inline cudaError_t gen_sort_run(const u32 *kx, const u32 *ky, const u32 *kz, u32 n, const Geom &gm, const GenSort &s,
+                                       u32 *counters, cudaStream_t stream) {
+    const u32 X = (u32) gm.X, Y = (u32) gm.Y;
+    const u32 g = GenSort::pick_groups(n, X, Y);
+    SegGeom geom{gm.amin[0], gm.asize[0], gm.amin[1], gm.asize[1], gm.amin[2], gm.asize[2], (u32) gm.Xg, Y, (u32) gm.Z, gm.x_off, g, g,
+                 (Y + g - 1) / g, false};
+    geom.grouped = geom.ystep + 2 <= (u32) SEG_GROUPS;
+    cudaError_t e = cudaMemsetAsync(s.head.count, 0, SegHead::words(s.nb) * sizeof(u32), stream);
+    if (e != cudaSuccess) return e;
+    const int blocks = (int) ((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+    ISX_LAUNCH(k_gen_bucket, blocks, 256, 0, stream, kx, ky, n, geom, X, s.cb, s.head.count, counters + C_ABORT);
+    ISX_LAUNCH(k_seg_scan, 1, 1024, 0, stream, s.nb, s.head.count, s.head.start, s.head.cursor, s.head.bigoff, counters + C_NBIG,
+               counters + C_MAXB);
+    const CandOut co{s.gkx, s.gky, s.gkz, s.seg.perm0, s.seg.cbucket, s.head.count, s.head.start, s.head.bigoff, s.head.cursor,
+                     s.seg.bkx, s.seg.bky, s.seg.bkz, s.seg.bid, s.head.xinvmin, s.head.xmax};
+    ISX_LAUNCH(k_gen_group, blocks, 256, 0, stream, kx, ky, kz, n, s.cb, co);
+    e = seg_sort_run(s.gkx, s.gky, s.gkz, n, nullptr, n, n, s.nb, 0, counters + C_NBIG, n, s.head, s.seg, geom, false,
+                     counters + C_RADIX, stream);
+    return e;
+}
+// gate of the weld pass behind gen_sort_run: no capacities to check, but NaN keys (C_ABORT) or a still-oversized
+// second-level bucket (C_RADIX) mean the permutation is incomplete
+static inline Gate gen_sort_gate() {
+    Gate g;
+    g.allow_radix = 0;
+    g.on = 1;
+    return g;
+}
+// The caller's second attempt after counters[C_ABORT] / counters[C_RADIX] != 0: clears what the first attempt left in the counter block.
+static inline cudaError_t gen_sort_reset_for_radix(u32 *counters, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(counters + C_TICKET_C, 0, 4 * sizeof(u32), stream);   // C_TICKET_C, C_V, C_NLO, C_NHI
+    if (e == cudaSuccess) e = cudaMemsetAsync(counters + C_RADIX, 0, 2 * sizeof(u32), stream);   // C_RADIX, C_ABORT
+    return e;
 }
 
 }   // namespace isx

@@ -14,6 +14,7 @@
 #include "dense.cuh"
 #include "radix.cuh"
 #include "weld.cuh"
+#include "segsort.cuh"
 #include "dcmath.cuh"
 
 #define ISX_LUT_QUAL static __device__
@@ -314,13 +315,54 @@ __device__ __forceinline__ u32 find_sparse_cell(const i64 *__restrict__ cell_idx
     }
     return (lo < n && cell_idx[lo] == key) ? lo : 0xffffffffu;
 }
+// same, inside the list range [lo, hi) (one x plane of cells: plane_start[x] .. plane_start[x + 1])
+__device__ __forceinline__ u32 find_sparse_cell_in(const i64 *__restrict__ cell_idx, u32 lo, u32 hi, i64 key) {
+    const u32 end = hi;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (cell_idx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < end && cell_idx[lo] == key) ? lo : 0xffffffffu;
+}
+// same, for a key below cell_idx[s] that lies a short way back in the list (a neighbour in the same x plane: one cell
+// or one row back): gallop backwards from s, then bisect the last stride
+__device__ __forceinline__ u32 find_sparse_cell_back(const i64 *__restrict__ cell_idx, u32 s, i64 key) {
+    u32 hi = s, step = 1;          // invariant: cell_idx[hi] > key
+    u32 lo;
+    while (true) {
+        if (step > hi) { lo = 0; break; }
+        const u32 probe = hi - step;
+        const i64 v = cell_idx[probe];
+        if (v == key) return probe;
+        if (v < key) { lo = probe + 1; break; }
+        hi = probe;
+        step <<= 1;
+    }
+    return find_sparse_cell_in(cell_idx, lo, hi, key);
+}
+// first list position of every x plane of cells: plane_start[x] = lower_bound(cell_idx, x * cy * cz), x = 0 .. X-1
+// (X - 1 cell planes; the last entry is n)
+static __global__ void __launch_bounds__(256) k_sp_plane_start(const i64 *__restrict__ cell_idx, u32 n, SparseParams p,
+                                                               u32 *__restrict__ plane_start) {
+    const u32 planes = (u32) p.g.X;   // entries 0 .. X-1
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < planes; x += gridDim.x * blockDim.x) {
+        const i64 key = (i64) x * p.cy * p.cz;
+        u32 lo = 0, hi = n;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (cell_idx[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        plane_start[x] = lo;
+    }
+}
 
 // The edge (p_lo, axis) is handled by the cell whose corner 0 is p_lo (its edges e0 = +z, e3 = +y,
 // e8 = +x): that cell is always one of the 4 cells around the edge, so if it is absent the reference
 // skips the quad anyway.  Quad order = sorted (p_lo, p_hi) = ascending cell, then +z, +y, +x.
 // q[k] = sparse-list slots of the 4 cells in the reference's cyclic order; false -> skip.
 __device__ __forceinline__ bool sparse_quad_cells(const SparseParams &p, const i64 *__restrict__ cell_idx, u32 n,
-                                                  const u32 *__restrict__ cinfo, u32 s, int axis, u32 q[4]) {
+                                                  const u32 *__restrict__ cinfo, const u32 *__restrict__ plane_start, u32 s, int axis,
+                                                  u32 q[4]) {
     u32 x, y, z;
     cell_coords(p, cell_idx[s], x, y, z);
     int dx[4], dy[4], dz[4];
@@ -328,11 +370,15 @@ __device__ __forceinline__ bool sparse_quad_cells(const SparseParams &p, const i
     else if (axis == 1) { dx[0] = 0; dy[0] = 0; dz[0] = 0; dx[1] = 0; dy[1] = 0; dz[1] = 1; dx[2] = 1; dy[2] = 0; dz[2] = 1; dx[3] = 1; dy[3] = 0; dz[3] = 0; }
     else { dx[0] = 0; dy[0] = 0; dz[0] = 0; dx[1] = 1; dy[1] = 0; dz[1] = 0; dx[2] = 1; dy[2] = 1; dz[2] = 0; dx[3] = 0; dy[3] = 1; dz[3] = 0; }
     q[0] = s;
+    // the neighbours of the previous x plane lie inside [plane_start[x-1], plane_start[x]): 11 probes instead of 21 at
+    // 2.4 M cells; those of the own plane are one cell or one row back: a short gallop from s
+    u32 pl = 0, ph = 0;
+    if (x >= 1 && axis != 2) { pl = plane_start[x - 1]; ph = plane_start[x]; }
 #pragma unroll
     for (int k = 1; k < 4; k++) {
         if (x < (u32) dx[k] || y < (u32) dy[k] || z < (u32) dz[k]) return false;
         const i64 key = ((i64) (x - dx[k]) * p.cy + (y - dy[k])) * p.cz + (z - dz[k]);
-        const u32 t = find_sparse_cell(cell_idx, n, key);
+        const u32 t = dx[k] ? find_sparse_cell_in(cell_idx, pl, ph, key) : find_sparse_cell_back(cell_idx, s, key);
         if (t == 0xffffffffu || !(cinfo[t] & 0x100u)) return false;
         q[k] = t;
     }
@@ -348,7 +394,8 @@ __device__ __forceinline__ u32 own_edges_of_case(u32 cs) {
 // dinfo = qmask (3 bits) | isout (3 bits) << 4
 __global__ void __launch_bounds__(128) k_sp_dc_quads(const float *__restrict__ values8, const i64 *__restrict__ cell_idx,
                                                      SparseParams p, u32 n, const u32 *__restrict__ cinfo,
-                                                     u32 *__restrict__ dinfo, unsigned char *__restrict__ used) {
+                                                     const u32 *__restrict__ plane_start, u32 *__restrict__ dinfo,
+                                                     unsigned char *__restrict__ used) {
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const u32 w = cinfo[s];
         u32 m = 0, io = 0;
@@ -363,7 +410,7 @@ __global__ void __launch_bounds__(128) k_sp_dc_quads(const float *__restrict__ v
                 for (int a = 0; a < 3; a++) {
                     if (!((own >> a) & 1u)) continue;
                     u32 q[4];
-                    if (sparse_quad_cells(p, cell_idx, n, cinfo, s, a, q)) {
+                    if (sparse_quad_cells(p, cell_idx, n, cinfo, plane_start, s, a, q)) {
                         m |= 1u << a;
                         used[q[0]] = 1; used[q[1]] = 1; used[q[2]] = 1; used[q[3]] = 1;
                     }
@@ -394,7 +441,8 @@ __global__ void __launch_bounds__(256) k_sp_dc_keys(u32 n, const u32 *__restrict
 }
 
 __global__ void __launch_bounds__(128) k_sp_dc_faces(const i64 *__restrict__ cell_idx, SparseParams p, u32 n,
-                                                     const u32 *__restrict__ cinfo, const u32 *__restrict__ dinfo,
+                                                     const u32 *__restrict__ cinfo, const u32 *__restrict__ plane_start,
+                                                     const u32 *__restrict__ dinfo,
                                                      const u32 *__restrict__ quad_off, const u32 *__restrict__ cand_off,
                                                      const u32 *__restrict__ cellslot, const u32 *__restrict__ cand_rank,
                                                      const float *__restrict__ dual_v, int *__restrict__ F, int *__restrict__ quads_out) {
@@ -406,7 +454,7 @@ __global__ void __launch_bounds__(128) k_sp_dc_faces(const i64 *__restrict__ cel
         for (int a = 0; a < 3; a++) {
             if (!((m >> a) & 1u)) continue;
             u32 q[4];
-            sparse_quad_cells(p, cell_idx, n, cinfo, s, a, q);
+            sparse_quad_cells(p, cell_idx, n, cinfo, plane_start, s, a, q);
             if (!((io >> a) & 1u)) {
                 const u32 t0 = q[0], t1 = q[1];
                 q[0] = q[3]; q[1] = q[2]; q[2] = t1; q[3] = t0;
@@ -452,28 +500,58 @@ static size_t carve_sp_ws(Carver &c, size_t n, SpWs *out) {
 struct SpScratch {
     u32 *kx, *ky, *kz, *cand_rank;
     u64 *descV;
-    RadixBuffers radix;
+    GenSort gs;   // segmented sort by grid layer (segsort.cuh); its radix buffers serve the fallback
 };
-static size_t carve_sp_scratch(Carver &c, size_t nc, SpScratch *out) {
+static size_t carve_sp_scratch(Carver &c, size_t nc, u32 x_planes, u32 Y, SpScratch *out) {
     SpScratch s;
     s.kx = c.take<u32>(nc);
     s.ky = c.take<u32>(nc);
     s.kz = c.take<u32>(nc);
     s.cand_rank = c.take<u32>(nc);
     s.descV = c.take<u64>(nc / UQ_TILE + 2);
-    RadixBuffers::carve(c, nc, &s.radix);
+    GenSort::carve(c, nc, x_planes, Y, &s.gs);
     if (out) *out = s;
     return c.bytes();
+}
+// sort (segmented by grid layer, radix sort as the fallback) + weld, then `faces()` enqueues the face kernel;
+// leaves the counter block in h
+template <typename FacesFn>
+static int sort_weld_faces(const SpScratch &s, u32 nc, const Geom &g, u32 *counters, float x_lo_threshold, float x_hi_threshold, float *V,
+                           cudaStream_t stream, u32 *h, bool use_seg, FacesFn faces) {
+    const int sms = device_sms();
+    for (int attempt = use_seg ? 0 : 1; attempt < 2; attempt++) {
+        if (attempt == 0) {
+            ISX_CUDA(gen_sort_run(s.kx, s.ky, s.kz, nc, g, s.gs, counters, stream));
+            ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.gs.seg.perm, s.gs.seg.skx, s.gs.seg.sky, s.gs.seg.skz, s.cand_rank, V,
+                       counters, s.descV, host_float_key(x_lo_threshold), host_float_key(x_hi_threshold), nullptr, 0xffffffffu, true, gen_sort_gate());
+        } else {   // NaN keys, or a piece the two bucket levels could not cut below the shared-memory capacity
+            if (use_seg) {
+                ISX_CUDA(gen_sort_reset_for_radix(counters, stream));
+                ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
+            }
+            ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.gs.seg.radix, stream));
+            ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.gs.seg.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, counters,
+                       s.descV, host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
+        }
+        faces();
+        ISX_CUDA(cudaGetLastError());
+        ISX_CUDA(cudaMemcpyAsync(h, counters, C_COUNT * sizeof(u32), cudaMemcpyDeviceToHost, stream));
+        ISX_CUDA(cudaStreamSynchronize(stream));
+        if (!h[C_ABORT] && !h[C_RADIX]) break;
+    }
+    return OK;
 }
 struct SpDcWs {
     u32 *counters;
     u32 *dinfo, *quad_off, *cand_off;
     unsigned char *used;
     u64 *descA, *descB;
+    u32 *plane_start;   // X + 1
 };
-static size_t carve_sp_dc_ws(Carver &c, size_t n, SpDcWs *out) {
+static size_t carve_sp_dc_ws(Carver &c, size_t n, size_t X, SpDcWs *out) {
     SpDcWs b;
     b.counters = c.take<u32>(C_COUNT);
+    b.plane_start = c.take<u32>(X + 1);
     b.dinfo = c.take<u32>(n + 1);
     b.quad_off = c.take<u32>(n + 1);
     b.cand_off = c.take<u32>(n + 1);
@@ -535,9 +613,9 @@ size_t isoext_mc_sparse_workspace_bytes(int64_t n) {
     Carver c(nullptr);
     return carve_sp_ws(c, (size_t) (n > 0 ? n : 1), nullptr);
 }
-size_t isoext_sparse_scratch_bytes(int64_t n_candidates) {
+size_t isoext_sparse_scratch_bytes(int64_t n_candidates, int64_t X, int64_t Y) {
     Carver c(nullptr);
-    return carve_sp_scratch(c, (size_t) (n_candidates > 0 ? n_candidates : 1), nullptr);
+    return carve_sp_scratch(c, (size_t) (n_candidates > 0 ? n_candidates : 1), (u32) X, (u32) Y, nullptr);
 }
 
 // marching_cubes on a SparseGrid, phase 1: counts_out[0..1] = triangles T, vertex candidates Vc.
@@ -593,19 +671,18 @@ int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t
     if (carve_sp_ws(c, (size_t) n, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
     Carver cs(scratch);
     SpScratch s;
-    if (carve_sp_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
+    if (carve_sp_scratch(cs, (size_t) n_candidates, (u32) X, (u32) Y, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
     const u32 nc = (u32) n_candidates;
     const int sms = device_sms();
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_mc_keys, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, b.cinfo, b.offB, s.kx, s.ky, s.kz);
-    ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
-               host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
-    ISX_LAUNCH(k_sp_mc_faces, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, method, b.cinfo, b.offA, b.offB, s.cand_rank, F);
-    ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
-    ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    ISX_CUDA(cudaStreamSynchronize(stream));
+    // every (cell, edge) vertex is a candidate (4 bit-equal copies of most positions): measured, the global radix sort
+    // (1.17 ms at 9.6 M candidates) beats the layer-segmented sort (1.3 ms: the in-group ranking pays for the duplicates)
+    rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, g_tuning[3] == 100, [&]() {
+        ISX_LAUNCH(k_sp_mc_faces, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, method, b.cinfo, b.offA, b.offB, s.cand_rank, F);
+    });
+    if (rc != OK) return rc;
     counts_out[0] = h[C_V];
     counts_out[1] = h[C_NLO];
     counts_out[2] = h[C_NHI];
@@ -663,9 +740,9 @@ int isoext_its_sparse_emit(const float *values8, const int64_t *cell_idx, int64_
     return OK;
 }
 
-size_t isoext_dc_sparse_workspace_bytes(int64_t n) {
+size_t isoext_dc_sparse_workspace_bytes(int64_t n, int64_t X) {
     Carver c(nullptr);
-    return carve_sp_dc_ws(c, (size_t) (n > 0 ? n : 1), nullptr);
+    return carve_sp_dc_ws(c, (size_t) (n > 0 ? n : 1), (size_t) (X > 0 ? X : 1), nullptr);
 }
 
 // dual_contouring on a SparseGrid, phase 1: dual_v (n_cells x 3); counts_out[0..1] = quads Q, used vertices Vc
@@ -681,7 +758,7 @@ int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     if (n <= 0) return OK;
     Carver c(workspace);
     SpDcWs b;
-    if (carve_sp_dc_ws(c, (size_t) n, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
+    if (carve_sp_dc_ws(c, (size_t) n, (size_t) X, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
     const int sms = device_sms();
     const int blocks = grid_for(n, 128, sms * 16);
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
@@ -689,7 +766,8 @@ int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_CUDA(cudaMemsetAsync(b.descA, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descB, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_dc_solve, blocks, 128, 0, stream, cell_idx, p, (u32) n, cinfo, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
-    ISX_LAUNCH(k_sp_dc_quads, blocks, 128, 0, stream, values8, cell_idx, p, (u32) n, cinfo, b.dinfo, b.used);
+    ISX_LAUNCH(k_sp_plane_start, grid_for(X, 256, sms * 4), 256, 0, stream, cell_idx, (u32) n, p, b.plane_start);
+    ISX_LAUNCH(k_sp_dc_quads, blocks, 128, 0, stream, values8, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.used);
     ISX_LAUNCH(k_sp_fold_used, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.used, b.dinfo);
     ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, b.dinfo, 0, 7u, 8, 1u, b.quad_off, b.cand_off, b.descA, b.descB,
                (int) C_Q, (int) C_VC, (int) C_TICKET_D);
@@ -714,23 +792,21 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
     if (n <= 0 || n_candidates <= 0) return OK;
     Carver c(workspace);
     SpDcWs b;
-    if (carve_sp_dc_ws(c, (size_t) n, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
+    if (carve_sp_dc_ws(c, (size_t) n, (size_t) X, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
     Carver cs(scratch);
     SpScratch s;
-    if (carve_sp_scratch(cs, (size_t) n_candidates, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
+    if (carve_sp_scratch(cs, (size_t) n_candidates, (u32) X, (u32) Y, &s) > scratch_bytes) return fail(E_WORKSPACE, "scratch too small");
     const u32 nc = (u32) n_candidates;
     const int sms = device_sms();
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_dc_keys, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.dinfo, b.cand_off, cellslot, dual_v, s.kx, s.ky, s.kz);
-    ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
-    ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
-               host_float_key(-INFINITY), host_float_key(INFINITY));
-    ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.dinfo, b.quad_off, b.cand_off, cellslot,
-               s.cand_rank, dual_v, F, quads_out);
-    ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
-    ISX_CUDA(cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    ISX_CUDA(cudaStreamSynchronize(stream));
+    // dual vertices: one candidate per cell, segmented by grid layer (0.39 ms vs 0.76 ms for the global radix sort at 2.4 M)
+    rc = sort_weld_faces(s, nc, p.g, b.counters, -INFINITY, INFINITY, V, stream, h, g_tuning[3] != 101, [&]() {
+        ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.quad_off, b.cand_off,
+                   cellslot, s.cand_rank, dual_v, F, quads_out);
+    });
+    if (rc != OK) return rc;
     counts_out[0] = h[C_V];
     return OK;
 }

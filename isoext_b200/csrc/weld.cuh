@@ -20,14 +20,14 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
                                                 u32 *__restrict__ cand_rank, float *__restrict__ V, u32 *__restrict__ counters,
                                                 u64 *__restrict__ desc, u32 key_lo, u32 key_hi,
                                                 const u32 *__restrict__ n_dev = nullptr, u32 n_cap = 0xffffffffu,
-                                                bool keys_sorted = false) {
+                                                bool keys_sorted = false, Gate gate = Gate()) {
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
     // the tile's new vertices have consecutive ranks: they are staged here and copied out with coalesced stores
     // (three scalar stores per vertex at a 12-byte stride cost 22 of the kernel's 47 us at 1024^3)
     __shared__ float sv[3 * UQ_TILE];
     if (n_dev) n = *n_dev;       // single-call fast path: the count lives on the device
-    if (n > n_cap || counters[C_ABORT]) return;   // C_ABORT: `perm` is incomplete, the host re-runs
+    if (n > n_cap || gate_bad(counters, gate)) return;   // `perm` is incomplete, the host re-runs
     const u32 ntiles = (n + UQ_TILE - 1) / UQ_TILE;
     while (true) {
         __syncthreads();

@@ -230,7 +230,7 @@ def mc_sparse(grid: SparseGrid, level: float, method_id: int, emit_range=None, x
         T, Vc = int(counts[0]), int(counts[1])
         if Vc == 0 or (T == 0 and not with_counts):
             return empty
-        scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc), dev)
+        scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc, X, Y), dev)
         V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
         F = torch.empty((T, 3), dtype=torch.int32, device=dev)
         out = (C.c_int64 * 4)()
@@ -283,7 +283,7 @@ def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads:
         return None, None, dual_v, None
     with torch.cuda.device(dev):
         stream = _stream_ptr()
-        ws = grid._ws.get("dc_ws", lib.isoext_dc_sparse_workspace_bytes(n), dev)
+        ws = grid._ws.get("dc_ws", lib.isoext_dc_sparse_workspace_bytes(n, X), dev)
         counts = (C.c_int64 * 4)()
         _lib.check(lib.isoext_dc_sparse_count(grid._values.data_ptr(), grid._cells.data_ptr(), n, X, Y, Z, amin, amax,
                                               its.cinfo.data_ptr(), its.cellslot.data_ptr(), its.its_off.data_ptr(),
@@ -294,7 +294,7 @@ def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads:
             return None, None, dual_v, None
         if dual_v_in is not None:
             dual_v.copy_(dual_v_in)
-        scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc), dev)
+        scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc, X, Y), dev)
         V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
         F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)
         quads = torch.empty((Q, 4), dtype=torch.int32, device=dev) if want_quads else None
