@@ -18,6 +18,9 @@
 //   k_dc_scan      look-back scan: quad offsets, candidate ids of the used cells
 //   k_dc_keys      sortable position keys of the used dual vertices
 //   radix_sort96 + k_unique (weld.cuh): reference order = lexicographic positions
+//                  (the layer-segmented sort of segsort.cuh was measured here: 103 vs 233 us on curved surfaces, but
+//                  320 us on the 512^3 CSG of BASELINE configs[3], whose flat faces put 260 k dual vertices with
+//                  almost-equal x into one layer and through the second bucket level -- the radix sort stays)
 //   k_dc_faces     orientation flip, shorter-diagonal split, final ids
 #include "../../include/isoext_b200.h"   // the C-ABI prototypes are compiler-checked against the definitions
 #include "dense.cuh"
@@ -35,7 +38,7 @@ struct ItsWs {
     u32 *counters;
     u32 *bits;
     u64 *descA, *descC, *descI;
-    unsigned char *span_cnt;
+    unsigned char *span_cnt;   // entries per candidate span: count pass -> fill pass (dense.cuh), not initialised
     u32 *heavy_list;
 };
 static size_t carve_its_ws(Carver &c, const DenseParams &p, size_t cap, ItsWs *out) {
@@ -495,12 +498,11 @@ int isoext_its_dense_count(const float *values, int64_t X, int64_t Y, int64_t Z,
     ISX_CUDA(cudaMemsetAsync(b.counters, 0, C_COUNT * sizeof(u32), stream));
     ISX_CUDA(cudaMemsetAsync(b.descA, 0, compact_desc_count(p) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(row_start, 0, ((size_t) p.R + 2) * sizeof(u32), stream));
-    ISX_CUDA(cudaMemsetAsync(b.span_cnt, 0, compact_span_bytes(p), stream));
     ISX_CUDA(cudaMemsetAsync(b.descC, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descI, 0, ((size_t) cap / IT_TILE + 2) * sizeof(u64), stream));
     const int sms = device_sms();
     if (p.sdf) launch_sdf_bits(p, b.bits, stream);
-    else launch_signbits(values, b.bits, p.P, level, stream);
+    else launch_signbits(values, b.bits, span_sum_of(b.bits, p.P), p.P, level, stream);
     launch_compact(b.bits, p, ent, cap, row_start, b.descA, b.counters, b.span_cnt, b.heavy_list, stream);
     ISX_LAUNCH(k_its_scan, scan_blocks(sms), 256, 0, stream, cap, b.counters, ent, cellslot, its_off, b.descC, b.descI);
     ISX_CUDA(cudaGetLastError());

@@ -142,9 +142,17 @@ __device__ __forceinline__ void ld_stream_f8(const float *p, float4 &a, float4 &
                  : "l"(p));
 }
 
+// Per-span summary (one byte per 128-point span of the flat point array, written beside the sign bits): 0 = all 128
+// bits clear, 1 = all set, 2 = mixed.  The compaction decides "this part of the volume holds no entry" from the
+// summary alone (1/128 B per voxel instead of the 1/8 B per voxel of the bits, which no longer fit the L2 at 2048^3).
+constexpr u32 SUM_MIXED = 2u;
+__device__ __forceinline__ u32 span_summary(u32 zero_lanes, u32 ones_lanes, u32 mask) {
+    return (zero_lanes & mask) == mask ? 0u : ((ones_lanes & mask) == mask ? 1u : SUM_MIXED);
+}
+
 // tail group (possibly empty) + one zero group of padding so that readers may over-fetch
-__device__ __forceinline__ void signbits_tail(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level,
-                                              i64 first_tail_group, i64 ngroups_total, u32 lane, bool pad) {
+__device__ __forceinline__ void signbits_tail(const float *__restrict__ v, u32 *__restrict__ bits, unsigned char *__restrict__ sum, i64 P,
+                                              float level, i64 first_tail_group, i64 ngroups_total, u32 lane, bool pad) {
     if (!pad && first_tail_group >= ngroups_total && (P & 127) == 0) return;   // sub-range of a larger volume: nothing to finish
     for (i64 g = first_tail_group; g <= ngroups_total; g++) {   // remaining full groups + the partial one
         i64 base = g << 7;
@@ -156,14 +164,17 @@ __device__ __forceinline__ void signbits_tail(const float *__restrict__ v, u32 *
         }
         u32 w = gather_word(nib, lane);
         if ((lane & 7) == 0) bits[(g << 2) + (lane >> 3)] = w;
+        const u32 bz = __ballot_sync(0xffffffffu, w == 0u), bo = __ballot_sync(0xffffffffu, w == 0xffffffffu);
+        if (lane == 0) sum[g] = (unsigned char) (g < ngroups_total ? span_summary(bz, bo, 0xffffffffu) : SUM_MIXED);   // partial group: never trusted
     }
     if (pad && (lane & 7) == 0) bits[((ngroups_total + 1) << 2) + (lane >> 3)] = 0u;
+    if (pad && lane == 0) sum[ngroups_total + 1] = (unsigned char) SUM_MIXED;
 }
 
 // VEC8 = false: one float4 per lane per step (warp = 128 points); true: one 256-bit load (warp = 256 points).
 template <bool VEC8, int UNROLL>
-static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restrict__ v, u32 *__restrict__ bits, i64 P, float level,
-                                                           bool pad) {
+static __global__ void __launch_bounds__(256, 6) k_signbits_t(const float *__restrict__ v, u32 *__restrict__ bits,
+                                                           unsigned char *__restrict__ sum, i64 P, float level, bool pad) {
     const u32 lane = threadIdx.x & 31;
     const i64 ngroups = P >> 7;   // full groups of 128 points
     const i64 nwarps = ((i64) gridDim.x * blockDim.x) >> 5;
@@ -179,11 +190,14 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
                 if (g + u < ngroups) {
                     u32 w = gather_word(nibble_of(a[u], level), lane);
                     if ((lane & 7) == 0) bits[((g + u) << 2) + (lane >> 3)] = w;
+                    const u32 bz = __ballot_sync(0xffffffffu, w == 0u), bo = __ballot_sync(0xffffffffu, w == 0xffffffffu);
+                    if (lane == 0) sum[g + u] = (unsigned char) span_summary(bz, bo, 0xffffffffu);
                 }
         }
-        if (wg == 0) signbits_tail(v, bits, P, level, ngroups, ngroups, lane, pad);
+        if (wg == 0) signbits_tail(v, bits, sum, P, level, ngroups, ngroups, lane, pad);
     } else {
         const i64 npairs = ngroups >> 1;   // units of 256 points
+        unsigned short *sum2 = reinterpret_cast<unsigned short *>(sum);   // two spans per warp step (the array is 2-byte aligned)
         for (i64 g = wg * UNROLL; g < npairs; g += nwarps * UNROLL) {
             float4 a[UNROLL], b[UNROLL];
 #pragma unroll
@@ -194,13 +208,16 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
                 if (g + u < npairs) {
                     // lane holds 8 consecutive bits; 4 lanes make one 32-bit word, the warp makes 8 words
                     u32 byte = nibble_of(a[u], level) | (nibble_of(b[u], level) << 4);
+                    const u32 bz = __ballot_sync(0xffffffffu, byte == 0u), bo = __ballot_sync(0xffffffffu, byte == 0xffu);
                     u32 w = byte << (8 * (lane & 3));
                     w |= __shfl_xor_sync(0xffffffffu, w, 1);
                     w |= __shfl_xor_sync(0xffffffffu, w, 2);
                     if ((lane & 3) == 0) bits[((g + u) << 3) + (lane >> 2)] = w;
+                    if (lane == 0)
+                        sum2[g + u] = (unsigned short) (span_summary(bz, bo, 0x0000ffffu) | (span_summary(bz, bo, 0xffff0000u) << 8));
                 }
         }
-        if (wg == 0) signbits_tail(v, bits, P, level, npairs << 1, ngroups, lane, pad);
+        if (wg == 0) signbits_tail(v, bits, sum, P, level, npairs << 1, ngroups, lane, pad);
     }
 }
 
@@ -211,7 +228,7 @@ static __global__ void __launch_bounds__(256) k_signbits_t(const float *__restri
 // plus a float-error margin all 32 points have the sign of the middle and the word is written without evaluating them
 // (> 95 % of the words of a typical volume).  Otherwise (and for words straddling two rows) the points are evaluated.
 // ---------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__restrict__ bits) {
+static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__restrict__ bits, unsigned char *__restrict__ sum) {
     // Two phases per block of 256 consecutive words.  Phase 1, thread per word: one evaluation at the middle of the
     // word decides it if the surface is provably farther than half a word (1-Lipschitz bound + float margin);
     // undecided words go to a shared list.  Phase 2, warp per listed word: the 32 lanes evaluate the 32 points at
@@ -220,7 +237,7 @@ static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__r
     __shared__ u32 s_n;
     __shared__ u32 s_list[256];
     const i64 P = p.P, nwords = (P + 31) >> 5;
-    const i64 nall = (i64) (((P >> 7) + 2) << 2);             // = signbits_words(P): the array is zero-padded to here
+    const i64 nall = (i64) (((P >> 7) + 2) << 2);             // = signbits_bit_words(P): the array is zero-padded to here
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
     const u32 resx = (u32) p.g.Xg - 1, resy = Y - 1, resz = Z - 1;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -284,6 +301,19 @@ static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__r
             if (lane == 0) bits[ww] = word;
         }
         __syncthreads();
+        if (threadIdx.x < 64) {                                // per-span summary of the block's 64 spans (span_summary)
+            const i64 sp = (base >> 2) + threadIdx.x, full = P >> 7;
+            if (sp <= full + 1) {
+                u32 sv = SUM_MIXED;
+                if (sp < full) {
+                    const u32 w0 = bits[4 * sp], w1 = bits[4 * sp + 1], w2 = bits[4 * sp + 2], w3 = bits[4 * sp + 3];
+                    const u32 any = w0 | w1 | w2 | w3, all = w0 & w1 & w2 & w3;
+                    sv = any == 0u ? 0u : (all == 0xffffffffu ? 1u : SUM_MIXED);
+                }
+                sum[sp] = (unsigned char) sv;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -301,7 +331,8 @@ int device_sms();
 extern int g_signbits_variant;   // tuning knob (api.cu); 0 = default
 // Launch the volume-streaming kernel (timed by the bench hooks).
 // pad = false: the range is a piece (a multiple of 256 points) of a larger volume whose last piece writes the padding
-static inline void launch_signbits(const float *values, u32 *bits, i64 P, float level, cudaStream_t stream, bool pad = true) {
+// sum: the span summary of the range (span_sum_of(bits base, P total) + first span of the range)
+static inline void launch_signbits(const float *values, u32 *bits, unsigned char *sum, i64 P, float level, cudaStream_t stream, bool pad = true) {
     const int sms = device_sms();
     const int var = g_signbits_variant;
     const int per_sm = (var >> 8) ? (var >> 8) : 32;          // blocks per SM to launch (tools/tune_signbits.py)
@@ -310,23 +341,29 @@ static inline void launch_signbits(const float *values, u32 *bits, i64 P, float 
     int blocks = (int) (want < 1 ? 1 : (want > (i64) sms * per_sm ? (i64) sms * per_sm : want));
     stream_timer_mark(stream);
     switch (var & 0xff) {
-        case 1: ISX_LAUNCH((k_signbits_t<false, 8>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
-        case 3: ISX_LAUNCH((k_signbits_t<true, 4>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
-        case 4: ISX_LAUNCH((k_signbits_t<false, 4>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
-        case 5: ISX_LAUNCH((k_signbits_t<true, 1>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
-        // default: 256-bit loads, 2 in flight per lane -- 6.0 TB/s at 512^3, 6.6 TB/s at 1024^3 on B200
-        default: ISX_LAUNCH((k_signbits_t<true, 2>), blocks, 256, 0, stream, values, bits, P, level, pad); break;
+        case 1: ISX_LAUNCH((k_signbits_t<false, 8>), blocks, 256, 0, stream, values, bits, sum, P, level, pad); break;
+        case 3: ISX_LAUNCH((k_signbits_t<true, 4>), blocks, 256, 0, stream, values, bits, sum, P, level, pad); break;
+        case 4: ISX_LAUNCH((k_signbits_t<false, 4>), blocks, 256, 0, stream, values, bits, sum, P, level, pad); break;
+        case 5: ISX_LAUNCH((k_signbits_t<true, 1>), blocks, 256, 0, stream, values, bits, sum, P, level, pad); break;
+        // default: 256-bit loads, 2 in flight per lane -- 5.9 TB/s at 512^3, 6.5 TB/s at 1024^3 on B200.  Measured and
+        // dropped (profiles/r2_signbits_variants.txt): software-pipelined loads (6.3 TB/s) and per-warp TMA rings of
+        // cp.async.bulk + mbarrier stages (5.7-6.4 TB/s): the plain loop already sits at the copy peak of the part
+        default: ISX_LAUNCH((k_signbits_t<true, 2>), blocks, 256, 0, stream, values, bits, sum, P, level, pad); break;
     }
     stream_timer_mark(stream);
 }
-static inline size_t signbits_words(i64 P) { return (size_t) (((P >> 7) + 2) << 2); }
+// u32 words of the sign-bit array (incl. one zero group of padding) followed by the per-span summary bytes
+static inline size_t signbits_bit_words(i64 P) { return (size_t) (((P >> 7) + 2) << 2); }
+static inline size_t signbits_words(i64 P) { return signbits_bit_words(P) + (size_t) (((P >> 7) + 2 + 3) >> 2) + 4; }
+static inline unsigned char *span_sum_of(u32 *bits, i64 P) { return reinterpret_cast<unsigned char *>(bits + signbits_bit_words(P)); }
+static inline const unsigned char *span_sum_of(const u32 *bits, i64 P) { return reinterpret_cast<const unsigned char *>(bits + signbits_bit_words(P)); }
 // volume pass of an implicit field (timed like the streaming kernel)
 static inline void launch_sdf_bits(const DenseParams &p, u32 *bits, cudaStream_t stream) {
-    const i64 nwords = (i64) signbits_words(p.P);
+    const i64 nwords = (i64) signbits_bit_words(p.P);
     i64 want = (nwords + 255) / 256;
     const i64 cap = (i64) device_sms() * 64;
     stream_timer_mark(stream);
-    ISX_LAUNCH(k_sdf_bits, (int) (want > cap ? cap : want), 256, 0, stream, p, bits);
+    ISX_LAUNCH(k_sdf_bits, (int) (want > cap ? cap : want), 256, 0, stream, p, bits, span_sum_of(bits, p.P));
     stream_timer_mark(stream);
 }
 
@@ -570,54 +607,172 @@ __device__ __forceinline__ SpanRows span_rows(const u32 *__restrict__ bits, cons
     return q;
 }
 
-// Threads cover (y, c4) of a plane; blockIdx.y selects a chunk of RC_XCHUNK consecutive x planes that the
-// thread marches through with a rolling two-plane window, so every row of the bit volume is fetched from
-// L2 about once (as row y of plane x+1, reused as plane x of the next step; row y+1 comes from L1).
-struct SpanQuad { uint4 v; u32 nx; };   // 128 sign bits + the following word (bit 0 = z+1 neighbour of the last point)
-
-__device__ __forceinline__ SpanQuad load_quad(const uint4 *row, u32 c4, bool last) {
-    SpanQuad q;
-    q.v = __ldg(row + c4);
-    q.nx = last ? 0u : __ldg(reinterpret_cast<const u32 *>(row + c4 + 1));
+// Summary rows round the cells of point row (x, y): (x,y), (x,y+1), (x+1,y), (x+1,y+1); a missing row aliases an
+// existing one, exactly like the bit rows of span_rows().
+struct SumRows { const unsigned char *a, *b, *c, *d; };
+__device__ __forceinline__ SumRows sum_rows(const unsigned char *__restrict__ sum, const DenseParams &p, u32 x, u32 y, u32 spr) {
+    SumRows q;
+    q.a = sum + ((size_t) x * (u32) p.g.Y + y) * spr;
+    q.b = q.a + (y + 1u < (u32) p.g.Y ? spr : 0u);
+    const size_t dx = x + 1u < (u32) p.g.X ? (size_t) (u32) p.g.Y * spr : 0;
+    q.c = q.a + dx;
+    q.d = q.b + dx;
     return q;
 }
+// True if span c4 of the row provably owns no entry: its 4 x 128 sign bits and the z+1 neighbours of its last points
+// are all equal.  Conservative (a mixed neighbour span may still start with the right bit): spans that fail the test
+// are classified from the bits (span_detail), so the result is exact either way.
+__device__ __forceinline__ bool span_provably_empty(const SumRows &q, u32 c4, bool last) {
+    const u32 v = __ldg(q.a + c4);
+    if (v >= SUM_MIXED || __ldg(q.b + c4) != v || __ldg(q.c + c4) != v || __ldg(q.d + c4) != v) return false;
+    if (last) return true;
+    return __ldg(q.a + c4 + 1) == v && __ldg(q.b + c4 + 1) == v && __ldg(q.c + c4 + 1) == v && __ldg(q.d + c4 + 1) == v;
+}
+template <int G> struct SumWord;
+template <> struct SumWord<8> { using T = unsigned long long; static constexpr T ONES = 0x0101010101010101ull; };
+template <> struct SumWord<4> { using T = u32; static constexpr T ONES = 0x01010101u; };
+template <> struct SumWord<1> { using T = unsigned char; static constexpr T ONES = 1u; };
 
-static __global__ void __launch_bounds__(256) k_rowcount128(const u32 *__restrict__ bits, DenseParams p, u32 *__restrict__ row_count,
-                                                            unsigned char *__restrict__ span_cnt, u32 xchunk) {
-    const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
-    const u32 idx = blockIdx.x * 256u + threadIdx.x;
-    if (idx >= Y * spr) return;
-    const u32 y = idx / spr, c4 = idx - y * spr;
-    const bool hasY = y + 1u < Y, last = c4 + 1u == spr;
-    const u32 dy = hasY ? spr : 0u;
-    const u32 x_begin = blockIdx.y * xchunk;
-    const u32 x_end = min(x_begin + xchunk, X);
-    const size_t plane4 = (size_t) Y * spr;                       // uint4 per x plane
-    const uint4 *row = reinterpret_cast<const uint4 *>(bits) + (size_t) x_begin * plane4 + (size_t) y * spr;
-    SpanQuad A = load_quad(row, c4, last), B = load_quad(row + dy, c4, last);
-    for (u32 x = x_begin; x < x_end; x++) {
-        const bool hasX = x + 1u < X;
-        const uint4 *nrow = row + (hasX ? plane4 : 0);           // missing plane aliases the current one
-        const SpanQuad Cq = load_quad(nrow, c4, last), Dq = load_quad(nrow + dy, c4, last);
-        u32 any = (A.v.x | A.v.y | A.v.z | A.v.w) | (B.v.x | B.v.y | B.v.z | B.v.w) | (Cq.v.x | Cq.v.y | Cq.v.z | Cq.v.w) |
-                  (Dq.v.x | Dq.v.y | Dq.v.z | Dq.v.w);
-        u32 all = (A.v.x & A.v.y & A.v.z & A.v.w) & (B.v.x & B.v.y & B.v.z & B.v.w) & (Cq.v.x & Cq.v.y & Cq.v.z & Cq.v.w) &
-                  (Dq.v.x & Dq.v.y & Dq.v.z & Dq.v.w);
-        if (!last) {
-            any |= (A.nx | B.nx | Cq.nx | Dq.nx) & 1u;
-            if (!(A.nx & B.nx & Cq.nx & Dq.nx & 1u)) all &= ~1u;
+// Entry count of every point row, from the span summary: one thread per row; G spans are tested per load (G divides
+// the spans per row) and >98 % of a typical volume is rejected with four loads per G*128 points; only spans round the
+// surface touch the sign bits.  Writes row_count[r] for every row (no atomics, nothing to zero).
+template <int G>
+static __global__ void __launch_bounds__(256) k_rowcount_sum(const u32 *__restrict__ bits, const unsigned char *__restrict__ sum, DenseParams p,
+                                                             u32 *__restrict__ row_count) {
+    using T = typename SumWord<G>::T;
+    const u32 r = blockIdx.x * 256u + threadIdx.x;
+    if (r >= p.R) return;
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
+    const u32 x = r / Y, y = r - x * Y;
+    const SumRows q = sum_rows(sum, p, x, y, spr);
+    u32 n = 0;
+    for (u32 g0 = 0; g0 < spr; g0 += G) {
+        const T A = __ldg(reinterpret_cast<const T *>(q.a + g0)), B = __ldg(reinterpret_cast<const T *>(q.b + g0));
+        const T C = __ldg(reinterpret_cast<const T *>(q.c + g0)), D = __ldg(reinterpret_cast<const T *>(q.d + g0));
+        bool empty = A == B && A == C && A == D && (A == (T) 0 || A == SumWord<G>::ONES);
+        if (empty && g0 + G < spr) {
+            const u32 v = (u32) (A & (T) 0xff);
+            empty = __ldg(q.a + g0 + G) == v && __ldg(q.b + g0 + G) == v && __ldg(q.c + g0 + G) == v && __ldg(q.d + g0 + G) == v;
         }
-        if (!(any == 0u || all == 0xffffffffu)) {
-            SpanRows q = span_rows(bits, p, x, y, spr);
-            q.last = last;
-            const u32 n = span_detail(q, x * Y + y, c4, Z, nullptr, 0, 0);
-            if (n) {
-                atomicAdd(&row_count[x * Y + y], n);
-                span_cnt[(size_t) (x * Y + y) * spr + c4] = (unsigned char) n;   // <= 128; the array is zero-initialised
+        if (empty) continue;
+#pragma unroll 1
+        for (u32 c4 = g0; c4 < g0 + G; c4++) {
+            const bool last = c4 + 1u == spr;
+            if (span_provably_empty(q, c4, last)) continue;
+            SpanRows qb = span_rows(bits, p, x, y, spr);
+            qb.last = last;
+            n += span_detail(qb, r, c4, Z, nullptr, 0, 0);
+        }
+    }
+    row_count[r] = n;
+}
+
+// Bit c4 set <=> span c4 of the row may own entries (rows of at most 32 spans).  G spans are tested per load.
+template <int G>
+__device__ __forceinline__ u32 row_span_mask(const SumRows &q, u32 spr) {
+    using T = typename SumWord<G>::T;
+    u32 m = 0;
+    for (u32 g0 = 0; g0 < spr; g0 += G) {
+        const T A = __ldg(reinterpret_cast<const T *>(q.a + g0)), B = __ldg(reinterpret_cast<const T *>(q.b + g0));
+        const T C = __ldg(reinterpret_cast<const T *>(q.c + g0)), D = __ldg(reinterpret_cast<const T *>(q.d + g0));
+        bool empty = A == B && A == C && A == D && (A == (T) 0 || A == SumWord<G>::ONES);
+        if (empty && g0 + G < spr) {
+            const u32 v = (u32) (A & (T) 0xff);
+            empty = __ldg(q.a + g0 + G) == v && __ldg(q.b + g0 + G) == v && __ldg(q.c + g0 + G) == v && __ldg(q.d + g0 + G) == v;
+        }
+        if (empty) continue;
+#pragma unroll 1
+        for (u32 c4 = g0; c4 < g0 + G; c4++)
+            if (!span_provably_empty(q, c4, c4 + 1u == spr)) m |= 1u << c4;
+    }
+    return m;
+}
+
+// Count, rows of <= 32 spans: a block takes 256 consecutive rows.  Stage 1, thread per row: span mask from the summary.
+// Stage 2: the candidate spans of the block are listed in shared memory and classified with one thread per SPAN (the
+// per-row loop left most lanes of a warp idle while one row worked through its spans).
+// Stage 3, thread per row: row_count[r] = sum over the row's spans (every row is written: no atomics, nothing to zero);
+// rows with candidate spans also write their per-span counts for the fill pass (span_cnt needs no zeroing either: the
+// fill pass only reads the rows that own entries).
+constexpr u32 RC_ROWS = 256;
+template <int G>
+static __global__ void __launch_bounds__(RC_ROWS) k_rowcount_blk(const u32 *__restrict__ bits, const unsigned char *__restrict__ sum, DenseParams p,
+                                                                 u32 *__restrict__ row_count, unsigned char *__restrict__ span_cnt) {
+    __shared__ u32 sw[33];
+    __shared__ unsigned short s_item[RC_ROWS * 32];
+    __shared__ unsigned char s_n[RC_ROWS * 32];
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
+    const u32 r0 = blockIdx.x * RC_ROWS, r = r0 + threadIdx.x;
+    u32 mask = 0;
+    if (r < p.R) {
+        const u32 x = r / Y, y = r - x * Y;
+        mask = row_span_mask<G>(sum_rows(sum, p, x, y, spr), spr);
+    }
+    const u32 cnt = __popc(mask);
+    u32 total;
+    const u32 ex0 = block_exclusive_scan(cnt, &total, sw);
+    {
+        u32 m = mask, e = ex0;
+        while (m) {
+            const u32 c4 = __ffs(m) - 1;
+            m &= m - 1;
+            s_item[e++] = (unsigned short) (threadIdx.x | (c4 << 8));
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < total; i += RC_ROWS) {
+        const u32 it = s_item[i], r2 = r0 + (it & 255u), c4 = it >> 8;
+        const u32 x = r2 / Y, y = r2 - x * Y;
+        SpanRows qb = span_rows(bits, p, x, y, spr);
+        qb.last = c4 + 1u == spr;
+        const u32 n = span_detail(qb, r2, c4, Z, nullptr, 0, 0);
+        s_n[i] = (unsigned char) n;                       // <= 128
+    }
+    __syncthreads();
+    if (r < p.R) {
+        u32 n = 0;
+        if (mask) {                                       // rows without candidate spans own no entry: the fill pass never reads their counts
+            unsigned char *rc = span_cnt + (size_t) r * spr;
+            u32 i = ex0;
+            for (u32 c4 = 0; c4 < spr; c4++) {
+                const u32 k = (mask >> c4) & 1u ? s_n[i++] : 0u;
+                rc[c4] = (unsigned char) k;
+                n += k;
             }
         }
-        A = Cq; B = Dq;
-        row += plane4;
+        row_count[r] = n;
+    }
+}
+
+// Fill, rows of <= 32 spans: one thread per row that owns entries (no grid-stride loop: a stride that is a multiple of Y
+// would hand every full-face row of a CSG box to the same threads); only the spans with a non-zero count are
+// re-classified.  (Listing the spans in shared memory and filling with one thread per span, like the count pass,
+// was measured slower: 54 vs 40 us at 1024^3, 362 vs 120 us at 2048^3.)  HEAVY rows -- a row lying in an axis-aligned
+// face owns up to Z entries -- are appended to a list and filled by k_rowfill_heavy with one warp per row.
+constexpr u32 FILL_HEAVY = 160;   // entries per row above which the row goes to the heavy list
+static __global__ void __launch_bounds__(128) k_rowfill_cnt(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
+                                                            const unsigned char *__restrict__ span_cnt, uint2 *__restrict__ entries, u32 cap,
+                                                            u32 *__restrict__ heavy_list, u32 heavy_cap, u32 *__restrict__ n_heavy) {
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R) return;
+    u32 off = row_start[r];
+    const u32 end = row_start[r + 1];
+    if (off == end) return;
+    if (end - off > FILL_HEAVY) {
+        const u32 slot = atomicAdd(n_heavy, 1u);
+        if (slot < heavy_cap) heavy_list[slot] = r;   // heavy_cap >= cap / FILL_HEAVY + 1 always suffices when S <= cap
+        return;
+    }
+    const u32 x = r / Y, y = r - x * Y;
+    SpanRows q = span_rows(bits, p, x, y, spr);
+    const unsigned char *rc = span_cnt + (size_t) r * spr;
+    for (u32 c4 = 0; c4 < spr && off < end; c4++) {
+        const u32 n = rc[c4];
+        if (!n) continue;
+        q.last = c4 + 1u == spr;
+        span_detail(q, r, c4, Z, entries, cap, off);
+        off += n;
     }
 }
 
@@ -672,9 +827,8 @@ static __global__ void __launch_bounds__(256) k_scan_rows(u32 *__restrict__ data
 // every full-face row of a CSG box to the same threads); only the mixed spans (count byte != 0) are
 // re-classified.  HEAVY rows -- a row lying in an axis-aligned face owns up to Z entries -- are appended to a
 // list and filled by k_rowfill_heavy with one warp per row.
-constexpr u32 FILL_HEAVY = 160;   // entries per row above which the row goes to the heavy list
 static __global__ void __launch_bounds__(128) k_rowfill128(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
-                                                           const unsigned char *__restrict__ span_cnt, uint2 *__restrict__ entries, u32 cap,
+                                                           const unsigned char *__restrict__ sum, uint2 *__restrict__ entries, u32 cap,
                                                            u32 *__restrict__ heavy_list, u32 heavy_cap, u32 *__restrict__ n_heavy) {
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -689,13 +843,12 @@ static __global__ void __launch_bounds__(128) k_rowfill128(const u32 *__restrict
     }
     const u32 x = r / Y, y = r - x * Y;
     SpanRows q = span_rows(bits, p, x, y, spr);
-    const unsigned char *rc = span_cnt + (size_t) r * spr;
+    const SumRows qs = sum_rows(sum, p, x, y, spr);
     for (u32 c4 = 0; c4 < spr && off < end; c4++) {
-        const u32 n = rc[c4];
-        if (!n) continue;
-        q.last = c4 + 1u == spr;
-        span_detail(q, r, c4, Z, entries, cap, off);
-        off += n;
+        const bool last = c4 + 1u == spr;
+        if (span_provably_empty(qs, c4, last)) continue;
+        q.last = last;
+        off += span_detail(q, r, c4, Z, entries, cap, off);
     }
 }
 
@@ -892,29 +1045,37 @@ static __global__ void __launch_bounds__(256) k_grid_points(Geom g, float *__res
 }
 
 static inline u32 compact_heavy_cap(u32 cap) { return cap / FILL_HEAVY + 2; }
-// Enqueue the compaction stage: bits -> entries (ordered) + row_start + counters[C_S].
-// desc must hold compact_desc_count(p) zeroed descriptors; counters, row_start and span_cnt (one byte per
-// 128-point span, compact_span_bytes(p)) zeroed.
+// Enqueue the compaction stage: bits (+ the span summary behind them) -> entries (ordered) + row_start + counters[C_S].
+// desc must hold compact_desc_count(p) zeroed descriptors; counters zeroed; span_cnt: compact_span_bytes(p), not initialised.
 static inline void launch_compact(const u32 *bits, const DenseParams &p, uint2 *entries, u32 cap, u32 *row_start, u64 *desc,
                                   u32 *counters, unsigned char *span_cnt, u32 *heavy_list, cudaStream_t stream) {
     if (compact128_ok(p)) {
         const u32 spr = (u32) (p.g.Z >> 7);
-        // x planes marched per thread: keep >= ~1M threads in flight, at most 8 planes per thread
-        const u64 nsp = (u64) p.R * spr;
-        u32 xchunk = (u32) (nsp >> 20);
-        xchunk = xchunk < 1 ? 1 : (xchunk > 8 ? 8 : xchunk);
-        dim3 grid(((u32) p.g.Y * spr + 255) / 256, ((u32) p.g.X + xchunk - 1) / xchunk);
-        ISX_LAUNCH(k_rowcount128, grid, 256, 0, stream, bits, p, row_start, span_cnt, xchunk);
-        ISX_LAUNCH(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+        const unsigned char *sum = span_sum_of(bits, p.P);
         const u32 heavy_cap = compact_heavy_cap(cap);
-        ISX_LAUNCH(k_rowfill128, (p.R + 127u) / 128u, 128, 0, stream, bits, p, row_start, span_cnt, entries, cap, heavy_list, heavy_cap,
-                   counters + C_NHEAVY);
+        if (spr <= 32u) {       // block-cooperative count / fill (thread per candidate span)
+            constexpr u32 RF_ROWS = 128;
+            const u32 rb = (p.R + RC_ROWS - 1u) / RC_ROWS, fb = (p.R + RF_ROWS - 1u) / RF_ROWS;
+            if (spr % 8u == 0u) ISX_LAUNCH(k_rowcount_blk<8>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
+            else if (spr % 4u == 0u) ISX_LAUNCH(k_rowcount_blk<4>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
+            else ISX_LAUNCH(k_rowcount_blk<1>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
+            ISX_LAUNCH(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+            ISX_LAUNCH(k_rowfill_cnt, fb, RF_ROWS, 0, stream, bits, p, row_start, span_cnt, entries, cap, heavy_list, heavy_cap, counters + C_NHEAVY);
+        } else {                // very long rows (Z > 4096): thread per row
+            const u32 rb = (p.R + 255u) / 256u;
+            if (spr % 8u == 0u) ISX_LAUNCH(k_rowcount_sum<8>, rb, 256, 0, stream, bits, sum, p, row_start);
+            else if (spr % 4u == 0u) ISX_LAUNCH(k_rowcount_sum<4>, rb, 256, 0, stream, bits, sum, p, row_start);
+            else ISX_LAUNCH(k_rowcount_sum<1>, rb, 256, 0, stream, bits, sum, p, row_start);
+            ISX_LAUNCH(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+            ISX_LAUNCH(k_rowfill128, (p.R + 127u) / 128u, 128, 0, stream, bits, p, row_start, sum, entries, cap, heavy_list, heavy_cap,
+                       counters + C_NHEAVY);
+        }
         ISX_LAUNCH(k_rowfill_heavy, 148 * 4, 256, 0, stream, bits, p, row_start, entries, cap, heavy_list, heavy_cap, counters + C_NHEAVY);
     } else {
         ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, bits, p, entries, cap, row_start, desc, counters);
     }
 }
-static inline size_t compact_span_bytes(const DenseParams &p) { return compact128_ok(p) ? (size_t) p.R * (size_t) (p.g.Z >> 7) + 16 : 16; }
+static inline size_t compact_span_bytes(const DenseParams &p) { return compact128_ok(p) && (p.g.Z >> 7) <= 32 ? (size_t) p.R * (size_t) (p.g.Z >> 7) + 16 : 16; }
 static inline size_t compact_desc_count(const DenseParams &p) {
     size_t a = (size_t) p.NQ / CP_TILE + 2, b = (size_t) p.R / RS_TILE + 2;
     return a > b ? a : b;

@@ -46,7 +46,7 @@ struct McBuffers {
     unsigned char *used;   // 3 per entry
     u32 *tri_off, *cand_info;
     u64 *descT, *descU, *descV;
-    unsigned char *span_cnt;   // entries per 128-point span (span fast path)
+    unsigned char *span_cnt;   // entries per candidate 128-point span (written by the count pass, read by the fill pass)
     u32 *heavy_list;           // rows filled cooperatively (k_rowfill_heavy)
     size_t zero_bytes;       // bytes from `counters` that one memset clears at the start of a call
     u32 *bdelta;   // per entry: sort bucket (layer offset + sub-bucket) of its 3 owned edge vertices, one byte each
@@ -63,7 +63,6 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.descV = c.take<u64>(3 * cap / UQ_TILE + 2);
     SegHead::carve(c, (size_t) sort_buckets(p), &b.seg);
     b.row_start = c.take<u32>((size_t) p.R + 2);   // accumulates the per-row entry counts before it is scanned
-    b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
     b.used = c.take<unsigned char>(3 * (cap + 2));
     b.zero_bytes = (size_t) ((char *) (b.used + 3 * (cap + 2)) - (char *) b.counters);
     // --- the rest is fully overwritten before it is read ---
@@ -76,6 +75,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.cand_info = c.take<u32>(cap + 1);
     b.bdelta = c.take<u32>(cap + 1);
     b.heavy_list = c.take<u32>(compact_heavy_cap((u32) cap));
+    b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
     if (out) *out = b;
     return c.bytes();
 }
@@ -600,20 +600,21 @@ static int enqueue_signbits(const float *values, const DenseParams &p, const McB
         launch_sdf_bits(p, b.bits, stream);
         return OK;
     }
+    unsigned char *sum = span_sum_of(b.bits, p.P);
     if (!h.event) {
-        launch_signbits(values, b.bits, p.P, p.level, stream);
+        launch_signbits(values, b.bits, sum, p.P, p.level, stream);
         return OK;
     }
     if ((plane & 255) != 0 || h.lo < 0 || h.hi < 0 || h.lo + h.hi >= p.g.X) {   // pieces must be multiples of 256 points
         ISX_CUDA(cudaStreamWaitEvent(stream, h.event, 0));
-        launch_signbits(values, b.bits, p.P, p.level, stream);
+        launch_signbits(values, b.bits, sum, p.P, p.level, stream);
         return OK;
     }
     const i64 lo = h.lo * plane, hi = h.hi * plane, mid = p.P - lo - hi;
-    launch_signbits(values + lo, b.bits + (lo >> 5), mid, p.level, stream, hi == 0);
+    launch_signbits(values + lo, b.bits + (lo >> 5), sum + (lo >> 7), mid, p.level, stream, hi == 0);
     ISX_CUDA(cudaStreamWaitEvent(stream, h.event, 0));
-    if (lo) launch_signbits(values, b.bits, lo, p.level, stream, false);
-    if (hi) launch_signbits(values + lo + mid, b.bits + ((lo + mid) >> 5), hi, p.level, stream, true);
+    if (lo) launch_signbits(values, b.bits, sum, lo, p.level, stream, false);
+    if (hi) launch_signbits(values + lo + mid, b.bits + ((lo + mid) >> 5), sum + ((lo + mid) >> 7), hi, p.level, stream, true);
     return OK;
 }
 static void enqueue_compact(const DenseParams &p, const McBuffers &b, u32 cap, cudaStream_t stream) {
