@@ -125,32 +125,30 @@ __device__ __forceinline__ u32 sub_bucket(const DenseParams &p, i64 xb /* global
     return p.gy + k;
 }
 
-template <bool IMPLICIT>
-__device__ __forceinline__ u32 owned_buckets(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, u32 own) {
+// v0 / vz / vy / vx: the values at the entry's point and at its +z / +y / +x neighbours (only those of owned edges are read)
+__device__ __forceinline__ u32 owned_buckets(const DenseParams &p, u32 r, u32 own, float v0, float vz, float vy, float vx) {
     if (!own) return 0u;
-    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
+    const u32 Y = (u32) p.g.Y;
     const u32 x = r / Y, y = r - x * Y;
-    const i64 n = (i64) r * Z + z;
     const u32 xg = x + (u32) p.g.x_off;
-    const float v0 = field_at<IMPLICIT>(values, p, n, 0, x, y, z);
     const float px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
     const float py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
     u32 out = 0;
     if (own & 1u) {
-        const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, 1, x, y, z + 1), p.level);
+        const float t = edge_t(v0, vz, p.level);
         const float xv = lerp_ref(t, px0, px0);
         const u32 code = xv < px0 ? 0u : 1u;
         out |= code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py0), y) << 2);
     }
     if (own & 2u) {
-        const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, Z, x, y + 1, z), p.level);
+        const float t = edge_t(v0, vy, p.level);
         const float xv = lerp_ref(t, px0, px0);
         const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
         const u32 code = xv < px0 ? 0u : 1u;
         out |= (code | (sub_bucket(p, (i64) xg + code - 1, xv, lerp_ref(t, py0, py1), y) << 2)) << 8;
     }
     if (own & 4u) {
-        const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, p.YZ, x + 1, y, z), p.level);
+        const float t = edge_t(v0, vx, p.level);
         const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
         const float xv = lerp_ref(t, px0, px1);
         const u32 code = xv >= px1 ? 2u : (xv < px0 ? 0u : 1u);
@@ -164,6 +162,8 @@ __device__ __forceinline__ u32 bucket_of(u32 x, u32 byte, u32 nsub) { return (x 
 // ---------------------------------------------------------------------------------------------
 // K3: one thread per entry that is a valid cell.
 // ---------------------------------------------------------------------------------------------
+// The kernel is bound by the latency of its dependent loads (entry -> row bounds -> binary searches -> neighbour
+// entries, and the value gathers from HBM), so the value loads are issued first and overlap the searches.
 template <bool IMPLICIT>
 __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ values, DenseParams p, int method,
                                                    const uint2 *__restrict__ entries, const u32 *__restrict__ row_start,
@@ -172,26 +172,38 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
                                                    unsigned char *__restrict__ used, u32 *__restrict__ bdelta) {
     const u32 S = counters[C_S];
     if (S > cap) return;
-    const u32 Y = (u32) p.g.Y;
+    const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const uint2 e = entries[s];
-        const u32 w = e.y;
-        bdelta[s] = owned_buckets<IMPLICIT>(values, p, e.x, ent_z(w), ent_own(w));
-        if (!ent_cell(w) || ent_case(w) == 0u || ent_case(w) == 255u) {
+        const u32 w = e.y, r = e.x, z = ent_z(w), cs = ent_case(w), own = ent_own(w);
+        const bool is_cell = ent_cell(w) && cs != 0u && cs != 255u;
+        CellData c;
+        if (is_cell) {
+            load_cell_values<IMPLICIT>(values, p, r, z, c);
+        } else if (own) {
+            const u32 x = r / Y, y = r - x * Y;
+            const i64 n = (i64) r * Z + z;
+            c.v[0] = field_at<IMPLICIT>(values, p, n, 0, x, y, z);
+            c.v[1] = (own & 1u) ? field_at<IMPLICIT>(values, p, n, 1, x, y, z + 1) : 0.f;
+            c.v[2] = (own & 2u) ? field_at<IMPLICIT>(values, p, n, Z, x, y + 1, z) : 0.f;
+            c.v[4] = (own & 4u) ? field_at<IMPLICIT>(values, p, n, p.YZ, x + 1, y, z) : 0.f;
+        }
+        if (!is_cell) {
+            bdelta[s] = owned_buckets(p, r, own, c.v[0], c.v[1], c.v[2], c.v[4]);
             ntri[s] = 0;
             trimask[s] = 0;
             continue;
         }
-        const u32 r = e.x, z = ent_z(w), cs = ent_case(w);
-        const u32 lbY = row_lower_bound(entries, row_start[r + 1], row_start[r + 2], z);
-        const u32 lbX = row_lower_bound(entries, row_start[r + Y], row_start[r + Y + 1], z);
-        const u32 lbXY = row_lower_bound(entries, row_start[r + Y + 1], row_start[r + Y + 2], z);
+        const u32 rsY0 = row_start[r + 1], rsY1 = row_start[r + 2], rsX0 = row_start[r + Y], rsX1 = row_start[r + Y + 1],
+                  rsXY1 = row_start[r + Y + 2];
+        const u32 lbY = row_lower_bound(entries, rsY0, rsY1, z);
+        const u32 lbX = row_lower_bound(entries, rsX0, rsX1, z);
+        const u32 lbXY = row_lower_bound(entries, rsX1, rsXY1, z);
         nb[s] = lbY;                    // structure of arrays (three planes of `cap` entries): coalesced 4-byte accesses
         nb[cap + s] = lbX;
         nb[2 * (size_t) cap + s] = lbXY;
+        bdelta[s] = owned_buckets(p, r, own, c.v[0], c.v[1], c.v[2], c.v[4]);
 
-        CellData c;
-        load_cell_values<IMPLICIT>(values, p, r, z, c);
         const u32 status = edge_mask_of_case(cs);
         u32 slot[12];
         cell_edge_slots(entries, s, z, lbY, lbX, lbXY, S, slot);
@@ -304,6 +316,24 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
         }
 #pragma unroll
         for (int j = 0; j < SE_ITEMS; j++) {
+            sumT += nt[j];
+            sumU += __popc(um[j]);
+        }
+        u32 totT, totU;
+        u32 exT = block_exclusive_scan(sumT, &totT, sw);
+        u32 exU = block_exclusive_scan(sumU, &totU, sw);
+        const u32 warp = threadIdx.x >> 5;
+        // warps 0 / 1 look back for the tile's prefixes; the histogram of the tile (shared-memory atomics) is built by the
+        // other warps meanwhile and by these two afterwards, so the block does not idle at the barrier behind the look-back
+        if (warp == 0) {
+            u32 pre = lookback_exclusive(descT, 1, tile, totT, 1u);
+            if (threadIdx.x == 0) s_preT = pre;
+        } else if (warp == 1) {
+            u32 pre = lookback_exclusive(descU, 1, tile, totU, 1u);
+            if ((threadIdx.x & 31) == 0) s_preU = pre;
+        }
+#pragma unroll
+        for (int j = 0; j < SE_ITEMS; j++) {
             if (um[j]) {   // x-bucket histogram of the vertices this entry owns (segsort.cuh)
                 const u32 x = ex_[j] / Y, bd = bd_[j];
 #pragma unroll
@@ -314,19 +344,6 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
                         else atomicAdd(&bucket_count[bkt], 1u);
                     }
             }
-            sumT += nt[j];
-            sumU += __popc(um[j]);
-        }
-        u32 totT, totU;
-        u32 exT = block_exclusive_scan(sumT, &totT, sw);
-        u32 exU = block_exclusive_scan(sumU, &totU, sw);
-        const u32 warp = threadIdx.x >> 5;
-        if (warp == 0) {
-            u32 pre = lookback_exclusive(descT, 1, tile, totT, 1u);
-            if (threadIdx.x == 0) s_preT = pre;
-        } else if (warp == 1) {
-            u32 pre = lookback_exclusive(descU, 1, tile, totU, 1u);
-            if ((threadIdx.x & 31) == 0) s_preU = pre;
         }
         __syncthreads();
         if (threadIdx.x < WIN && s_hist[threadIdx.x]) atomicAdd(&bucket_count[win0 + threadIdx.x], s_hist[threadIdx.x]);
@@ -365,10 +382,13 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
                 }
             }
         }
-        // the block that finishes the last tile turns the bucket histogram into offsets (saves a launch)
-        __threadfence();
+        // the block that finishes the last tile turns the bucket histogram into offsets (saves a launch); one fence by the
+        // thread that takes the ticket, behind the barrier, orders the whole block's writes before it
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(&counters[C_TICKET_E], 1u) == ntiles - 1) ? 1u : 0u;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = (atomicAdd(&counters[C_TICKET_E], 1u) == ntiles - 1) ? 1u : 0u;
+        }
         __syncthreads();
         if (s_last) {
             __threadfence();
@@ -623,11 +643,12 @@ static void enqueue_compact(const DenseParams &p, const McBuffers &b, u32 cap, c
 static int enqueue_analysis(const float *values, const DenseParams &p, int method, const McBuffers &b, u32 cap, cudaStream_t stream) {
     const int sms = device_sms();
     const u32 nb = sort_buckets(p);
+    const int ct_blocks = sms * (g_tuning[4] > 0 ? g_tuning[4] : 32);
     if (p.sdf)
-        ISX_LAUNCH(k_cell_tris<true>, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+        ISX_LAUNCH(k_cell_tris<true>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                    b.trimask, b.used, b.bdelta);
     else
-        ISX_LAUNCH(k_cell_tris<false>, sms * 8, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+        ISX_LAUNCH(k_cell_tris<false>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                    b.trimask, b.used, b.bdelta);
     ISX_LAUNCH(k_scan_entries, scan_blocks(sms), 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
                b.entries, b.bdelta, (u32) p.g.Y, sort_nsub(p), b.seg.count, nb, b.seg);
@@ -675,7 +696,7 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
                b.descV, klo, khi, n_dev, cand_cap, true, gate);
-    ISX_LAUNCH(k_emit_faces, sms * 8, 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
+    ISX_LAUNCH(k_emit_faces, sms * (g_tuning[5] > 0 ? g_tuning[5] : 16), 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
                s.cand_rank, F, entry_cap, gate);
     ISX_CUDA(cudaGetLastError());
     return OK;

@@ -399,13 +399,18 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                         const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
                         if (e1 - s1 > (u32) SEG_GROUP_MAX) continue;   // member of a large group: nested stage below
                         const u32 x = sk[2 * CAP + i], y = sk[CAP + i], z = sk[i];
-                        u32 r = 0;
-                        for (u32 j = s1; j < e1; j++) {
-                            const u32 lj = ord[j];
+                        // (the loop is bound by the latency of its dependent shared-memory loads -- ord[j], then the keys
+                        // of that element: four members per step keep four such chains in flight)
+                        auto before = [&](u32 lj) -> u32 {
                             const u32 xj = sk[2 * CAP + lj], yj = sk[CAP + lj], zj = sk[lj];
-                            const bool before = xj < x || (xj == x && (yj < y || (yj == y && (zj < z || (zj == z && lj < i)))));
-                            r += before ? 1u : 0u;
+                            return (xj < x || (xj == x && (yj < y || (yj == y && (zj < z || (zj == z && lj < i)))))) ? 1u : 0u;
+                        };
+                        u32 r = 0, j = s1;
+                        for (; j + 4 <= e1; j += 4) {
+                            const u32 l0 = ord[j], l1 = ord[j + 1], l2 = ord[j + 2], l3 = ord[j + 3];
+                            r += before(l0) + before(l1) + before(l2) + before(l3);
                         }
+                        for (; j < e1; j++) r += before(ord[j]);
                         dst[q] = s1 + r;
                     }
                 }
