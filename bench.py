@@ -313,13 +313,17 @@ def run_ours(args):
         view = grid.values_view()
         for a in range(0, n, 64):
             host[a:a + 64].copy_(view[a:a + 64])
-        dbuf = torch.empty((n, n, n), dtype=torch.float32, device=dev)
+        hv_pin = torch.empty((nV + nV // 8 + 1024, 3), dtype=torch.float32, pin_memory=True)   # pinned landing buffers for the mesh
+        hf_pin = torch.empty((nT + nT // 8 + 1024, 3), dtype=torch.int32, pin_memory=True)
 
         def e2e_step():
-            dbuf.copy_(host, non_blocking=True)           # H2D of this step's input
-            grid.set_values(dbuf)
+            view.copy_(host, non_blocking=True)           # H2D of this step's input, straight into the grid's storage (values_view())
             vv, ff = iso.marching_cubes(grid)
-            return vv.cpu(), ff.cpu()                     # D2H of the step's result
+            hv, hf = hv_pin[: vv.shape[0]], hf_pin[: ff.shape[0]]
+            hv.copy_(vv, non_blocking=True)               # D2H of the step's result
+            hf.copy_(ff, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return hv, hf
 
         e2e_step()
         torch.cuda.synchronize()
@@ -331,7 +335,7 @@ def run_ours(args):
         dt = (time.perf_counter() - t0) / k
         e2e = {"value": voxels / dt / 1e9, "unit": "Gvoxels/s", "ms_per_step": dt * 1e3, "steps": k,
                "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(hv.numel() * 4 + hf.numel() * 4)}
-        del host, dbuf, grid, view, hv, hf
+        del host, grid, view, hv, hf, hv_pin, hf_pin
         torch.cuda.empty_cache()
     else:
         from isoext_b200 import dist as idist
@@ -375,12 +379,18 @@ def run_ours(args):
         # ---- end to end: each rank uploads its own slab from pinned host memory and reads its mesh part back
         host = sg.owned_values().cpu().pin_memory()
         dbuf = torch.empty_like(sg.owned_values())
+        hv_pin = torch.empty((v.shape[0] + v.shape[0] // 8 + 1024, 3), dtype=torch.float32, pin_memory=True)
+        hf_pin = torch.empty((f.shape[0] + f.shape[0] // 8 + 1024, 3), dtype=f.dtype, pin_memory=True)
 
         def e2e_step():
             dbuf.copy_(host, non_blocking=True)
-            sg.set_owned_values(dbuf)
+            sg.set_owned_values(dbuf)                     # (guards the neighbours' halo pulls of the previous epoch)
             vv, ff = idist.marching_cubes(sg)
-            return vv.cpu(), ff.cpu()
+            hv, hf = hv_pin[: vv.shape[0]], hf_pin[: ff.shape[0]]
+            hv.copy_(vv, non_blocking=True)
+            hf.copy_(ff, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return hv, hf
 
         e2e_step()
         barrier()
@@ -394,7 +404,7 @@ def run_ours(args):
         dist.all_reduce(nb)
         e2e = {"value": voxels / dt / 1e9, "unit": "Gvoxels/s", "ms_per_step": dt * 1e3, "steps": k,
                "h2d_bytes_per_step": int(nb[0].item()), "d2h_bytes_per_step": int(nb[1].item())}
-        del host, dbuf
+        del host, dbuf, hv_pin, hf_pin
 
         # ---- beside it: slab cuts balanced by the measured load of the previous extraction (time-series use)
         if not args.no_balanced:

@@ -62,6 +62,30 @@ void detail_mark(const char *name, cudaStream_t s, bool begin);
         if (isx::g_detail_timing) isx::detail_mark(#kernel, (stream), false);  \
     } while (0)
 
+// Programmatic dependent launch (griddepcontrol, sm_90+): a kernel launched with ISX_LAUNCH_PDL may be scheduled while
+// the previous kernel of the stream is still draining; its blocks park at pdl_wait() -- which returns once that kernel
+// has completed and its writes are visible -- so the launch latency and the ramp-up (2-4 us per boundary, 12 boundaries
+// per extraction) overlap the predecessor's tail.  Rules: pdl_wait() is the FIRST statement of every kernel that is
+// ever launched this way (nothing produced by an earlier kernel may be touched before it); pdl_trigger() right behind it
+// lets the NEXT kernel do the same.  Both are no-ops under an ordinary launch.  g_tuning[6] = 1 switches the launch
+// attribute off (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define ISX_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                     \
+    do {                                                                                           \
+        ++isx::g_kernel_launches;                                                                  \
+        if (isx::g_detail_timing) isx::detail_mark(#kernel, (stream), true);                       \
+        cudaLaunchConfig_t cfg_ = {};                                                              \
+        cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block);                                    \
+        cfg_.dynamicSmemBytes = (smem); cfg_.stream = (stream);                                    \
+        cudaLaunchAttribute at_[1];                                                                \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
+        cfg_.attrs = at_; cfg_.numAttrs = isx::g_tuning[6] == 1 ? 0 : 1;                           \
+        cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                            \
+        if (isx::g_detail_timing) isx::detail_mark(#kernel, (stream), false);                      \
+    } while (0)
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Carves typed sub-buffers out of one caller-provided device blob (256-byte aligned pieces).

@@ -175,6 +175,7 @@ __device__ __forceinline__ void signbits_tail(const float *__restrict__ v, u32 *
 template <bool VEC8, int UNROLL>
 static __global__ void __launch_bounds__(256, 6) k_signbits_t(const float *__restrict__ v, u32 *__restrict__ bits,
                                                            unsigned char *__restrict__ sum, i64 P, float level, bool pad) {
+    pdl_trigger();   // the count pass may be scheduled while the stream drains (it waits for completion: pdl_wait)
     const u32 lane = threadIdx.x & 31;
     const i64 ngroups = P >> 7;   // full groups of 128 points
     const i64 nwarps = ((i64) gridDim.x * blockDim.x) >> 5;
@@ -229,6 +230,8 @@ static __global__ void __launch_bounds__(256, 6) k_signbits_t(const float *__res
 // (> 95 % of the words of a typical volume).  Otherwise (and for words straddling two rows) the points are evaluated.
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) k_sdf_bits(DenseParams p, u32 *__restrict__ bits, unsigned char *__restrict__ sum) {
+    pdl_wait();
+    pdl_trigger();
     // Two phases per block of 256 consecutive words.  Phase 1, thread per word: one evaluation at the middle of the
     // word decides it if the surface is provably farther than half a word (1-Lipschitz bound + float margin);
     // undecided words go to a shared list.  Phase 2, warp per listed word: the 32 lanes evaluate the 32 points at
@@ -429,6 +432,8 @@ __device__ __forceinline__ u32 chunk_classify(const u32 *__restrict__ bits, cons
 static __global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ bits, DenseParams p, uint2 *__restrict__ entries,
                                                  u32 cap, u32 *__restrict__ row_start, u64 *__restrict__ desc,
                                                  u32 *__restrict__ counters) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(&counters[C_TICKET_A], 1u);
@@ -639,6 +644,8 @@ template <> struct SumWord<1> { using T = unsigned char; static constexpr T ONES
 template <int G>
 static __global__ void __launch_bounds__(256) k_rowcount_sum(const u32 *__restrict__ bits, const unsigned char *__restrict__ sum, DenseParams p,
                                                              u32 *__restrict__ row_count) {
+    pdl_wait();
+    pdl_trigger();
     using T = typename SumWord<G>::T;
     const u32 r = blockIdx.x * 256u + threadIdx.x;
     if (r >= p.R) return;
@@ -698,6 +705,8 @@ constexpr u32 RC_ROWS = 256;
 template <int G>
 static __global__ void __launch_bounds__(RC_ROWS) k_rowcount_blk(const u32 *__restrict__ bits, const unsigned char *__restrict__ sum, DenseParams p,
                                                                  u32 *__restrict__ row_count, unsigned char *__restrict__ span_cnt) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u32 sw[33];
     __shared__ unsigned short s_item[RC_ROWS * 32];
     __shared__ unsigned char s_n[RC_ROWS * 32];
@@ -753,6 +762,8 @@ constexpr u32 FILL_HEAVY = 160;   // entries per row above which the row goes to
 static __global__ void __launch_bounds__(128) k_rowfill_cnt(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
                                                             const unsigned char *__restrict__ span_cnt, uint2 *__restrict__ entries, u32 cap,
                                                             u32 *__restrict__ heavy_list, u32 heavy_cap, u32 *__restrict__ n_heavy) {
+    pdl_wait();
+    pdl_trigger();
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.R) return;
@@ -781,6 +792,8 @@ constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = 256 * RS_ITEMS;
 static __global__ void __launch_bounds__(256) k_scan_rows(u32 *__restrict__ data, u32 n, u64 *__restrict__ desc, u32 *__restrict__ counters,
                                                           int ticket_idx, int total_idx) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
     const u32 ntiles = (n + RS_TILE - 1) / RS_TILE;
@@ -830,6 +843,8 @@ static __global__ void __launch_bounds__(256) k_scan_rows(u32 *__restrict__ data
 static __global__ void __launch_bounds__(128) k_rowfill128(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
                                                            const unsigned char *__restrict__ sum, uint2 *__restrict__ entries, u32 cap,
                                                            u32 *__restrict__ heavy_list, u32 heavy_cap, u32 *__restrict__ n_heavy) {
+    pdl_wait();
+    pdl_trigger();
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, spr = Z >> 7;
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.R) return;
@@ -857,6 +872,8 @@ static __global__ void __launch_bounds__(128) k_rowfill128(const u32 *__restrict
 static __global__ void __launch_bounds__(256) k_rowfill_heavy(const u32 *__restrict__ bits, DenseParams p, const u32 *__restrict__ row_start,
                                                               uint2 *__restrict__ entries, u32 cap, const u32 *__restrict__ heavy_list,
                                                               u32 heavy_cap, const u32 *__restrict__ n_heavy) {
+    pdl_wait();
+    pdl_trigger();
     const u32 X = (u32) p.g.X, Y = (u32) p.g.Y, Z = (u32) p.g.Z, wpr = Z >> 5;   // words per row
     const u32 lane = threadIdx.x & 31;
     const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1056,21 +1073,21 @@ static inline void launch_compact(const u32 *bits, const DenseParams &p, uint2 *
         if (spr <= 32u) {       // block-cooperative count / fill (thread per candidate span)
             constexpr u32 RF_ROWS = 128;
             const u32 rb = (p.R + RC_ROWS - 1u) / RC_ROWS, fb = (p.R + RF_ROWS - 1u) / RF_ROWS;
-            if (spr % 8u == 0u) ISX_LAUNCH(k_rowcount_blk<8>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
-            else if (spr % 4u == 0u) ISX_LAUNCH(k_rowcount_blk<4>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
-            else ISX_LAUNCH(k_rowcount_blk<1>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
-            ISX_LAUNCH(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
-            ISX_LAUNCH(k_rowfill_cnt, fb, RF_ROWS, 0, stream, bits, p, row_start, span_cnt, entries, cap, heavy_list, heavy_cap, counters + C_NHEAVY);
+            if (spr % 8u == 0u) ISX_LAUNCH_PDL(k_rowcount_blk<8>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
+            else if (spr % 4u == 0u) ISX_LAUNCH_PDL(k_rowcount_blk<4>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
+            else ISX_LAUNCH_PDL(k_rowcount_blk<1>, rb, RC_ROWS, 0, stream, bits, sum, p, row_start, span_cnt);
+            ISX_LAUNCH_PDL(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, (u32) p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+            ISX_LAUNCH_PDL(k_rowfill_cnt, fb, RF_ROWS, 0, stream, bits, p, row_start, (const unsigned char *) span_cnt, entries, cap, heavy_list, heavy_cap, counters + C_NHEAVY);
         } else {                // very long rows (Z > 4096): thread per row
             const u32 rb = (p.R + 255u) / 256u;
             if (spr % 8u == 0u) ISX_LAUNCH(k_rowcount_sum<8>, rb, 256, 0, stream, bits, sum, p, row_start);
             else if (spr % 4u == 0u) ISX_LAUNCH(k_rowcount_sum<4>, rb, 256, 0, stream, bits, sum, p, row_start);
             else ISX_LAUNCH(k_rowcount_sum<1>, rb, 256, 0, stream, bits, sum, p, row_start);
-            ISX_LAUNCH(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
+            ISX_LAUNCH_PDL(k_scan_rows, scan_blocks(148), 256, 0, stream, row_start, (u32) p.R, desc, counters, (int) C_TICKET_A, (int) C_S);
             ISX_LAUNCH(k_rowfill128, (p.R + 127u) / 128u, 128, 0, stream, bits, p, row_start, sum, entries, cap, heavy_list, heavy_cap,
                        counters + C_NHEAVY);
         }
-        ISX_LAUNCH(k_rowfill_heavy, 148 * 4, 256, 0, stream, bits, p, row_start, entries, cap, heavy_list, heavy_cap, counters + C_NHEAVY);
+        ISX_LAUNCH_PDL(k_rowfill_heavy, 148 * 4, 256, 0, stream, bits, p, (const u32 *) row_start, entries, cap, (const u32 *) heavy_list, heavy_cap, (const u32 *) (counters + C_NHEAVY));
     } else {
         ISX_LAUNCH(k_compact, (p.NQ + CP_TILE - 1) / CP_TILE, 256, 0, stream, bits, p, entries, cap, row_start, desc, counters);
     }

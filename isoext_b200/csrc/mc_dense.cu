@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
                                                    u32 cap, const u32 *__restrict__ counters, u32 *__restrict__ nb,
                                                    unsigned char *__restrict__ ntri, unsigned char *__restrict__ trimask,
                                                    unsigned char *__restrict__ used, u32 *__restrict__ bdelta) {
+    pdl_wait();
+    pdl_trigger();
     const u32 S = counters[C_S];
     if (S > cap) return;
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z;
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
                                                       u32 *__restrict__ cand_info, u64 *__restrict__ descT, u64 *__restrict__ descU,
                                                       const uint2 *__restrict__ entries, const u32 *__restrict__ bdelta,
                                                       u32 Y, u32 nsub, u32 *__restrict__ bucket_count, u32 nb, SegHead seg) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_preT, s_preU;
     // x-bucket histogram window: the entries of a tile are sorted by x, so almost all of its vertices fall
@@ -406,6 +410,8 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
                                                   const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
                                                   const u32 *__restrict__ cand_info, const u32 *__restrict__ bdelta,
                                                   CandOut out, u32 cand_cap, u32 entry_cap) {
+    pdl_wait();
+    pdl_trigger();
     const u32 S = counters[C_S];
     if (S > entry_cap || counters[C_VC] > cand_cap) return;   // single-call fast path: the host re-runs with larger buffers
     const u32 Y = (u32) p.g.Y, Z = (u32) p.g.Z, nsub = sort_nsub(p);
@@ -484,6 +490,8 @@ __global__ void __launch_bounds__(128) k_emit_faces(DenseParams p, int method, c
                                                     const unsigned char *__restrict__ trimask, const u32 *__restrict__ tri_off,
                                                     const u32 *__restrict__ cand_info, const u32 *__restrict__ cand_rank,
                                                     int *__restrict__ F, u32 entry_cap, Gate gate) {
+    pdl_wait();
+    pdl_trigger();
     const u32 S = counters[C_S];
     if (S > entry_cap || gate_bad(counters, gate)) return;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
@@ -645,12 +653,12 @@ static int enqueue_analysis(const float *values, const DenseParams &p, int metho
     const u32 nb = sort_buckets(p);
     const int ct_blocks = sms * (g_tuning[4] > 0 ? g_tuning[4] : 32);
     if (p.sdf)
-        ISX_LAUNCH(k_cell_tris<true>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+        ISX_LAUNCH_PDL(k_cell_tris<true>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                    b.trimask, b.used, b.bdelta);
     else
-        ISX_LAUNCH(k_cell_tris<false>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
+        ISX_LAUNCH_PDL(k_cell_tris<false>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
                    b.trimask, b.used, b.bdelta);
-    ISX_LAUNCH(k_scan_entries, scan_blocks(sms), 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
+    ISX_LAUNCH_PDL(k_scan_entries, scan_blocks(sms), 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
                b.entries, b.bdelta, (u32) p.g.Y, sort_nsub(p), b.seg.count, nb, b.seg);
     ISX_CUDA(cudaGetLastError());
     return OK;
@@ -677,9 +685,9 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const CandOut co{s.kx, s.ky, s.kz, s.seg.perm0, s.seg.cbucket, b.seg.count, b.seg.start, b.seg.bigoff, b.seg.cursor,
                      s.seg.bkx, s.seg.bky, s.seg.bkz, s.seg.bid, b.seg.xinvmin, b.seg.xmax};
     if (p.sdf)
-        ISX_LAUNCH(k_cand_pos<true>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
+        ISX_LAUNCH_PDL(k_cand_pos<true>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
     else
-        ISX_LAUNCH(k_cand_pos<false>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
+        ISX_LAUNCH_PDL(k_cand_pos<false>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg,
                           SegGeom{p.g.amin[0], p.g.asize[0], p.g.amin[1], p.g.asize[1], p.g.amin[2], p.g.asize[2], (u32) p.g.Xg, (u32) p.g.Y,
@@ -696,7 +704,7 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const u32 klo = host_float_key(x_lo_threshold), khi = host_float_key(x_hi_threshold);
     ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, host_nc, s.seg.perm, s.seg.skx, s.seg.sky, s.seg.skz, s.cand_rank, V, b.counters,
                b.descV, klo, khi, n_dev, cand_cap, true, gate);
-    ISX_LAUNCH(k_emit_faces, sms * (g_tuning[5] > 0 ? g_tuning[5] : 16), 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
+    ISX_LAUNCH_PDL(k_emit_faces, sms * (g_tuning[5] > 0 ? g_tuning[5] : 16), 128, 0, stream, p, method, b.entries, b.counters, b.nb, b.trimask, b.tri_off, b.cand_info,
                s.cand_rank, F, entry_cap, gate);
     ISX_CUDA(cudaGetLastError());
     return OK;

@@ -21,6 +21,8 @@ static __global__ void __launch_bounds__(256) k_unique(u32 n, const u32 *__restr
                                                 u64 *__restrict__ desc, u32 key_lo, u32 key_hi,
                                                 const u32 *__restrict__ n_dev = nullptr, u32 n_cap = 0xffffffffu,
                                                 bool keys_sorted = false, Gate gate = Gate()) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u32 sw[33];
     __shared__ u32 s_tile, s_pre;
     // the tile's new vertices have consecutive ranks: they are staged here and copied out with coalesced stores
