@@ -389,18 +389,21 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                 __syncthreads();
                 // rank of every element inside its group on the full key (ties cannot occur between different elements
                 // other than exact duplicates, which are ordered by their slot): O(group size) per element, all threads busy
-                u32 dst[CHUNKS];
+                // Threads take POSITIONS of the group-ordered list, not elements: neighbouring lanes then rank members of the
+                // same (or the next) group -- equal loop bounds instead of the largest group among 32 unrelated elements,
+                // and the loads of the loop are broadcasts.
+                u32 dst[CHUNKS], del[CHUNKS];
 #pragma unroll
                 for (int q = 0; q < CHUNKS; q++) {
-                    const u32 i = tid + (u32) q * THREADS;
+                    const u32 jp = tid + (u32) q * THREADS;
                     dst[q] = 0xffffffffu;
-                    if (i < n) {
+                    del[q] = 0;
+                    if (jp < n) {
+                        const u32 i = ord[jp];
                         const u32 g = gid[i];
                         const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
                         if (e1 - s1 > (u32) SEG_GROUP_MAX) continue;   // member of a large group: nested stage below
                         const u32 x = sk[2 * CAP + i], y = sk[CAP + i], z = sk[i];
-                        // (the loop is bound by the latency of its dependent shared-memory loads -- ord[j], then the keys
-                        // of that element: four members per step keep four such chains in flight)
                         auto before = [&](u32 lj) -> u32 {
                             const u32 xj = sk[2 * CAP + lj], yj = sk[CAP + lj], zj = sk[lj];
                             return (xj < x || (xj == x && (yj < y || (yj == y && (zj < z || (zj == z && lj < i)))))) ? 1u : 0u;
@@ -412,6 +415,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                         }
                         for (; j < e1; j++) r += before(ord[j]);
                         dst[q] = s1 + r;
+                        del[q] = i;
                     }
                 }
                 if (vary[3]) {   // list the large groups
@@ -509,7 +513,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                 if (grouped) {
 #pragma unroll
                     for (int q = 0; q < CHUNKS; q++)
-                        if (dst[q] != 0xffffffffu) gid[dst[q]] = (unsigned short) (tid + (u32) q * THREADS);   // second half of ord = result
+                        if (dst[q] != 0xffffffffu) gid[dst[q]] = (unsigned short) del[q];   // second half of ord = result
                     cur = 1;
                 }
             }
