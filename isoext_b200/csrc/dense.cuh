@@ -600,6 +600,20 @@ static __device__ __noinline__ u32 span_detail(const SpanRows q, u32 r, u32 c4, 
     return n;
 }
 
+// count-only twin of span_detail (the count pass is bound by the latency of these loads: fewer registers = more
+// spans in flight per SM)
+__device__ __forceinline__ u32 span_count(const SpanRows &q, u32 c4) {
+    SpanBits k;
+    span_load_g(q, 0, c4, k);
+    u32 n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        u32 a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca;
+        n += __popc(span_word_masks(k, j, a0, a1, b0, b1, cc0, c1, d0, d1, ez, ey, ex, ca));
+    }
+    return n;
+}
+
 __device__ __forceinline__ SpanRows span_rows(const u32 *__restrict__ bits, const DenseParams &p, u32 x, u32 y, u32 spr) {
     SpanRows q;
     q.hasY = y + 1u < (u32) p.g.Y;
@@ -703,7 +717,7 @@ __device__ __forceinline__ u32 row_span_mask(const SumRows &q, u32 spr) {
 // fill pass only reads the rows that own entries).
 constexpr u32 RC_ROWS = 256;
 template <int G>
-static __global__ void __launch_bounds__(RC_ROWS) k_rowcount_blk(const u32 *__restrict__ bits, const unsigned char *__restrict__ sum, DenseParams p,
+static __global__ void __launch_bounds__(RC_ROWS, 6) k_rowcount_blk(const u32 *__restrict__ bits, const unsigned char *__restrict__ sum, DenseParams p,
                                                                  u32 *__restrict__ row_count, unsigned char *__restrict__ span_cnt) {
     pdl_wait();
     pdl_trigger();
@@ -734,7 +748,7 @@ static __global__ void __launch_bounds__(RC_ROWS) k_rowcount_blk(const u32 *__re
         const u32 x = r2 / Y, y = r2 - x * Y;
         SpanRows qb = span_rows(bits, p, x, y, spr);
         qb.last = c4 + 1u == spr;
-        const u32 n = span_detail(qb, r2, c4, Z, nullptr, 0, 0);
+        const u32 n = span_count(qb, c4);
         s_n[i] = (unsigned char) n;                       // <= 128
     }
     __syncthreads();
