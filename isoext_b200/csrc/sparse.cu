@@ -125,6 +125,43 @@ __global__ void __launch_bounds__(128) k_sp_mc_classify(const float *__restrict_
     }
 }
 
+// Candidate de-duplication along z.  Every (cell, edge) vertex is a candidate of the position sort because cells carry
+// their own corner values; but the list is sorted by cell id, so the cell below (x, y, z-1) -- if present -- is the
+// PREVIOUS list element, and it shares the four edges of this cell's low-z face (this cell's e3, e7, e8, e11 are its
+// e1, e5, e9, e10: same end points, same direction, hence the same arithmetic).  Where the two cells hold bit-equal
+// corner values on such an edge and the lower cell emits it, this cell refers to the lower cell's candidate instead
+// of emitting a bit-identical one: a third fewer keys to sort.  Cells with different values keep their own vertex
+// (positional welding decides, as in the reference).
+//   cinfo after this pass = case | trimask << 8 | EMITTED edges << 16 | dup4 << 28   (dup4: e3, e7, e8, e11)
+__device__ __forceinline__ u32 sp_dup_edges(u32 dup4) {
+    return ((dup4 & 1u) << 3) | ((dup4 & 2u) << 6) | ((dup4 & 4u) << 6) | ((dup4 & 8u) << 8);
+}
+__global__ void __launch_bounds__(256) k_sp_mc_dedupe(const float *__restrict__ values8, const i64 *__restrict__ cell_idx, SparseParams p,
+                                                      u32 n, u32 *__restrict__ cinfo) {
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        if (s == 0) continue;
+        const u32 w = cinfo[s];
+        const u32 used = (w >> 16) & 0xfffu;
+        if (!(used & 0x988u)) continue;                             // none of e3, e7, e8, e11 in use
+        const i64 id = cell_idx[s];
+        if (cell_idx[s - 1] + 1 != id || id % p.cz == 0) continue;  // previous element is not the cell below in the same row
+        const u32 usedp = (cinfo[s - 1] >> 16) & 0xfffu;            // (its low-face bits may change concurrently, e1/e5/e9/e10 never do)
+        const float4 lo = __ldg(reinterpret_cast<const float4 *>(values8 + 8 * (size_t) s));
+        const float4 hi = __ldg(reinterpret_cast<const float4 *>(values8 + 8 * (size_t) s) + 1);
+        const float4 plo = __ldg(reinterpret_cast<const float4 *>(values8 + 8 * (size_t) (s - 1)));
+        const float4 phi = __ldg(reinterpret_cast<const float4 *>(values8 + 8 * (size_t) (s - 1)) + 1);
+        // bit-equality of my corners 0, 2, 4, 6 with the lower cell's corners 1, 3, 5, 7
+        const bool c0 = __float_as_uint(lo.x) == __float_as_uint(plo.y), c2 = __float_as_uint(lo.z) == __float_as_uint(plo.w);
+        const bool c4 = __float_as_uint(hi.x) == __float_as_uint(phi.y), c6 = __float_as_uint(hi.z) == __float_as_uint(phi.w);
+        u32 dup4 = 0;
+        if (((used >> 3) & 1u) && ((usedp >> 1) & 1u) && c0 && c2) dup4 |= 1u;    // e3  (0-2) == lower e1  (1-3)
+        if (((used >> 7) & 1u) && ((usedp >> 5) & 1u) && c4 && c6) dup4 |= 2u;    // e7  (4-6) == lower e5  (5-7)
+        if (((used >> 8) & 1u) && ((usedp >> 9) & 1u) && c0 && c4) dup4 |= 4u;    // e8  (0-4) == lower e9  (1-5)
+        if (((used >> 11) & 1u) && ((usedp >> 10) & 1u) && c2 && c6) dup4 |= 8u;  // e11 (2-6) == lower e10 (3-7)
+        if (dup4) cinfo[s] = (w & ~(sp_dup_edges(dup4) << 16)) | (dup4 << 28);
+    }
+}
+
 // scan over cells of (kept triangles, used edges)
 __global__ void __launch_bounds__(256) k_sp_scan2(u32 n, u32 *__restrict__ counters, const u32 *__restrict__ cinfo, int shiftA,
                                                   u32 maskA, int shiftB, u32 maskB, u32 *__restrict__ offA, u32 *__restrict__ offB,
@@ -188,7 +225,7 @@ __global__ void __launch_bounds__(128) k_sp_mc_keys(const float *__restrict__ va
                                                     const u32 *__restrict__ cand_off, u32 *__restrict__ kx, u32 *__restrict__ ky,
                                                     u32 *__restrict__ kz) {
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        const u32 used = cinfo[s] >> 16;
+        const u32 used = (cinfo[s] >> 16) & 0xfffu;   // the edges this cell emits (k_sp_mc_dedupe)
         if (!used) continue;
         CellData c;
         load_sparse_cell(values8, p, s, cell_idx[s], c);
@@ -213,7 +250,13 @@ __global__ void __launch_bounds__(256) k_sp_mc_faces(u32 n, int method, const u3
         const u32 w = cinfo[s];
         const u32 mask = (w >> 8) & 0xffu;
         if (!mask) continue;
-        const u32 cs = w & 0xffu, used = w >> 16, base = cand_off[s];
+        const u32 cs = w & 0xffu, emitted = (w >> 16) & 0xfffu, base = cand_off[s];
+        const u32 dup = sp_dup_edges(w >> 28);             // edges whose vertex is the lower cell's candidate (k_sp_mc_dedupe)
+        u32 pemit = 0, pbase = 0;
+        if (dup) {
+            pemit = (cinfo[s - 1] >> 16) & 0xfffu;
+            pbase = cand_off[s - 1];
+        }
         const u64 word = method == 0 ? kTriWords_nagae[cs] : kTriWords_lorensen[cs];
         const u32 nt = (u32) (word >> 60);
         size_t o = 3 * (size_t) tri_off[s];
@@ -222,7 +265,14 @@ __global__ void __launch_bounds__(256) k_sp_mc_faces(u32 n, int method, const u3
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const u32 e = (u32) (word >> (12 * k + 4 * j)) & 15u;
-                F[o + j] = (int) cand_rank[base + __popc(used & ((1u << e) - 1u))];
+                u32 cand;
+                if ((dup >> e) & 1u) {
+                    const u32 ep = e == 3u ? 1u : (e == 7u ? 5u : (e == 8u ? 9u : 10u));   // the same edge in the lower cell
+                    cand = pbase + __popc(pemit & ((1u << ep) - 1u));
+                } else {
+                    cand = base + __popc(emitted & ((1u << e) - 1u));
+                }
+                F[o + j] = (int) cand_rank[cand];
             }
             o += 3;
         }
@@ -642,6 +692,7 @@ int isoext_mc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_LAUNCH(k_sp_mc_classify, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, method, b.cinfo,
                (u32) emit_begin, (u32) emit_end);
     stream_timer_mark(stream);
+    if (g_tuning[7] != 1) ISX_LAUNCH(k_sp_mc_dedupe, grid_for(n, 256, sms * 16), 256, 0, stream, values8, cell_idx, p, (u32) n, b.cinfo);
     ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, b.cinfo, 8, 0xffu, 16, 0xfffu, b.offA, b.offB, b.descA,
                b.descB, (int) C_T, (int) C_VC, (int) C_TICKET_B);
     ISX_CUDA(cudaGetLastError());
@@ -677,9 +728,9 @@ int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_mc_keys, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, b.cinfo, b.offB, s.kx, s.ky, s.kz);
     u32 h[C_COUNT];
-    // every (cell, edge) vertex is a candidate (4 bit-equal copies of most positions): measured, the global radix sort
-    // (1.17 ms at 9.6 M candidates) beats the layer-segmented sort (1.3 ms: the in-group ranking pays for the duplicates)
-    rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, g_tuning[3] == 100, [&]() {
+    // (cell, edge) vertices minus the duplicates along z (k_sp_mc_dedupe), segmented by grid layer; g_tuning[3] = 101
+    // selects the global radix sort (it was the faster one before the ranking stage of k_seg_sort worked on list positions)
+    rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, g_tuning[3] != 101, [&]() {
         ISX_LAUNCH(k_sp_mc_faces, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, method, b.cinfo, b.offA, b.offB, s.cand_rank, F);
     });
     if (rc != OK) return rc;
