@@ -49,6 +49,7 @@ struct McBuffers {
     unsigned char *span_cnt;   // entries per candidate 128-point span (written by the count pass, read by the fill pass)
     u32 *heavy_list;           // rows filled cooperatively (k_rowfill_heavy)
     size_t zero_bytes;       // bytes from `counters` that one memset clears at the start of a call
+    float4 *vals4;  // per entry that owns an edge: the values at its point and at the +z / +y / +x neighbours (k_cell_tris -> k_cand_pos)
     u32 *bdelta;   // per entry: sort bucket (layer offset + sub-bucket) of its 3 owned edge vertices, one byte each
     SegHead seg;             // bucket histogram / offsets over the sort buckets (sort_buckets(p))
 };
@@ -74,6 +75,7 @@ static size_t carve_mc(Carver &c, const DenseParams &p, size_t cap, McBuffers *o
     b.tri_off = c.take<u32>(cap);
     b.cand_info = c.take<u32>(cap + 1);
     b.bdelta = c.take<u32>(cap + 1);
+    b.vals4 = c.take<float4>(cap + 1);
     b.heavy_list = c.take<u32>(compact_heavy_cap((u32) cap));
     b.span_cnt = c.take<unsigned char>(compact_span_bytes(p));
     if (out) *out = b;
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
                                                    const uint2 *__restrict__ entries, const u32 *__restrict__ row_start,
                                                    u32 cap, const u32 *__restrict__ counters, u32 *__restrict__ nb,
                                                    unsigned char *__restrict__ ntri, unsigned char *__restrict__ trimask,
-                                                   unsigned char *__restrict__ used, u32 *__restrict__ bdelta) {
+                                                   unsigned char *__restrict__ used, u32 *__restrict__ bdelta,
+                                                   float4 *__restrict__ vals4) {
     pdl_wait();
     pdl_trigger();
     const u32 S = counters[C_S];
@@ -190,6 +193,8 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
             c.v[2] = (own & 2u) ? field_at<IMPLICIT>(values, p, n, Z, x, y + 1, z) : 0.f;
             c.v[4] = (own & 4u) ? field_at<IMPLICIT>(values, p, n, p.YZ, x + 1, y, z) : 0.f;
         }
+        // the position kernel reads the four values from here (coalesced) instead of gathering them from the field again
+        if (own) vals4[s] = make_float4(c.v[0], c.v[1], c.v[2], c.v[4]);
         if (!is_cell) {
             bdelta[s] = owned_buckets(p, r, own, c.v[0], c.v[1], c.v[2], c.v[4]);
             ntri[s] = 0;
@@ -405,11 +410,9 @@ __global__ void __launch_bounds__(256) k_scan_entries(u32 cap, u32 *__restrict__
 // K5: positions (as sortable keys) of the used edge slots, computed once by the owning entry.
 // ---------------------------------------------------------------------------------------------
 // (CandOut / emit_candidate: segsort.cuh)
-template <bool IMPLICIT>
-__global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ values, DenseParams p,
-                                                  const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
+__global__ void __launch_bounds__(256) k_cand_pos(DenseParams p, const uint2 *__restrict__ entries, const u32 *__restrict__ counters,
                                                   const u32 *__restrict__ cand_info, const u32 *__restrict__ bdelta,
-                                                  CandOut out, u32 cand_cap, u32 entry_cap) {
+                                                  const float4 *__restrict__ vals4, CandOut out, u32 cand_cap, u32 entry_cap) {
     pdl_wait();
     pdl_trigger();
     const u32 S = counters[C_S];
@@ -423,19 +426,18 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
         if (!__any_sync(0xffffffffu, um != 0u)) continue;
         u32 id = ci & 0x1fffffffu;
         u32 x = 0, bd = 0;
-        float v0 = 0.f, px0 = 0.f, py0 = 0.f, pz0 = 0.f;
-        i64 n = 0;
+        float px0 = 0.f, py0 = 0.f, pz0 = 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // values at the point and at its +z / +y / +x neighbours (k_cell_tris)
         u32 y = 0, z = 0, xg = 0;
         if (um) {
             const uint2 e = entries[s];
+            v = vals4[s];
+            bd = bdelta[s];
             const u32 r = e.x;
             z = ent_z(e.y);
             x = r / Y;
             y = r - x * Y;
-            n = (i64) r * Z + z;
-            v0 = field_at<IMPLICIT>(values, p, n, 0, x, y, z);
             xg = x + (u32) p.g.x_off;
-            bd = bdelta[s];
             px0 = axis_pos(xg, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
             py0 = axis_pos(y, Y - 1, p.g.amin[1], p.g.asize[1]);
             pz0 = axis_pos(z, Z - 1, p.g.amin[2], p.g.asize[2]);
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             const bool has = um & 1u;
             u32 a = 0, b2 = 0, c = 0;
             if (has) {
-                const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, 1, x, y, z + 1), p.level);
+                const float t = edge_t(v.x, v.y, p.level);
                 const float pz1 = axis_pos(z + 1, Z - 1, p.g.amin[2], p.g.asize[2]);
                 a = float_key(lerp_ref(t, px0, px0));
                 b2 = float_key(lerp_ref(t, py0, py0));
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             const bool has = um & 2u;
             u32 a = 0, b2 = 0, c = 0;
             if (has) {
-                const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, Z, x, y + 1, z), p.level);
+                const float t = edge_t(v.x, v.z, p.level);
                 const float py1 = axis_pos(y + 1, Y - 1, p.g.amin[1], p.g.asize[1]);
                 a = float_key(lerp_ref(t, px0, px0));
                 b2 = float_key(lerp_ref(t, py0, py1));
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(256) k_cand_pos(const float *__restrict__ valu
             const bool has = um & 4u;
             u32 a = 0, b2 = 0, c = 0;
             if (has) {
-                const float t = edge_t(v0, field_at<IMPLICIT>(values, p, n, p.YZ, x + 1, y, z), p.level);
+                const float t = edge_t(v.x, v.w, p.level);
                 const float px1 = axis_pos(xg + 1, (u32) p.g.Xg - 1, p.g.amin[0], p.g.asize[0]);
                 a = float_key(lerp_ref(t, px0, px1));
                 b2 = float_key(lerp_ref(t, py0, py0));
@@ -654,10 +656,10 @@ static int enqueue_analysis(const float *values, const DenseParams &p, int metho
     const int ct_blocks = sms * (g_tuning[4] > 0 ? g_tuning[4] : 32);
     if (p.sdf)
         ISX_LAUNCH_PDL(k_cell_tris<true>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
-                   b.trimask, b.used, b.bdelta);
+                   b.trimask, b.used, b.bdelta, b.vals4);
     else
         ISX_LAUNCH_PDL(k_cell_tris<false>, ct_blocks, 128, 0, stream, values, p, method, b.entries, b.row_start, cap, b.counters, b.nb, b.ntri,
-                   b.trimask, b.used, b.bdelta);
+                   b.trimask, b.used, b.bdelta, b.vals4);
     ISX_LAUNCH_PDL(k_scan_entries, scan_blocks(sms), 256, 0, stream, cap, b.counters, b.ntri, b.used, b.tri_off, b.cand_info, b.descT, b.descU,
                b.entries, b.bdelta, (u32) p.g.Y, sort_nsub(p), b.seg.count, nb, b.seg);
     ISX_CUDA(cudaGetLastError());
@@ -684,10 +686,7 @@ static int enqueue_phase2(const float *values, const DenseParams &p, int method,
     const u32 grid_n = device_counts ? cand_cap : host_nc;
     const CandOut co{s.kx, s.ky, s.kz, s.seg.perm0, s.seg.cbucket, b.seg.count, b.seg.start, b.seg.bigoff, b.seg.cursor,
                      s.seg.bkx, s.seg.bky, s.seg.bkz, s.seg.bid, b.seg.xinvmin, b.seg.xmax};
-    if (p.sdf)
-        ISX_LAUNCH_PDL(k_cand_pos<true>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
-    else
-        ISX_LAUNCH_PDL(k_cand_pos<false>, sms * 8, 256, 0, stream, values, p, b.entries, b.counters, b.cand_info, b.bdelta, co, cand_cap, entry_cap);
+    ISX_LAUNCH_PDL(k_cand_pos, sms * 8, 256, 0, stream, p, b.entries, b.counters, b.cand_info, b.bdelta, b.vals4, co, cand_cap, entry_cap);
     ISX_CUDA(seg_sort_run(s.kx, s.ky, s.kz, host_nc, n_dev, cand_cap, grid_n, sort_buckets(p), n_big,
                           device_counts ? b.counters + C_NBIG : nullptr, big_cap, b.seg, s.seg,
                           SegGeom{p.g.amin[0], p.g.asize[0], p.g.amin[1], p.g.asize[1], p.g.amin[2], p.g.asize[2], (u32) p.g.Xg, (u32) p.g.Y,
