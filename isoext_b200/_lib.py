@@ -6,6 +6,7 @@ fails, this module raises.  The test-only checker package is never imported from
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -109,6 +110,10 @@ def lib():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
         _lib = handle
+        # development knobs (isoext_debug_set_tuning), e.g. ISOEXT_B200_TUNING="3=101,6=1" for A/B runs of the tools
+        for item in filter(None, os.environ.get("ISOEXT_B200_TUNING", "").split(",")):
+            key, _, val = item.partition("=")
+            handle.isoext_debug_set_tuning(int(key), int(val))
     return _lib
 
 

@@ -565,6 +565,8 @@ static size_t carve_sp_scratch(Carver &c, size_t nc, u32 x_planes, u32 Y, SpScra
 }
 // sort (segmented by grid layer, radix sort as the fallback) + weld, then `faces()` enqueues the face kernel;
 // leaves the counter block in h
+constexpr u32 SP_SEG_MAX = 16u << 20;
+static bool sp_use_seg(u32 nc) { return g_tuning[3] == 100 || (g_tuning[3] != 101 && nc < SP_SEG_MAX); }
 template <typename FacesFn>
 static int sort_weld_faces(const SpScratch &s, u32 nc, const Geom &g, u32 *counters, float x_lo_threshold, float x_hi_threshold, float *V,
                            cudaStream_t stream, u32 *h, bool use_seg, FacesFn faces) {
@@ -728,9 +730,10 @@ int isoext_mc_sparse_emit(const float *values8, const int64_t *cell_idx, int64_t
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_mc_keys, grid_for(n, 128, sms * 16), 128, 0, stream, values8, cell_idx, p, (u32) n, b.cinfo, b.offB, s.kx, s.ky, s.kz);
     u32 h[C_COUNT];
-    // (cell, edge) vertices minus the duplicates along z (k_sp_mc_dedupe), segmented by grid layer; g_tuning[3] = 101
-    // selects the global radix sort (it was the faster one before the ranking stage of k_seg_sort worked on list positions)
-    rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, g_tuning[3] != 101, [&]() {
+    // (cell, edge) vertices minus the duplicates along z (k_sp_mc_dedupe), segmented by grid layer up to SP_SEG_MAX
+    // candidates, global radix sort beyond (measured: 1.10 vs 1.25 ms at 6.4 M candidates, 30.2 vs 21.1 ms at 100 M);
+    // g_tuning[3] = 100 / 101 force one or the other
+    rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, sp_use_seg(nc), [&]() {
         ISX_LAUNCH(k_sp_mc_faces, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, method, b.cinfo, b.offA, b.offB, s.cand_rank, F);
     });
     if (rc != OK) return rc;
@@ -852,8 +855,9 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
     ISX_CUDA(cudaMemsetAsync(s.descV, 0, ((size_t) nc / UQ_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_dc_keys, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.dinfo, b.cand_off, cellslot, dual_v, s.kx, s.ky, s.kz);
     u32 h[C_COUNT];
-    // dual vertices: one candidate per cell, segmented by grid layer (0.39 ms vs 0.76 ms for the global radix sort at 2.4 M)
-    rc = sort_weld_faces(s, nc, p.g, b.counters, -INFINITY, INFINITY, V, stream, h, g_tuning[3] != 101, [&]() {
+    // dual vertices: one candidate per cell, segmented by grid layer (0.39 ms vs 0.76 ms for the global radix sort at
+    // 2.4 M; at 38.7 M the radix sort is the faster one: 29.1 vs 38.0 ms for the whole call)
+    rc = sort_weld_faces(s, nc, p.g, b.counters, -INFINITY, INFINITY, V, stream, h, sp_use_seg(nc), [&]() {
         ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.quad_off, b.cand_off,
                    cellslot, s.cand_rank, dual_v, F, quads_out);
     });

@@ -271,6 +271,9 @@ class SlabGrid:
         return int(self._ext.numel())
 
     def owned_values(self) -> torch.Tensor:
+        """View of the owned planes.  Read it freely; to WRITE new values use ``set_owned_values`` (or call
+        ``_guard_overwrite()`` first): with the peer transport the neighbours pull their halo planes straight out of
+        this storage, and an in-place fill must not overtake the pull of the previous exchange."""
         p = self.plan
         return self._ext[p["own_lo"] - p["ext_lo"]:p["own_hi"] - p["ext_lo"]]
 
@@ -304,32 +307,67 @@ class SlabGrid:
         dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
         if len(set(hosts)) != 1:
             return
+        # Every step that can fail on one rank only (allocation, IPC export, mapping a neighbour: GPUs without peer
+        # access, MIG slices, containers that share a host name across nodes) is followed by an all-reduce of a success
+        # flag, so that ALL ranks fall back to the NCCL transport together instead of one raising inside a collective.
+        def all_ok(ok: bool) -> bool:
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            return bool(flag.item())
+
+        ext_ptr, sync_ptr = C.c_void_p(), C.c_void_p()
+        h_ext, h_sync = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+        peer_ext, peer_sync = {}, {}
+
+        def release():
+            for ptr in list(peer_ext.values()) + list(peer_sync.values()):
+                lib.isoext_peer_close(ptr)
+            for ptr in (ext_ptr, sync_ptr):
+                if ptr.value:
+                    lib.isoext_peer_free(ptr.value)
+
         with torch.cuda.device(self.device):
-            ext_ptr, sync_ptr = C.c_void_p(), C.c_void_p()
-            h_ext, h_sync = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
-            _lib.check(lib.isoext_peer_alloc(n_floats * 4, C.byref(ext_ptr), h_ext))
-            _lib.check(lib.isoext_peer_alloc(words * 8, C.byref(sync_ptr), h_sync))
-            self._ext = _device_view(ext_ptr.value, n_floats, torch.float32, self.device).view(ext_shape)
+            ok = lib.isoext_peer_alloc(n_floats * 4, C.byref(ext_ptr), h_ext) == 0
+            ok = ok and lib.isoext_peer_alloc(words * 8, C.byref(sync_ptr), h_sync) == 0
+            fail_rank = os.environ.get("ISOEXT_B200_PEER_TEST_FAIL_RANK")      # test hook: this rank "cannot" map its peers
+            if not all_ok(ok):
+                release()
+                return
             sync = _device_view(sync_ptr.value, words, torch.int64, self.device)
             sync.zero_()
             torch.cuda.synchronize()
             allh = [None] * self.world
             dist.all_gather_object(allh, (bytes(h_ext), bytes(h_sync)), group=self.group)
-            peer_ext, peer_sync = {}, {}
+            ok = True
             for r in range(self.world):
-                if r == self.rank:
+                if r == self.rank or not ok:
                     continue
                 p = C.c_void_p()
-                _lib.check(lib.isoext_peer_open((C.c_ubyte * 64).from_buffer_copy(allh[r][1]), C.byref(p)))
-                peer_sync[r] = p.value
-                if abs(r - self.rank) == 1:
+                ok = lib.isoext_peer_open((C.c_ubyte * 64).from_buffer_copy(allh[r][1]), C.byref(p)) == 0
+                if ok:
+                    peer_sync[r] = p.value
+                if ok and abs(r - self.rank) == 1:
                     p = C.c_void_p()
-                    _lib.check(lib.isoext_peer_open((C.c_ubyte * 64).from_buffer_copy(allh[r][0]), C.byref(p)))
-                    peer_ext[r] = p.value
+                    ok = lib.isoext_peer_open((C.c_ubyte * 64).from_buffer_copy(allh[r][0]), C.byref(p)) == 0
+                    if ok:
+                        peer_ext[r] = p.value
+            if fail_rank is not None and int(fail_rank) == self.rank:
+                ok = False
+            if not all_ok(ok):
+                del sync
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)      # nobody still maps what is about to be freed
+                release()
+                return
+            self._ext = _device_view(ext_ptr.value, n_floats, torch.float32, self.device).view(ext_shape)
         err = torch.zeros(1, dtype=torch.int32).pin_memory()     # written by the kernels on a wait timeout
         sync_ptrs = (C.c_void_p * 32)(*[peer_sync.get(r) for r in range(min(self.world, 32))])
         self._peer = dict(ext_ptr=ext_ptr.value, sync_ptr=sync_ptr.value, sync=sync, peer_ext=peer_ext, peer_sync=peer_sync,
                           sync_ptrs=sync_ptrs, err=err, epoch=0, counts_epoch=0)
+        # best effort for a SlabGrid that is dropped without close(): free this rank's exported allocations (the
+        # collective unmapping of close() is not possible from a finalizer)
+        import weakref
+        self._finalizer = weakref.finalize(self, _free_exported, self._peer)
 
     def _peer_check(self) -> None:
         if self._peer is not None and int(self._peer["err"][0]) != 0:
@@ -392,6 +430,8 @@ class SlabGrid:
         pr, self._peer = self._peer, None
         if pr is None:
             return
+        if getattr(self, "_finalizer", None) is not None:
+            self._finalizer.detach()
         from . import _lib
         lib = _lib.lib()
         with torch.cuda.device(self.device):
@@ -406,6 +446,19 @@ class SlabGrid:
             pr["sync"] = None
             lib.isoext_peer_free(pr["ext_ptr"])
             lib.isoext_peer_free(pr["sync_ptr"])
+
+
+def _free_exported(pr: dict) -> None:
+    """Finalizer of a SlabGrid that was never close()d: frees the rank's own IPC-exported slab and SYNC block."""
+    try:
+        from . import _lib
+        lib = _lib.lib()
+        pr["sync"] = None
+        torch.cuda.synchronize()
+        lib.isoext_peer_free(pr["ext_ptr"])
+        lib.isoext_peer_free(pr["sync_ptr"])
+    except Exception:      # interpreter shutdown: the driver reclaims the memory
+        pass
 
 
 class _RawDevice:

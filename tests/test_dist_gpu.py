@@ -216,7 +216,9 @@ def test_c3_2048_csg_two_slabs_equal_single_gpu():
 
 
 def _nccl_worker(rank, world, port, transport, field_name):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ISOEXT_B200_PEER="1" if transport == "peer" else "0")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ISOEXT_B200_PEER="0" if transport == "nccl" else "1")
+    if transport == "peer_fails":      # one rank cannot map its peers: ALL ranks must fall back to NCCL (no hang, same mesh)
+        os.environ["ISOEXT_B200_PEER_TEST_FAIL_RANK"] = str(world - 1)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -224,7 +226,7 @@ def _nccl_worker(rank, world, port, transport, field_name):
         from isoext_b200 import dist as idist
         vals = FIELDS[field_name]().cuda()
         sg = idist.SlabGrid(list(vals.shape))
-        assert (sg._peer is not None) == (transport == "peer")
+        assert (sg._peer is not None) == (transport == "peer")       # "peer_fails": every rank fell back together
         lo, hi = sg.owned_point_range()
         g = iso.UniformGrid(list(vals.shape))
         # several steps with changing values: epochs, the overwrite guard and the count ring all advance
@@ -276,7 +278,7 @@ def _nccl_worker(rank, world, port, transport, field_name):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer", "nccl", "peer_fails"])
 @pytest.mark.parametrize("field_name", ["cuboid65_faces_on_slab_planes", "torus_96x64x128"])
 def test_real_ranks(field_name, transport):
     """Real ranks, one process per GPU: NVLink peer transport (csrc/peer.cu) and the NCCL fallback."""
@@ -284,4 +286,4 @@ def test_real_ranks(field_name, transport):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(n, 4)
-    mp.spawn(_nccl_worker, args=(world, 29610 + (1 if transport == "peer" else 0), transport, field_name), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, 29610 + {"peer": 1, "nccl": 0, "peer_fails": 2}[transport], transport, field_name), nprocs=world, join=True)

@@ -48,6 +48,14 @@ CASES = {
     "noise_20x24x128_spanpath": lambda: (fields.noise((20, 24, 128), 3), 0.0, BOX),
     "noise_7x5x256_spanpath": lambda: (fields.noise((7, 5, 256), 4), 0.0, BOX),
     "sphere_33x40x128_spanpath": lambda: (fields.eval_field(S.SphereSDF(0.8), (33, 40, 128)), 0.0, BOX),
+    # span-summary compaction (dense.cuh): 3 / 4 / 8 / 16 spans per row (1, 4 and 8 spans per summary load), rows of
+    # more than 32 spans (thread-per-row fallback), and rows lying in a z-aligned face (heavy-row fill)
+    "noise_5x6x384_spans3": lambda: (fields.noise((5, 6, 384), 5), 0.0, BOX),
+    "sphere_9x300x512_spans4": lambda: (fields.eval_field(S.SphereSDF(0.8), (9, 300, 512)), 0.0, BOX),
+    "torus_6x40x1024_spans8": lambda: (fields.eval_field(fields.torus(), (6, 40, 1024)), 0.0, BOX),
+    "noise_3x4x2048_spans16": lambda: (fields.noise((3, 4, 2048), 6), 0.0, BOX),
+    "sphere_3x5x4224_spans33_serial": lambda: (fields.eval_field(S.SphereSDF(0.8), (3, 5, 4224)), 0.0, BOX),
+    "yface_4x9x640_heavy_rows": lambda: (_plane((4, 9, 640), (0.0, 1.0, 0.0), 0.13), 0.0, BOX),
     "surface_crosses_boundary": lambda: (fields.eval_field(S.SphereSDF(1.2), (48, 48, 48)), 0.0, BOX),
     "shifted_aabb": lambda: (fields.eval_field(S.SphereSDF(0.5), (40, 40, 40)), 0.0, ((0, -2, 5), (3, 1, 6))),
     "tiny_2x2x2": lambda: (torch.tensor([[[-1., 1], [1, 1]], [[1, 1], [1, -1]]]), 0.0, BOX),

@@ -10,7 +10,8 @@ def dense(vals):
     g = iso.UniformGrid(list(vals.shape)); g.set_values(vals.cuda()); return g
 
 for vals in (fields.eval_field(S.SphereSDF(0.5), (24, 24, 24)), fields.noise((9, 10, 130), 1), fields.eval_field(fields.csg_box_minus_sphere(), (20, 24, 128)),
-             fields.eval_field(S.CuboidSDF([1, 1, 1]), (17, 17, 17)), torch.ones(6, 6, 6)):
+             fields.eval_field(S.CuboidSDF([1, 1, 1]), (17, 17, 17)), torch.ones(6, 6, 6),
+             fields.noise((3, 4, 1024), 7), fields.eval_field(S.SphereSDF(0.8), (3, 5, 4224)), fields.noise((5, 6, 384), 5)):   # span-summary paths
     g = dense(vals)
     for m in ("nagae", "lorensen"):
         for _ in range(2):                       # second call takes the single-sync fast path
