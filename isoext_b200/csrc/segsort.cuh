@@ -309,7 +309,15 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
         // axis-aligned face by y plane: k_big_sub) -- there the y-plane index relative to the piece's lowest y is the index.
         bool piece_const_x = false;
         int j0_piece = 0;
-        if (LEVEL2 && geom.grouped && vary[2] == 0u) {          // block-uniform
+        // nested z stage available?  (needs room for one counter per z plane behind the group table)
+        constexpr u32 ZCAP = (u32) SegCfg<CAP, THREADS>::CNT_WORDS > (u32) SEG_GROUPS + 2 + 64
+                                 ? (u32) SegCfg<CAP, THREADS>::CNT_WORDS - ((u32) SEG_GROUPS + 2) : 0u;
+        const bool nested_ok = ZCAP > 0 && geom.Z + 1 <= ZCAP;
+        // A bucket whose keys all share (x, y) -- one row of an axis-aligned face, the typical second-level piece -- is ONE
+        // group for the y stage: skip that stage and sort by z plane at once (half the barrier-separated phases).
+        const bool xy_const = geom.grouped && nested_ok && vary[2] == 0u && vary[1] == 0u && n > (u32) SEG_GROUP_MAX &&
+                              (LEVEL2 || b >= geom.gy + geom.gx);                // block-uniform
+        if (LEVEL2 && geom.grouped && vary[2] == 0u && !xy_const) {          // block-uniform
             // lowest / highest y key of the piece -> its first y plane; NaN keys have no plane: radix passes
             if (tid == 0) { dbase[0] = 0xffffffffu; dbase[1] = 0u; }
             __syncthreads();
@@ -324,13 +332,17 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
             piece_const_x = mn >= 0x007fffffu && mx <= 0xff800000u;   // float_key(-inf) .. float_key(+inf)
             if (piece_const_x) j0_piece = (int) yplane_of(key_float(mn), geom) - 1;
         }
-        if (geom.grouped && (LEVEL2 ? piece_const_x : b >= geom.gy + geom.gx)) {   // (layer 0 = below the first plane: radix passes)
+        if (xy_const || (geom.grouped && (LEVEL2 ? piece_const_x : b >= geom.gy + geom.gx))) {   // (layer 0 = below the first plane: radix passes)
             const u32 nsub = geom.gy + geom.gx;
             const u32 L = b / nsub, sub = LEVEL2 ? 0u : b - L * nsub;
             const u32 xb = (u32) ((i64) L - 1 + geom.x_off);    // global index of the layer's lower plane (first level only)
             u32 *gtab = cnt;                                    // [SEG_GROUPS + 1]: counts -> starts -> ends
             unsigned short *gid = ord + CAP;                    // group of every element (second half of ord as temp)
             constexpr u32 ngroups = (u32) SEG_GROUPS;
+            if (xy_const) {               // the whole bucket is group 0 (ord is still the identity of the load)
+                if (tid == 0) { gtab[0] = n; vary[3] = 1; }
+                __syncthreads();
+            } else {
             for (u32 i = tid; i < (u32) SEG_GROUPS + 2; i += THREADS) gtab[i] = 0;
             if (tid == 0) vary[3] = 0;
             __syncthreads();
@@ -376,16 +388,14 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                 }
             }
             __syncthreads();
-            // nested z stage available?  (needs room for one counter per z plane behind the group table)
-            constexpr u32 ZCAP = (u32) SegCfg<CAP, THREADS>::CNT_WORDS > (u32) SEG_GROUPS + 2 + 64
-                                     ? (u32) SegCfg<CAP, THREADS>::CNT_WORDS - ((u32) SEG_GROUPS + 2) : 0u;
-            const bool nested_ok = ZCAP > 0 && geom.Z + 1 <= ZCAP;
+            }   // !xy_const
             grouped = vary[3] == 0 || nested_ok;
             if (grouped) {
                 u32 *zc = cnt + SEG_GROUPS + 2;                 // [Z + 1] z-plane counters of one large group
                 u32 *s_nl = dbase, *s_lg = dbase + 1, *s_bad = dbase + 1 + SEG_LARGE_MAX;   // dbase is free outside the radix passes
-                if (tid == 0) { *s_nl = 0; *s_bad = 0; }
-                for (u32 i = tid; i < n; i += THREADS) ord[atomicAdd(&gtab[gid[i]], 1u)] = (unsigned short) i;   // gtab: starts -> ends
+                if (tid == 0) { *s_nl = xy_const ? 1u : 0u; *s_bad = 0; s_lg[0] = 0; }
+                if (!xy_const)
+                    for (u32 i = tid; i < n; i += THREADS) ord[atomicAdd(&gtab[gid[i]], 1u)] = (unsigned short) i;   // gtab: starts -> ends
                 __syncthreads();
                 // rank of every element inside its group on the full key (ties cannot occur between different elements
                 // other than exact duplicates, which are ordered by their slot): O(group size) per element, all threads busy
@@ -398,7 +408,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                     const u32 jp = tid + (u32) q * THREADS;
                     dst[q] = 0xffffffffu;
                     del[q] = 0;
-                    if (jp < n) {
+                    if (jp < n && !xy_const) {
                         const u32 i = ord[jp];
                         const u32 g = gid[i];
                         const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
@@ -418,7 +428,7 @@ static __global__ void __launch_bounds__(THREADS, (CAP <= 1024 ? 8 : 2)) k_seg_s
                         del[q] = i;
                     }
                 }
-                if (vary[3]) {   // list the large groups
+                if (vary[3] && !xy_const) {   // list the large groups
                     for (u32 g = tid; g < ngroups; g += THREADS) {
                         const u32 s1 = g ? gtab[g - 1] : 0u, e1 = gtab[g];
                         if (e1 - s1 > (u32) SEG_GROUP_MAX) {
