@@ -203,9 +203,17 @@ __global__ void __launch_bounds__(128) k_cell_tris(const float *__restrict__ val
         }
         const u32 rsY0 = row_start[r + 1], rsY1 = row_start[r + 2], rsX0 = row_start[r + Y], rsX1 = row_start[r + Y + 1],
                   rsXY1 = row_start[r + Y + 2];
-        const u32 lbY = row_lower_bound(entries, rsY0, rsY1, z);
-        const u32 lbX = row_lower_bound(entries, rsX0, rsX1, z);
-        const u32 lbXY = row_lower_bound(entries, rsX1, rsXY1, z);
+        // the three neighbour rows are searched in lockstep: three independent loads per round instead of three
+        // binary searches one after the other (the kernel is bound by the latency of exactly this chain)
+        u32 lbY = rsY0, hiY = rsY1, lbX = rsX0, hiX = rsX1, lbXY = rsX1, hiXY = rsXY1;
+        while (lbY < hiY || lbX < hiX || lbXY < hiXY) {
+            const u32 mY = (lbY + hiY) >> 1, mX = (lbX + hiX) >> 1, mXY = (lbXY + hiXY) >> 1;
+            const bool aY = lbY < hiY, aX = lbX < hiX, aXY = lbXY < hiXY;
+            const u32 zY = aY ? ent_z(entries[mY].y) : 0u, zX = aX ? ent_z(entries[mX].y) : 0u, zXY = aXY ? ent_z(entries[mXY].y) : 0u;
+            if (aY) { if (zY < z) lbY = mY + 1; else hiY = mY; }
+            if (aX) { if (zX < z) lbX = mX + 1; else hiX = mX; }
+            if (aXY) { if (zXY < z) lbXY = mXY + 1; else hiXY = mXY; }
+        }
         nb[s] = lbY;                    // structure of arrays (three planes of `cap` entries): coalesced 4-byte accesses
         nb[cap + s] = lbX;
         nb[2 * (size_t) cap + s] = lbXY;

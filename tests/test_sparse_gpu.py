@@ -89,6 +89,28 @@ def test_sparse_with_inconsistent_corner_values_welds_by_position(iso):
         assert np.array_equal(f.cpu().numpy(), of) and np.array_equal(v.cpu().numpy().view(np.uint32), ov.view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["sphere", "cuboid_exact_hits"])
+def test_sparse_partially_inconsistent_values(iso, name):
+    """A band with consistent values in which some cells carry perturbed corners: the z-direction candidate
+    de-duplication (csrc/sparse.cu k_sp_mc_dedupe) applies to some shared edges and must not apply to others."""
+    make, shape = SDFS[name]
+    g = populate(iso.SparseGrid(list(shape)), make())
+    cells = g.get_cell_indices()
+    vals = g.get_values().clone()
+    gen = torch.Generator().manual_seed(11)
+    pick = torch.rand(vals.shape[0], generator=gen) < 0.3
+    corner = torch.randint(0, 8, (vals.shape[0],), generator=gen)
+    delta = (torch.rand(vals.shape[0], generator=gen) - 0.5) * 2e-2
+    rows = torch.nonzero(pick).flatten()
+    vals[rows.cuda(), corner[rows].cuda()] += delta[rows].cuda()
+    vals[rows[::5].cuda(), 0] = 0.0                  # exact level hits on a shared corner: degenerate triangles on one side only
+    g.set_values(vals)
+    for method in ("nagae", "lorensen"):
+        v, f = iso.marching_cubes(g, 0.0, method)
+        ov, of, _ = oracle.mc_sparse(vals.cpu().numpy(), cells.cpu().numpy(), shape, 0.0, method)
+        assert np.array_equal(f.cpu().numpy(), of) and np.array_equal(v.cpu().numpy().view(np.uint32), ov.view(np.uint32))
+
+
 @pytest.mark.parametrize("name", sorted(SDFS))
 def test_sparse_intersection_and_dc_vs_oracle(iso, name):
     from isoext_b200.sparse import dc_sparse_raw
