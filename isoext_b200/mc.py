@@ -49,7 +49,13 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
     X, Y, Z = shape
     xg = X if x_global is None else x_global
     lo, hi = (0, X - 1) if emit_range is None else emit_range
-    amin, amax = _lib.f3(aabb_min), _lib.f3(aabb_max)
+    # per-grid cache of what does not change between calls (ctypes arrays of the box, workspace sizes): the host side
+    # of a 300 us extraction is worth keeping short
+    cache = hints.setdefault("_cache", {}) if hints is not None else {}
+    box_key = (tuple(float(v) for v in aabb_min), tuple(float(v) for v in aabb_max))
+    if cache.get("box_key") != box_key:
+        cache["box_key"], cache["box"] = box_key, (_lib.f3(aabb_min), _lib.f3(aabb_max))
+    amin, amax = cache["box"]
     dev = values.device if values is not None else sdf_prog.device
     vptr = values.data_ptr() if values is not None else None
     sptr = sdf_prog.data_ptr() if sdf_prog is not None else None
@@ -63,8 +69,17 @@ def mc_dense_raw(values: torch.Tensor, shape, aabb_min, aabb_max, level, method_
         tri_cap = hints["T"] + (hints["T"] >> 6) + 16
         nb_hint = hints.get("n_big", 0)
         big_cap = min(cand_cap, nb_hint + (nb_hint >> 6) + 16) if nb_hint > 0 else 0
-        wsbuf = ws.get("mc_ws", lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap), dev)
-        scratch = ws.get("mc_scratch", lib.isoext_mc_dense_scratch_bytes(cand_cap), dev)
+        ws_key, sc_key = ("ws", X, Y, Z, cap), ("sc", cand_cap)
+        if ws_key not in cache:
+            cache[ws_key] = lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap)
+        if sc_key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+                cache["box_key"], cache["box"] = box_key, (amin, amax)
+                cache[ws_key] = lib.isoext_mc_dense_workspace_bytes(X, Y, Z, cap)
+            cache[sc_key] = lib.isoext_mc_dense_scratch_bytes(cand_cap)
+        wsbuf = ws.get("mc_ws", cache[ws_key], dev)
+        scratch = ws.get("mc_scratch", cache[sc_key], dev)
         V = torch.empty((cand_cap, 3), dtype=torch.float32, device=dev)
         F = torch.empty((tri_cap, 3), dtype=torch.int32, device=dev)
         h_lo, h_hi, h_ev = (0, 0, None) if halo is None else (int(halo[0]), int(halo[1]), halo[2].cuda_event)
@@ -128,9 +143,13 @@ def marching_cubes(grid, level: float = 0.0, method: str = "nagae"):
     mid = _method_id(method)
     from .grid import ImplicitGrid
     if isinstance(grid, (UniformGrid, ImplicitGrid)):
-        with torch.cuda.device(grid.device):
-            v, f, _, _, cap = mc_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, mid, grid._ws,
-                                           cap_hint=grid._cap_hint, hints=grid._hints, sdf_prog=getattr(grid, "_prog", None))
+        args = (grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, mid, grid._ws)
+        kw = dict(cap_hint=grid._cap_hint, hints=grid._hints, sdf_prog=getattr(grid, "_prog", None))
+        if torch.cuda.current_device() == grid.device.index:       # (entering a device context costs several us)
+            v, f, _, _, cap = mc_dense_raw(*args, **kw)
+        else:
+            with torch.cuda.device(grid.device):
+                v, f, _, _, cap = mc_dense_raw(*args, **kw)
         grid._cap_hint = cap
         if f is None or f.shape[0] == 0:
             return None, None   # src/isoext_ext.cu:47-49: empty arrays become None
