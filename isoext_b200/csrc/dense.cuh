@@ -486,35 +486,16 @@ static __global__ void __launch_bounds__(256) k_compact(const u32 *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 fast path (Z % 128 == 0): one thread per 128-point span of a row.  The four rows of the
+// K2 fast path (Z % 128 == 0): the unit of work is a 128-point span of a row.  The four rows of the
 // span's cells arrive as four aligned uint4 loads (+1 word for the z+1 neighbour of the last point);
-// a span whose 4x(128+1) sign bits are all equal -- >98% of a typical volume -- is rejected
-// with a few LOP3s, so the kernel costs ~0.4 instructions per voxel instead of ~8.
+// a span whose 4x(128+1) sign bits are all equal -- >98% of a typical volume -- owns no entry, and is
+// rejected from the one-byte span summary without touching the bits at all.
 // ---------------------------------------------------------------------------------------------
-constexpr int SP_ITEMS = 4;                 // consecutive spans per thread
-constexpr int SP_TILE = 256 * SP_ITEMS;     // spans per block
-
 struct SpanBits {
     u32 a[5], b[5], c[5], d[5];   // words 0..3 of the span + the following word (only bit 0 used)
     u32 r, z0;
     bool hasX, hasY, last;        // last: this span ends the row (no z+1 neighbour for its last point)
 };
-
-// true if some pair of the span's 4x129 sign bits differs (=> the span may own an entry)
-__device__ __forceinline__ bool span_mixed(const SpanBits &k) {
-    u32 any = 0, all = 0xffffffffu;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        any |= k.a[j] | k.b[j] | k.c[j] | k.d[j];
-        all &= k.a[j] & k.b[j] & k.c[j] & k.d[j];
-    }
-    if (!k.last) {
-        // the following word's bit 0 (z+1 neighbour of the span's last point) counts as one more sample
-        const u32 n_any = (k.a[4] | k.b[4] | k.c[4] | k.d[4]) & 1u, n_all = k.a[4] & k.b[4] & k.c[4] & k.d[4] & 1u;
-        return !((any == 0u && n_any == 0u) || (all == 0xffffffffu && n_all == 1u));
-    }
-    return !(any == 0u || all == 0xffffffffu);
-}
 
 // masks of word j of the span: m = entries, plus per-bit pieces
 __device__ __forceinline__ u32 span_word_masks(const SpanBits &k, int j, u32 &a0, u32 &a1, u32 &b0, u32 &b1, u32 &c0, u32 &c1,
@@ -536,13 +517,15 @@ __device__ __forceinline__ u32 span_word_masks(const SpanBits &k, int j, u32 &a0
     return cellact | ez | ey | ex;
 }
 
-// ---- span fast path, three sync-free stages (Z % 128 == 0) -------------------------------------
-//   k_rowcount128  thread = 128-point span, straight from L2: branch-free uniformity test; only the ~1 %
-//                  mixed spans are classified in detail and add their entry count to row_count[r]
-//   k_scan_rows    decoupled look-back exclusive scan over the X*Y row counts (in place) -> row_start, S
-//   k_rowfill128   thread = row that owns entries: re-classifies its spans and writes the entries
+// ---- span fast path, three stages (Z % 128 == 0) -----------------------------------------------
+//   k_rowcount_blk  block = 256 rows: span summary (written by k_signbits) -> candidate spans, classified from the
+//                   sign bits with one thread per span -> entry count of every row + per-span counts
+//                   (k_rowcount_sum: thread-per-row variant for rows of more than 32 spans)
+//   k_scan_rows     decoupled look-back exclusive scan over the X*Y row counts (in place) -> row_start, S
+//   k_rowfill_cnt   thread = row that owns entries: re-classifies its non-empty spans and writes the entries
+//                   (k_rowfill128: the variant driven by the summary alone, rows of more than 32 spans)
 // (a single-pass chained-scan version of this stage spent its time at barriers waiting for the
-//  look-back warp and ran 3x slower at 1024^3; see profiles/)
+//  look-back warp and ran 3x slower at 1024^3; fusing only the row scan into the count kernel: +10 us; see profiles/)
 struct SpanRows {
     const uint4 *a, *c;   // row (x,y) in plane x and in plane x+1 (aliases plane x when x+1 does not exist)
     u32 dy;               // uint4 offset of row y+1 (0 when it does not exist)
