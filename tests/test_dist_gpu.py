@@ -199,6 +199,12 @@ def test_c3_2048_csg_two_slabs_equal_single_gpu():
     for i in range(0, len(v), 1 << 22):
         worst = max(worst, float(fn(v[i:i + (1 << 22)]).abs().max()))
     assert worst < 0.5 * 2.0 / (n - 1)
+    # the CPU oracle on windows of x layers of the full-size grid: a box face (1.5 M vertices in one layer), box + sphere,
+    # the far box face -- bit-equal triangles
+    import fullsize
+    from isoext_b200 import _lib
+    checked = sum(fullsize.check_layers_vs_oracle(_lib.lib(), vals, v, f, a, b) for a, b in ((408, 411), (1300, 1302), (1636, 1639)))
+    assert checked > 1000000
     # two slabs with cuts balanced by the measured load
     hist = idist.vertex_layer_histogram(v, n, -1.0, 1.0)
     cuts = idist.balanced_cuts((2.6e-6 + 0.43e-9 * hist).tolist(), 2, ghost_cost=(0.43e-9 * hist).tolist())

@@ -173,6 +173,12 @@ def test_1024_properties(iso):
     v, f = iso.marching_cubes(g)
     assert len(v) == 2416776   # doc/grids.ipynb:307-309 records this count for the same field
     check_closed_manifold(v, f, euler=2)
+    # the CPU oracle on windows of x layers of the full-size grid: where the sphere is tangent to the planes, at its
+    # equator and in between (bit-equal triangles; the reference itself is invalid at this size)
+    import fullsize
+    from isoext_b200 import _lib
+    checked = sum(fullsize.check_layers_vs_oracle(_lib.lib(), vals, v, f, a, b) for a, b in ((152, 156), (300, 302), (510, 513), (868, 871)))
+    assert checked > 50000
     r = v.double().norm(dim=-1)
     assert float((r - 0.7).abs().max()) < 2e-6 * n / 64   # linear interpolation error of a sphere SDF
     # the same surface through level shift: marching_cubes(values, L) == marching_cubes(values - L', L - L') topologically
