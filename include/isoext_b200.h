@@ -213,17 +213,22 @@ int isoext_its_sparse_emit(const float *values8, const int64_t *cell_idx, int64_
                            const uint32_t *cellslot, const uint32_t *its_off, int64_t n_cells, int64_t n_its, float *points,
                            float *normals, uint32_t *cell_offsets, int64_t *cell_indices, void *stream);
 /* dual_contouring on a SparseGrid: neighbour cells by binary search in cell_idx (replaces the dense
- * X*Y*Z idx_map of src/grid/sparse.cu:223-243).  Phase 1 counts_out[0..1] = Q, Vc; phase 2 [0] = V. */
+ * X*Y*Z idx_map of src/grid/sparse.cu:223-243).  Phase 1 counts_out[0..1] = Q, Vc; phase 2 [0..2] = V, # with
+ * x < x_lo_threshold, # with x < x_hi_threshold.
+ * Slabs (new capability): only the cells [emit_begin, emit_end) of the list emit quads (0 .. n on one GPU), every
+ * quad of the list marks its cells as used (the welded vertex set does not depend on the emit range), and the welded
+ * vertices are classified by x position against the two thresholds (-inf / +inf on one GPU). */
 size_t isoext_dc_sparse_workspace_bytes(int64_t n, int64_t X);
 int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
                            const float *aabb_min, const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot,
                            const uint32_t *its_off, const float *points, const float *normals, float reg, float svd_tol,
-                           float *dual_v, void *workspace, size_t workspace_bytes, void *stream, int64_t *counts_out);
+                           int64_t emit_begin, int64_t emit_end, float *dual_v, void *workspace, size_t workspace_bytes,
+                           void *stream, int64_t *counts_out);
 int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z, const float *aabb_min,
                           const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot, const float *dual_v,
                           void *workspace, size_t workspace_bytes, void *scratch, size_t scratch_bytes,
-                          int64_t n_candidates, float *V, int32_t *F, int32_t *quads_out, void *stream,
-                          int64_t *counts_out);
+                          int64_t n_candidates, float x_lo_threshold, float x_hi_threshold, float *V, int32_t *F,
+                          int32_t *quads_out, void *stream, int64_t *counts_out);
 
 /* Single-call fast path of marching_cubes on a UniformGrid: both phases enqueued back to back, ONE
  * stream synchronisation.  The caller supplies capacities (typically the sizes of the previous extraction

@@ -71,10 +71,10 @@ SIGNATURES = {
     "isoext_its_sparse_emit": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _vp, _vp, _vp, _i64, _i64, _vp, _vp,
                                       _vp, _vp, _vp]),
     "isoext_dc_sparse_workspace_bytes": (_sz, [_i64, _i64]),
-    "isoext_dc_sparse_count": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _sz,
-                                      _vp, _pi64]),
-    "isoext_dc_sparse_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i64, _vp, _vp, _vp,
-                                     _vp, _pi64]),
+    "isoext_dc_sparse_count": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i64, _i64, _vp,
+                                      _vp, _sz, _vp, _pi64]),
+    "isoext_dc_sparse_emit": (_int, [_vp, _i64, _i64, _i64, _i64, _f3, _f3, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _i64, _f32, _f32, _vp,
+                                     _vp, _vp, _vp, _pi64]),
     "isoext_mc_dense_run": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _f3, _f3, _f32, _int, _i64, _i64,
                                    _vp, _sz, _i64, _vp, _sz, _i64, _i64, _i64, _int, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _pi64]),
     "isoext_relabel_faces": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),

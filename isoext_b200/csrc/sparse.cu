@@ -445,9 +445,13 @@ __device__ __forceinline__ u32 own_edges_of_case(u32 cs) {
 __global__ void __launch_bounds__(128) k_sp_dc_quads(const float *__restrict__ values8, const i64 *__restrict__ cell_idx,
                                                      SparseParams p, u32 n, const u32 *__restrict__ cinfo,
                                                      const u32 *__restrict__ plane_start, u32 *__restrict__ dinfo,
-                                                     unsigned char *__restrict__ used) {
+                                                     unsigned char *__restrict__ used, u32 emit_begin, u32 emit_end) {
+    // Every quad of the list marks its four cells as used (so that the set of welded dual vertices of a slab does not
+    // depend on which quads the slab emits); only the cells [emit_begin, emit_end) keep their quads (the owned cells
+    // of a slab; 0 .. n on one GPU).
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const u32 w = cinfo[s];
+        const bool emits = s >= emit_begin && s < emit_end;
         u32 m = 0, io = 0;
         if (w & 0x100u) {
             const u32 own = own_edges_of_case(w & 0xffu);
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(128) k_sp_dc_quads(const float *__restrict__ v
                     if (!((own >> a) & 1u)) continue;
                     u32 q[4];
                     if (sparse_quad_cells(p, cell_idx, n, cinfo, plane_start, s, a, q)) {
-                        m |= 1u << a;
+                        if (emits) m |= 1u << a;
                         used[q[0]] = 1; used[q[1]] = 1; used[q[2]] = 1; used[q[3]] = 1;
                     }
                 }
@@ -803,13 +807,15 @@ size_t isoext_dc_sparse_workspace_bytes(int64_t n, int64_t X) {
 int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z,
                            const float *aabb_min, const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot,
                            const uint32_t *its_off, const float *points, const float *normals, float reg, float svd_tol,
-                           float *dual_v, void *workspace, size_t workspace_bytes, void *stream_, int64_t *counts_out) {
+                           int64_t emit_begin, int64_t emit_end, float *dual_v, void *workspace, size_t workspace_bytes,
+                           void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SparseParams p;
     int rc = make_sparse_params(X, Y, Z, aabb_min, aabb_max, 0.f, n, &p);
     if (rc != OK) return rc;
     counts_out[0] = counts_out[1] = 0;
     if (n <= 0) return OK;
+    if (emit_begin < 0 || emit_end > n || emit_begin > emit_end) return fail(E_INVALID, "emit range out of bounds");
     Carver c(workspace);
     SpDcWs b;
     if (carve_sp_dc_ws(c, (size_t) n, (size_t) X, &b) > workspace_bytes) return fail(E_WORKSPACE, "workspace too small");
@@ -821,7 +827,8 @@ int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_CUDA(cudaMemsetAsync(b.descB, 0, ((size_t) n / SPT_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_sp_dc_solve, blocks, 128, 0, stream, cell_idx, p, (u32) n, cinfo, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
     ISX_LAUNCH(k_sp_plane_start, grid_for(X, 256, sms * 4), 256, 0, stream, cell_idx, (u32) n, p, b.plane_start);
-    ISX_LAUNCH(k_sp_dc_quads, blocks, 128, 0, stream, values8, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.used);
+    ISX_LAUNCH(k_sp_dc_quads, blocks, 128, 0, stream, values8, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.used, (u32) emit_begin,
+               (u32) emit_end);
     ISX_LAUNCH(k_sp_fold_used, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.used, b.dinfo);
     ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, b.dinfo, 0, 7u, 8, 1u, b.quad_off, b.cand_off, b.descA, b.descB,
                (int) C_Q, (int) C_VC, (int) C_TICKET_D);
@@ -836,13 +843,13 @@ int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
 
 int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t Y, int64_t Z, const float *aabb_min,
                           const float *aabb_max, const uint32_t *cinfo, const uint32_t *cellslot, const float *dual_v, void *workspace,
-                          size_t workspace_bytes, void *scratch, size_t scratch_bytes, int64_t n_candidates, float *V, int32_t *F,
-                          int32_t *quads_out, void *stream_, int64_t *counts_out) {
+                          size_t workspace_bytes, void *scratch, size_t scratch_bytes, int64_t n_candidates, float x_lo_threshold,
+                          float x_hi_threshold, float *V, int32_t *F, int32_t *quads_out, void *stream_, int64_t *counts_out) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SparseParams p;
     int rc = make_sparse_params(X, Y, Z, aabb_min, aabb_max, 0.f, n, &p);
     if (rc != OK) return rc;
-    counts_out[0] = 0;
+    counts_out[0] = counts_out[1] = counts_out[2] = 0;
     if (n <= 0 || n_candidates <= 0) return OK;
     Carver c(workspace);
     SpDcWs b;
@@ -857,12 +864,14 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
     u32 h[C_COUNT];
     // dual vertices: one candidate per cell, segmented by grid layer (0.39 ms vs 0.76 ms for the global radix sort at
     // 2.4 M; at 38.7 M the radix sort is the faster one: 29.1 vs 38.0 ms for the whole call)
-    rc = sort_weld_faces(s, nc, p.g, b.counters, -INFINITY, INFINITY, V, stream, h, sp_use_seg(nc), [&]() {
+    rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, sp_use_seg(nc), [&]() {
         ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.quad_off, b.cand_off,
                    cellslot, s.cand_rank, dual_v, F, quads_out);
     });
     if (rc != OK) return rc;
     counts_out[0] = h[C_V];
+    counts_out[1] = h[C_NLO];
+    counts_out[2] = h[C_NHI];
     return OK;
 }
 

@@ -153,16 +153,23 @@ def dc_slab_plan(X: int, rank: int, world: int, cuts=None) -> dict:
                 emit_lo=c_lo, emit_hi=(c_hi if rank < world - 1 else X))
 
 
-def sparse_slab_select(cell_idx, shape, rank: int, world: int, cuts=None):
+def sparse_slab_select(cell_idx, shape, rank: int, world: int, cuts=None, below: int = 1, above: int = 1):
     """Slab sharding of a SparseGrid (host logic; the sorted cell list is partitioned by x layer):
     returns boolean masks ``(ext, owned)`` over ``cell_idx``.  Rank r emits the faces of its ``owned`` cells (layers
-    ``[c_r, c_{r+1})``) and welds the vertices of the ``ext`` cells (one ghost layer on either side), so that -- as
-    in the dense path -- it knows every vertex near its two threshold planes and can number by position."""
+    ``[c_r, c_{r+1})``) and welds the vertices of the ``ext`` cells (``below`` / ``above`` ghost layers: one on either
+    side for marching cubes), so that -- as in the dense path -- it knows every vertex near its two threshold planes
+    and can number by position.
+
+    Dual contouring needs ``below=3, above=2``: its quads reach one layer down; the previous rank's vertices that
+    interleave with those of layer c_r - 1 include dual vertices of layer c_r - 2 clipped onto plane c_r - 1, and
+    whether such a vertex exists at all ("used by some quad") depends on which cells of layer c_r - 3 are present;
+    likewise the next rank's first vertices (x == px[c_{r+1}]) come from layer c_{r+1} as well, whose usage depends on
+    the presence of cells in layer c_{r+1} + 1."""
     X, Y, Z = (int(v) for v in shape)
     c = partition_cells(X, world) if cuts is None else check_cuts(X, world, cuts)
     layer = torch.as_tensor(cell_idx).to(torch.int64) // ((Y - 1) * (Z - 1))
     owned = (layer >= c[rank]) & (layer < c[rank + 1])
-    ext = (layer >= c[rank] - 1) & (layer <= c[rank + 1])
+    ext = (layer >= c[rank] - below) & (layer <= c[rank + 1] - 1 + above)
     return ext, owned
 
 
@@ -576,13 +583,14 @@ class SparseSlab:
     those cells (e.g. the whole band); afterwards the rank needs nothing from its neighbours but two counts, because
     sparse cells carry their own corner values -- there is no halo to exchange."""
 
-    def __init__(self, grid, group=None, rank=None, world=None, cuts=None):
+    def __init__(self, grid, group=None, rank=None, world=None, cuts=None, dc: bool = False):
         from .sparse import SparseGrid
         self.group = group
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         shape = grid.shape
-        ext, owned = sparse_slab_select(grid._cells, shape, self.rank, self.world, cuts)
+        self.dc = bool(dc)     # dual contouring: 3 ghost layers below, 2 above (sparse_slab_select)
+        ext, owned = sparse_slab_select(grid._cells, shape, self.rank, self.world, cuts, below=3 if dc else 1, above=2 if dc else 1)
         c = partition_cells(shape[0], self.world) if cuts is None else check_cuts(shape[0], self.world, cuts)
         local = SparseGrid(list(shape), grid.aabb_min, grid.aabb_max, grid.default_value, device=grid.device)
         local._cells = grid._cells[ext].contiguous()
@@ -616,6 +624,29 @@ def marching_cubes_sparse(ss: SparseSlab, level: float = 0.0, method: str = "nag
     """Distributed ``marching_cubes`` over a slab-partitioned SparseGrid: this rank's ``(v_own, f_own)``; the parts
     of ranks 0..R-1 concatenate to exactly the single-device sparse mesh (global vertex ids)."""
     v_own, f, n_lo, n_hi = marching_cubes_sparse_local(ss, level, method)
+    vb, fb, totals, _ = global_bases(n_hi - n_lo, int(f.shape[0]), ss.device, ss.group)
+    relabel_faces_(f, n_lo, n_hi, vb, vb + (n_hi - n_lo))
+    return v_own, f
+
+
+def dual_contouring_sparse_local(ss: SparseSlab, level: float = 0.0, reg: float = 1e-2, svd_tol: float = 1e-6):
+    """Rank-local part of dual contouring over a slab-partitioned SparseGrid (no communication):
+    ``(v_own, f_local, n_lo, n_hi)``.  Needs ``SparseSlab(..., dc=True)``."""
+    from .sparse import dc_sparse_raw, its_sparse
+    if not ss.dc and ss.world > 1:
+        raise RuntimeError("dual contouring on sparse slabs needs SparseSlab(..., dc=True): 3 ghost layers below, 2 above")
+    its = its_sparse(ss.local, level, True)
+    v, f, _, _, n_lo, n_hi = dc_sparse_raw(ss.local, its, reg, svd_tol, emit_range=ss.emit, x_thresholds=ss.thresholds, with_counts=True)
+    if v is None:
+        return (torch.empty((0, 3), dtype=torch.float32, device=ss.device),
+                torch.empty((0, 3), dtype=torch.int32, device=ss.device), 0, 0)
+    return v[n_lo:n_hi], f, n_lo, n_hi
+
+
+def dual_contouring_sparse(ss: SparseSlab, level: float = 0.0, reg: float = 1e-2, svd_tol: float = 1e-6):
+    """Distributed ``dual_contouring`` over a slab-partitioned SparseGrid: this rank's ``(v_own, f_own)``; the parts of
+    ranks 0..R-1 concatenate to exactly the single-device sparse DC mesh (global vertex ids)."""
+    v_own, f, n_lo, n_hi = dual_contouring_sparse_local(ss, level, reg, svd_tol)
     vb, fb, totals, _ = global_bases(n_hi - n_lo, int(f.shape[0]), ss.device, ss.group)
     relabel_faces_(f, n_lo, n_hi, vb, vb + (n_hi - n_lo))
     return v_own, f

@@ -272,26 +272,35 @@ def its_sparse(grid: SparseGrid, level: float, compute_normals: bool):
                               _has_normals=bool(compute_normals))
 
 
-def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads: bool = False, dual_v_in=None):
-    """(v, f, dual_v, quads) like dc.dc_dense_raw; ``dual_v_in`` replaces the solved dual vertices (parity tests)."""
+def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads: bool = False, dual_v_in=None, emit_range=None,
+                  x_thresholds=(-math.inf, math.inf), with_counts: bool = False):
+    """(v, f, dual_v, quads) like dc.dc_dense_raw; ``dual_v_in`` replaces the solved dual vertices (parity tests).
+
+    Slabs (``dist.SparseSlab(dc=True)``): only the cells ``emit_range = (begin, end)`` of the list emit quads, the welded
+    vertices are classified by x against ``x_thresholds``; with ``with_counts`` the result is
+    ``(v_all, f, dual_v, quads, n_lo, n_hi)`` -- ``v_all[n_lo:n_hi]`` are the vertices this slab owns, ``f`` holds ids in
+    the slab's extended id space -- and a slab that emits no quad still welds (its vertices may be referenced by a
+    neighbour's quads)."""
     lib = _lib.lib()
     n = grid.get_num_cells()
     X, Y, Z, amin, amax = grid._geom()
     dev = grid.device
     dual_v = torch.empty((its.n_cells, 3), dtype=torch.float32, device=dev)
+    empty = (None, None, dual_v, None, 0, 0) if with_counts else (None, None, dual_v, None)
     if n == 0 or its.n_cells == 0:
-        return None, None, dual_v, None
+        return empty
+    e0, e1 = (0, n) if emit_range is None else (int(emit_range[0]), int(emit_range[1]))
     with torch.cuda.device(dev):
         stream = _stream_ptr()
         ws = grid._ws.get("dc_ws", lib.isoext_dc_sparse_workspace_bytes(n, X), dev)
         counts = (C.c_int64 * 4)()
         _lib.check(lib.isoext_dc_sparse_count(grid._values.data_ptr(), grid._cells.data_ptr(), n, X, Y, Z, amin, amax,
                                               its.cinfo.data_ptr(), its.cellslot.data_ptr(), its.its_off.data_ptr(),
-                                              its.points.data_ptr(), its.normals.data_ptr(), float(reg), float(svd_tol),
+                                              its.points.data_ptr(), its.normals.data_ptr(), float(reg), float(svd_tol), e0, e1,
                                               dual_v.data_ptr(), ws.data_ptr(), ws.numel(), stream, counts))
         Q, Vc = int(counts[0]), int(counts[1])
-        if Q == 0:
-            return None, None, dual_v, None
+        if Vc == 0 or (Q == 0 and not with_counts):
+            return empty
         if dual_v_in is not None:
             dual_v.copy_(dual_v_in)
         scratch = grid._ws.get("scratch", lib.isoext_sparse_scratch_bytes(Vc, X, Y), dev)
@@ -301,8 +310,11 @@ def dc_sparse_raw(grid: SparseGrid, its, reg: float, svd_tol: float, want_quads:
         out = (C.c_int64 * 4)()
         _lib.check(lib.isoext_dc_sparse_emit(grid._cells.data_ptr(), n, X, Y, Z, amin, amax, its.cinfo.data_ptr(),
                                              its.cellslot.data_ptr(), dual_v.data_ptr(), ws.data_ptr(), ws.numel(),
-                                             scratch.data_ptr(), scratch.numel(), Vc, V.data_ptr(), F.data_ptr(),
-                                             quads.data_ptr() if want_quads else None, stream, out))
+                                             scratch.data_ptr(), scratch.numel(), Vc, float(x_thresholds[0]), float(x_thresholds[1]),
+                                             V.data_ptr(), F.data_ptr() if Q else None, quads.data_ptr() if want_quads and Q else None,
+                                             stream, out))
+    if with_counts:
+        return V[:int(out[0])], F, dual_v, quads, int(out[1]), int(out[2])
     return V[:int(out[0])], F, dual_v, quads
 
 

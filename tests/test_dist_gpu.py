@@ -163,6 +163,37 @@ def test_sparse_grid_simulated_slabs_concatenate_to_single_device_mesh(iso, name
     assert torch.equal(f, gf)
 
 
+@pytest.mark.parametrize("holes", [False, True])
+@pytest.mark.parametrize("world", [2, 3, 6])
+@pytest.mark.parametrize("name", sorted(FIELDS))
+def test_sparse_dual_contouring_simulated_slabs_concatenate_to_single_device_mesh(iso, name, world, holes):
+    """Sparse dual contouring on slabs (dist.SparseSlab(dc=True): 3 ghost layers below, 2 above; every quad of the local
+    list marks its cells as used, only owned cells emit; ownership by position): the parts concatenate to the
+    single-device sparse DC mesh bit for bit.  ``holes``: a third of the band's cells is removed at random, so whether a
+    dual vertex exists at all depends on which neighbour cells are present -- also across the slab boundaries."""
+    from isoext_b200 import dist as idist
+    vals = FIELDS[name]()
+    g = _band_grid(iso, vals)
+    if holes:
+        gen = torch.Generator().manual_seed(3)
+        drop = g.get_cell_indices()[(torch.rand(g.get_num_cells(), generator=gen) < 0.33).cuda()]
+        keep_vals = g.get_values()
+        keep_mask = ~torch.isin(g.get_cell_indices(), drop)
+        g.remove_cells(drop)
+        g.set_values(keep_vals[keep_mask].contiguous())
+    gv, gf = iso.dual_contouring(g)
+    parts = [idist.dual_contouring_sparse_local(idist.SparseSlab(g, rank=r, world=world, dc=True)) for r in range(world)]
+    if gv is None:
+        assert all(len(p[1]) == 0 for p in parts)
+        return
+    bases = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])])
+    for r, (v_own, f, n_lo, n_hi) in enumerate(parts):
+        idist.relabel_faces_(f, n_lo, n_hi, int(bases[r]), int(bases[r + 1]))
+    v, f = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    assert v.shape == gv.shape and torch.equal(v.view(torch.int32), gv.view(torch.int32))
+    assert torch.equal(f, gf)
+
+
 def test_c3_2048_csg_two_slabs_equal_single_gpu():
     """BASELINE.json configs[2] at FULL size on one GPU: the 2048^3 CSG field extracted whole and as two simulated
     slabs with load-balanced cuts must agree bit for bit; the mesh is a closed genus-0 surface whose x-sorted
@@ -264,6 +295,9 @@ def _nccl_worker(rank, world, port, transport, field_name):
         sv, sf = idist.gather_mesh(*idist.marching_cubes_sparse(idist.SparseSlab(band)))
         gsv, gsf = iso.marching_cubes(band)
         assert torch.equal(sv.view(torch.int32), gsv.view(torch.int32)) and torch.equal(sf, gsf), f"rank {rank}: sparse slabs"
+        dv, df = idist.gather_mesh(*idist.dual_contouring_sparse(idist.SparseSlab(band, dc=True)))
+        gdv, gdf = iso.dual_contouring(band)
+        assert torch.equal(dv.view(torch.int32), gdv.view(torch.int32)) and torch.equal(df, gdf), f"rank {rank}: sparse DC slabs"
         # same values again without a new set_owned_values, and the explicit no-exchange variant
         v_own, f_own = idist.marching_cubes(sg, 0.0)
         v2_own, f2_own = idist.marching_cubes(sg, 0.0, exchange=False)
