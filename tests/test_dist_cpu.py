@@ -264,3 +264,23 @@ def test_sparse_slabs_concatenate_to_the_single_device_mesh(name, world):
     v, f = np.concatenate(vs), np.concatenate(fs)
     assert v.shape == gv.shape and np.array_equal(v.view(np.uint32), gv.view(np.uint32))
     assert np.array_equal(f, gf)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_sparse_slab_select_ghost_depths(world):
+    """Host logic of the sparse slabs: marching cubes keeps one ghost layer on either side, dual contouring three below
+    and two above (dist.sparse_slab_select); the owned cells of all ranks partition the list."""
+    shape = (33, 9, 11)
+    rng = np.random.default_rng(7)
+    cells = np.sort(rng.choice(32 * 8 * 10, size=900, replace=False)).astype(np.int64)
+    layer = cells // (8 * 10)
+    c = idist.partition_cells(shape[0], world)
+    owned_total = np.zeros(len(cells), dtype=int)
+    for r in range(world):
+        for below, above in ((1, 1), (3, 2)):
+            ext, owned = (m.numpy() for m in idist.sparse_slab_select(cells, shape, r, world, below=below, above=above))
+            assert np.array_equal(owned, (layer >= c[r]) & (layer < c[r + 1]))
+            assert np.array_equal(ext, (layer >= c[r] - below) & (layer < c[r + 1] + above))
+            assert not (owned & ~ext).any()
+        owned_total += owned
+    assert (owned_total == 1).all()
