@@ -15,7 +15,8 @@ is meaningful:
            ("balanced_cuts"), as is the first (cold: count + emit, capacity discovery) call ("first_call_ms").
   sub_records (N = 1): configs[1] 512^3 torus ("c2", the reference-representable single-GPU case) and the
            north-star target 1024^3 torus ("t1024"), each timed with the same protocol and with its own
-           whole_path_frac.
+           whole_path_frac; configs[3] 512^3 CSG dual_contouring ("c4") and configs[4] SparseGrid narrow band
+           ("c5", 1024^3-equivalent sphere, marching_cubes and dual_contouring), counts verified.
 Every line carries the global vertex / triangle totals and a 64-bit order-sensitive checksum of the mesh
 (V bits and F ids weighted by their global index); they are checked against the values the single-GPU
 path produced (EXPECTED below), so a wrong mesh at any N fails loudly instead of printing a number.
@@ -275,6 +276,48 @@ def single_gpu_record(iso, lib, wl_name, dev, steps, warmup, peak, keep=False):
     return rec, None, prof
 
 
+def other_config_records(iso, lib, dev, steps, warmup, peak):
+    """BASELINE.json configs[3] and configs[4] as timed sub-records of the N = 1 line (same protocol: W warm-ups, K
+    steps between synchronisations, CUDA events; field / band resident): c4 = 512^3 box-minus-sphere dual_contouring,
+    c5 = SparseGrid narrow band of the 1024^3-equivalent sphere r = 0.7 (the reference's documented example size; the
+    4096^3-equivalent band is in tools/bench_extra.py c5big), marching_cubes and dual_contouring."""
+    import torch
+    from isoext_b200 import sdf as S
+    recs = []
+    # ---- c4
+    n = 512
+    grid = iso.UniformGrid([n, n, n])
+    view = grid.values_view()
+    fn = field_fn("csg")
+    for a in range(0, n, 64):
+        build_field_gpu(fn, n, a, min(n, a + 64), dev, out=view[a:a + 64])
+    ms_total, (v, f), _, clocks = timed_loop(lambda: iso.dual_contouring(grid), steps, warmup, torch.cuda.synchronize, ClockSampler(dev.index or 0))
+    ms = ms_total / steps
+    nV, nT = int(v.shape[0]), int(f.shape[0])
+    recs.append({"workload": "c4: 512^3 dense CSG box-minus-sphere dual_contouring (reg=1e-2, svd_tol=1e-6, normals from the field), 1 GPU",
+                 "shape": [n] * 3, "value": float(n) ** 3 / (ms * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms, "steps": steps,
+                 "warmup": warmup, "vertices": nV, "triangles": nT, "mesh_verified": (nV, nT) == (561818, 1123632),
+                 "whole_path_frac": (4.0 * n ** 3 + 12.0 * nV + 12.0 * nT) / (ms * 1e-3) / 1e9 / peak, "clocks": clocks})
+    del grid, view, v, f
+    # ---- c5 (1024^3-equivalent band, populated on the GPU from the analytic program: no 1024^3 field is allocated)
+    n = 1024
+    band = iso.SparseGrid([n, n, n])
+    band.populate_from_dense(iso.ImplicitGrid([n, n, n], S.SphereSDF(0.7)))
+    cells = band.get_num_cells()
+    for op, run in (("marching_cubes", lambda: iso.marching_cubes(band)), ("dual_contouring", lambda: iso.dual_contouring(band))):
+        ms_total, (v, f), _, clocks = timed_loop(run, steps, warmup, torch.cuda.synchronize, ClockSampler(dev.index or 0))
+        ms = ms_total / steps
+        nV, nT = int(v.shape[0]), int(f.shape[0])
+        ok = (cells, nV) == (2416778, 2416776) if op == "marching_cubes" else (cells, nV) == (2416778, 2416778)
+        recs.append({"workload": f"c5: SparseGrid narrow band, 1024^3-equivalent sphere r=0.7 ({cells} cells), {op}, 1 GPU",
+                     "cells": cells, "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "equivalent_gvoxels_s": float(n) ** 3 / (ms * 1e-3) / 1e9,
+                     "ms_per_step": ms, "steps": steps, "warmup": warmup, "vertices": nV, "triangles": nT, "mesh_verified": ok,
+                     "whole_path_frac": (40.0 * cells + 12.0 * nV + 12.0 * nT) / (ms * 1e-3) / 1e9 / peak, "clocks": clocks})
+    del band
+    torch.cuda.empty_cache()
+    return recs
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -467,6 +510,10 @@ def run_ours(args):
                     subs.append(r)
                 except Exception as exc:    # the headline line must still be printed
                     subs.append({"workload": name, "unavailable": repr(exc)[:200]})
+            try:
+                subs.extend(other_config_records(iso, lib, dev, args.steps, args.warmup, peak))
+            except Exception as exc:
+                subs.append({"workload": "c4 / c5", "unavailable": repr(exc)[:200]})
             line["sub_records"] = subs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(wl["field"])
@@ -542,7 +589,56 @@ def run_reference(args):
         line["sub_records"] = [{"workload": f"c2: {WORKLOADS['c2']['desc']}", "shape": [512] * 3, "same_workload": True,
                                 "value": 512.0 ** 3 / (ms2 * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms2,
                                 "vertices": nv2, "triangles": nf2}]
+        try:
+            line["sub_records"] += reference_other_configs(ref, dev)
+        except Exception as exc:
+            line["sub_records"].append({"workload": "c4 / c5", "unavailable": repr(exc)[:200]})
     print(json.dumps(line), flush=True)
+
+
+def reference_other_configs(ref, dev, steps=3, warmup=1):
+    """The reference CUDA build on BASELINE.json configs[3] (512^3 CSG dual_contouring) and configs[4] at the size its
+    documentation uses (1024^3-equivalent sphere band: marching_cubes, dual_contouring) -- full size, identical inputs to
+    the sub-records of our arm (the band is populated with our GPU population, the reference's recipe being a Python loop
+    over 10,738 chunks)."""
+    import torch
+    import isoext_b200 as iso
+    from isoext_b200 import sdf as S
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
+
+    recs = []
+    n = 512
+    vals = build_field_gpu(field_fn("csg"), n, 0, n, dev)
+    rg = ref.UniformGrid([n] * 3)
+    rg.set_values(vals)
+    ms, (v, f) = timed(lambda: ref.dual_contouring(rg))
+    recs.append({"workload": "c4: 512^3 dense CSG box-minus-sphere dual_contouring", "same_workload": True, "ms_per_step": ms,
+                 "value": float(n) ** 3 / (ms * 1e-3) / 1e9, "unit": "Gvoxels/s", "vertices": int(v.shape[0]), "triangles": int(f.shape[0])})
+    del rg, vals, v, f
+    n = 1024
+    band = iso.SparseGrid([n] * 3)
+    band.populate_from_dense(iso.ImplicitGrid([n] * 3, S.SphereSDF(0.7)))
+    cells, vals8 = band.get_cell_indices(), band.get_values()
+    rg = ref.SparseGrid([n] * 3)
+    rg.add_cells(cells.to(torch.int32).contiguous())
+    rg.set_values(vals8)
+    for op, fn in (("marching_cubes", lambda: ref.marching_cubes(rg)), ("dual_contouring", lambda: ref.dual_contouring(rg))):
+        ms, (v, f) = timed(fn)
+        recs.append({"workload": f"c5: SparseGrid narrow band, 1024^3-equivalent sphere r=0.7 ({cells.numel()} cells), {op}",
+                     "same_workload": True, "ms_per_step": ms, "value": cells.numel() / (ms * 1e-3) / 1e6, "unit": "Mcells/s",
+                     "vertices": int(v.shape[0]), "triangles": int(f.shape[0])})
+    return recs
 
 
 def main():
