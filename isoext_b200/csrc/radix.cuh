@@ -45,6 +45,8 @@ struct RadixBuffers {
 static __global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict__ kx, const u32 *__restrict__ ky,
                                                     const u32 *__restrict__ kz, u32 n, u32 *__restrict__ hist,
                                                     const u32 *__restrict__ n_dev) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u32 sh[RADIX_PASSES * 256];
     if (n_dev) n = *n_dev;
     for (int i = threadIdx.x; i < RADIX_PASSES * 256; i += blockDim.x) sh[i] = 0;
@@ -63,6 +65,8 @@ static __global__ void __launch_bounds__(256) k_radix_hist(const u32 *__restrict
 
 // one warp per digit place: exclusive scan of its 256-bin histogram (8 bins per lane)
 static __global__ void __launch_bounds__(32 * RADIX_PASSES) k_radix_prefix(u32 *__restrict__ hist) {
+    pdl_wait();
+    pdl_trigger();
     const u32 lane = threadIdx.x & 31, p = threadIdx.x >> 5;
     u32 v[8], sum = 0;
 #pragma unroll
@@ -126,6 +130,8 @@ k_radix_pass(const u32 *__restrict__ key_in, const u32 *__restrict__ perm_in, u3
              const u32 *__restrict__ gprefix, u64 *__restrict__ desc, u32 *__restrict__ ticket, u32 epoch, u32 n,
              const u32 *__restrict__ n_dev) {
     __shared__ u32 cnt[RADIX_THREADS / 32][256];
+    pdl_wait();                  // launched with programmatic serialization behind the previous pass (common.cuh)
+    pdl_trigger();
     if (n_dev) n = *n_dev;       // device-side count: blocks beyond the last tile leave right after their ticket
     __shared__ u32 gbase[256];
     __shared__ u32 s_tile;
@@ -212,21 +218,21 @@ static inline cudaError_t radix_sort96(const u32 *kx, const u32 *ky, const u32 *
     u32 hist_blocks = (n + 256 * 16 - 1) / (256 * 16);
     if (hist_blocks > 148 * 4) hist_blocks = 148 * 4;
     ISX_LAUNCH(k_radix_hist, hist_blocks, 256, 0, stream, kx, ky, kz, n, b.hist, n_dev);
-    ISX_LAUNCH(k_radix_prefix, 1, 32 * RADIX_PASSES, 0, stream, b.hist);
+    ISX_LAUNCH_PDL(k_radix_prefix, 1, 32 * RADIX_PASSES, 0, stream, b.hist);
     const u32 *src[3] = {kz, ky, kx};
     for (int p = first_pass; p < RADIX_PASSES; p++) {
         const int in = p & 1, out = in ^ 1;
         const u32 shift = 8 * (p & 3);
         const u32 *coord = src[p >> 2];
         if (p == first_pass)
-            ISX_LAUNCH((k_radix_pass<true, true>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
-                       shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
+            ISX_LAUNCH_PDL((k_radix_pass<true, true>), ntiles, RADIX_THREADS, 0, stream, (const u32 *) b.key[in], (const u32 *) b.perm[in], b.key[out], b.perm[out], coord,
+                           shift, (const u32 *) (b.hist + p * 256), b.desc, b.ticket + p, (u32) (p + 1), n, n_dev);
         else if ((p & 3) == 0)
-            ISX_LAUNCH((k_radix_pass<true, false>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
-                       shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
+            ISX_LAUNCH_PDL((k_radix_pass<true, false>), ntiles, RADIX_THREADS, 0, stream, (const u32 *) b.key[in], (const u32 *) b.perm[in], b.key[out], b.perm[out], coord,
+                           shift, (const u32 *) (b.hist + p * 256), b.desc, b.ticket + p, (u32) (p + 1), n, n_dev);
         else
-            ISX_LAUNCH((k_radix_pass<false, false>), ntiles, RADIX_THREADS, 0, stream, b.key[in], b.perm[in], b.key[out], b.perm[out], coord,
-                       shift, b.hist + p * 256, b.desc, b.ticket + p, p + 1, n, n_dev);
+            ISX_LAUNCH_PDL((k_radix_pass<false, false>), ntiles, RADIX_THREADS, 0, stream, (const u32 *) b.key[in], (const u32 *) b.perm[in], b.key[out], b.perm[out], coord,
+                           shift, (const u32 *) (b.hist + p * 256), b.desc, b.ticket + p, (u32) (p + 1), n, n_dev);
     }
     return cudaGetLastError();
 }
