@@ -59,8 +59,12 @@ class Intersection:
         return Intersection._make(**d)
 
 
+def _margin(n: int) -> int:
+    return n + (n >> 6) + 16
+
+
 def its_dense_raw(values, shape, aabb_min, aabb_max, level: float, compute_normals: bool, ws, cap_hint=0,
-                  x_offset=0, x_global=None, sdf_prog=None):
+                  x_offset=0, x_global=None, sdf_prog=None, hints=None):
     """Intersections of a dense (X, Y, Z) float32 CUDA field (a whole grid, or the extended slab of a sharded grid:
     ``x_offset`` = global index of local plane 0, ``x_global`` = points along x of the whole grid).
     Returns ``(Intersection, entry capacity used)``."""
@@ -75,6 +79,15 @@ def its_dense_raw(values, shape, aabb_min, aabb_max, level: float, compute_norma
     counts = (C.c_int64 * 4)()
     cap = max(int(cap_hint), _initial_cap(shape))
     row_start = torch.empty(X * Y + 2, dtype=torch.int32, device=dev)
+    # Outputs sized by the previous extraction of the grid (``hints``) are allocated BEFORE the counting call, so that
+    # the host does nothing but slice between its synchronisation and the launch of the emit phase.
+    pre = None
+    if hints is not None and hints.get("its_n", 0) > 0:
+        ci, cc = _margin(hints["its_n"]), _margin(hints["its_cells"])
+        pre = (ci, cc, torch.empty((ci, 3), dtype=torch.float32, device=dev),
+               (torch.empty if compute_normals else torch.zeros)((ci, 3), dtype=torch.float32, device=dev),
+               torch.zeros(cc + 1, dtype=torch.int32, device=dev), torch.empty(cc, dtype=torch.int64, device=dev))
+    isout_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
     while True:
         nbytes = lib.isoext_its_dense_workspace_bytes(X, Y, Z, cap)
         if nbytes == 0:
@@ -93,11 +106,17 @@ def its_dense_raw(values, shape, aabb_min, aabb_max, level: float, compute_norma
         break
     S, n_cells, n_its = int(counts[0]), int(counts[1]), int(counts[2])
     entries, cellslot, its_off = entries[:S + 1], cellslot[:max(S, 1)], its_off[:max(S, 1)]
-    points = torch.empty((n_its, 3), dtype=torch.float32, device=dev)
-    normals = torch.zeros((n_its, 3), dtype=torch.float32, device=dev)
-    isout = torch.empty(max(S, 1), dtype=torch.uint8, device=dev)
-    cell_offsets = torch.zeros(n_cells + 1, dtype=torch.int32, device=dev)
-    cell_indices = torch.empty(n_cells, dtype=torch.int64, device=dev)
+    if pre is not None and n_its <= pre[0] and n_cells <= pre[1]:
+        points, normals, cell_offsets, cell_indices = pre[2][:n_its], pre[3][:n_its], pre[4][:n_cells + 1], pre[5][:n_cells]
+    else:
+        points = torch.empty((n_its, 3), dtype=torch.float32, device=dev)
+        # every normal is written when they are computed; otherwise get_normals() must read zeros, not garbage
+        normals = (torch.empty if compute_normals else torch.zeros)((n_its, 3), dtype=torch.float32, device=dev)
+        cell_offsets = torch.zeros(n_cells + 1, dtype=torch.int32, device=dev)
+        cell_indices = torch.empty(n_cells, dtype=torch.int64, device=dev)
+    isout = isout_buf[:max(S, 1)] if isout_buf.numel() >= max(S, 1) else torch.empty(max(S, 1), dtype=torch.uint8, device=dev)
+    if hints is not None:
+        hints.update(its_n=n_its, its_cells=n_cells)
     _lib.check(lib.isoext_its_dense_emit(vptr, X, Y, Z, x_offset, xg, amin, amax, float(level),
                                          int(bool(compute_normals)), entries.data_ptr(), S, cellslot.data_ptr(),
                                          its_off.data_ptr(), n_cells, n_its, points.data_ptr(), normals.data_ptr(),
@@ -111,7 +130,7 @@ def its_dense_raw(values, shape, aabb_min, aabb_max, level: float, compute_norma
 
 def _its_dense(grid, level: float, compute_normals: bool) -> Intersection:
     its, cap = its_dense_raw(grid._values, grid.shape, grid.aabb_min, grid.aabb_max, level, compute_normals, grid._ws,
-                             cap_hint=grid._cap_hint, sdf_prog=getattr(grid, "_prog", None))
+                             cap_hint=grid._cap_hint, sdf_prog=getattr(grid, "_prog", None), hints=getattr(grid, "_hints", None))
     grid._cap_hint = cap
     return its
 
@@ -163,6 +182,12 @@ def dc_dense_raw(grid, its: Intersection, reg: float, svd_tol: float, want_quads
     if S == 0 or n_cells == 0:
         return empty
     ws = grid._ws.get("dc_ws", lib.isoext_dc_dense_workspace_bytes(S, n_cells), dev)
+    hints = getattr(grid, "_hints", None)
+    pre = None                  # outputs sized by the previous extraction, allocated before the counting call (see its_dense_raw)
+    if hints is not None and hints.get("dc_Vc", 0) > 0:
+        cv, cq = _margin(hints["dc_Vc"]), _margin(hints["dc_Q"])
+        pre = (cv, cq, torch.empty((cv, 3), dtype=torch.float32, device=dev), torch.empty((2 * cq, 3), dtype=torch.int32, device=dev),
+               torch.empty((cq, 4), dtype=torch.int32, device=dev) if want_quads else None)
     counts = (C.c_int64 * 4)()
     _lib.check(lib.isoext_dc_dense_count(X, Y, Z, xo, xg, amin, amax, lo, hi, its.entries.data_ptr(), S, its.row_start.data_ptr(),
                                          its.cellslot.data_ptr(), its.its_off.data_ptr(), n_cells, its.points.data_ptr(),
@@ -174,9 +199,14 @@ def dc_dense_raw(grid, its: Intersection, reg: float, svd_tol: float, want_quads
     if dual_v_in is not None:
         dual_v.copy_(dual_v_in)
     scratch = grid._ws.get("dc_scratch", lib.isoext_dc_dense_scratch_bytes(Vc), dev)
-    V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
-    F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)
-    quads = torch.empty((Q, 4), dtype=torch.int32, device=dev) if want_quads else None
+    if hints is not None:
+        hints.update(dc_Vc=Vc, dc_Q=Q)
+    if pre is not None and Vc <= pre[0] and Q <= pre[1]:
+        V, F, quads = pre[2][:Vc], pre[3][:2 * Q], (pre[4][:Q] if want_quads else None)
+    else:
+        V = torch.empty((Vc, 3), dtype=torch.float32, device=dev)
+        F = torch.empty((2 * Q, 3), dtype=torch.int32, device=dev)
+        quads = torch.empty((Q, 4), dtype=torch.int32, device=dev) if want_quads else None
     out = (C.c_int64 * 4)()
     _lib.check(lib.isoext_dc_dense_emit(X, Y, Z, xo, xg, amin, amax, lo, hi, thr_lo, thr_hi, its.entries.data_ptr(), S,
                                         its.row_start.data_ptr(), its.cellslot.data_ptr(), its.isout.data_ptr(), n_cells,
