@@ -313,23 +313,30 @@ __global__ void __launch_bounds__(128) k_sp_its_emit(const float *__restrict__ v
         }
         CellData c;
         load_sparse_cell(values8, p, s, cell_idx[s], c);
-        const u32 status = w >> 16;
+        const u32 status = (w >> 16) & 0xfffu;
+        const u32 o0 = o;
+        if (POINTS) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-            if (!((status >> k) & 1u)) continue;
-            float qx, qy, qz;
-            if (POINTS) {
+            for (int k = 0; k < 12; k++) {      // the edge is a compile-time constant here (corner indices fold to registers)
+                if (!((status >> k) & 1u)) continue;
+                float qx, qy, qz;
                 cell_edge_point(c, k, p.level, qx, qy, qz);
                 points[3 * (size_t) o] = qx; points[3 * (size_t) o + 1] = qy; points[3 * (size_t) o + 2] = qz;
-            } else {
-                qx = points[3 * (size_t) o]; qy = points[3 * (size_t) o + 1]; qz = points[3 * (size_t) o + 2];
+                o++;
             }
-            if (NORMALS) {
+        }
+        if (NORMALS) {
+            // One copy of the (division-heavy, ~300 instructions) normal evaluation in a rolled loop over the cell's
+            // intersections, instead of twelve inlined copies behind the unrolled edge loop: the kernel was stalling on
+            // instruction fetch (ncu: no_inst among the top stall reasons on every hot line).
+            const u32 m = __popc(status);
+#pragma unroll 1
+            for (u32 j = 0; j < m; j++) {
+                const size_t q = 3 * (size_t) (o0 + j);
                 float nx, ny, nz;
-                cell_normal(c, qx, qy, qz, nx, ny, nz);
-                normals[3 * (size_t) o] = nx; normals[3 * (size_t) o + 1] = ny; normals[3 * (size_t) o + 2] = nz;
+                cell_normal(c, points[q], points[q + 1], points[q + 2], nx, ny, nz);
+                normals[q] = nx; normals[q + 1] = ny; normals[q + 2] = nz;
             }
-            o++;
         }
     }
 }
