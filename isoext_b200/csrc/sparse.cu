@@ -452,7 +452,8 @@ __device__ __forceinline__ u32 own_edges_of_case(u32 cs) {
 __global__ void __launch_bounds__(128) k_sp_dc_quads(const float *__restrict__ values8, const i64 *__restrict__ cell_idx,
                                                      SparseParams p, u32 n, const u32 *__restrict__ cinfo,
                                                      const u32 *__restrict__ plane_start, u32 *__restrict__ dinfo,
-                                                     unsigned char *__restrict__ used, u32 emit_begin, u32 emit_end) {
+                                                     unsigned char *__restrict__ used, u32 emit_begin, u32 emit_end,
+                                                     u32 *__restrict__ qnb) {
     // Every quad of the list marks its four cells as used (so that the set of welded dual vertices of a slab does not
     // depend on which quads the slab emits); only the cells [emit_begin, emit_end) keep their quads (the owned cells
     // of a slab; 0 .. n on one GPU).
@@ -472,7 +473,12 @@ __global__ void __launch_bounds__(128) k_sp_dc_quads(const float *__restrict__ v
                     if (!((own >> a) & 1u)) continue;
                     u32 q[4];
                     if (sparse_quad_cells(p, cell_idx, n, cinfo, plane_start, s, a, q)) {
-                        if (emits) m |= 1u << a;
+                        if (emits) {        // the face kernel reads the three neighbours back instead of searching again
+                            m |= 1u << a;
+                            qnb[(size_t) (3 * a + 0) * n + s] = q[1];
+                            qnb[(size_t) (3 * a + 1) * n + s] = q[2];
+                            qnb[(size_t) (3 * a + 2) * n + s] = q[3];
+                        }
                         used[q[0]] = 1; used[q[1]] = 1; used[q[2]] = 1; used[q[3]] = 1;
                     }
                 }
@@ -502,7 +508,7 @@ __global__ void __launch_bounds__(256) k_sp_dc_keys(u32 n, const u32 *__restrict
 }
 
 __global__ void __launch_bounds__(128) k_sp_dc_faces(const i64 *__restrict__ cell_idx, SparseParams p, u32 n,
-                                                     const u32 *__restrict__ cinfo, const u32 *__restrict__ plane_start,
+                                                     const u32 *__restrict__ cinfo, const u32 *__restrict__ qnb,
                                                      const u32 *__restrict__ dinfo,
                                                      const u32 *__restrict__ quad_off, const u32 *__restrict__ cand_off,
                                                      const u32 *__restrict__ cellslot, const u32 *__restrict__ cand_rank,
@@ -514,8 +520,7 @@ __global__ void __launch_bounds__(128) k_sp_dc_faces(const i64 *__restrict__ cel
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             if (!((m >> a) & 1u)) continue;
-            u32 q[4];
-            sparse_quad_cells(p, cell_idx, n, cinfo, plane_start, s, a, q);
+            u32 q[4] = {s, qnb[(size_t) (3 * a + 0) * n + s], qnb[(size_t) (3 * a + 1) * n + s], qnb[(size_t) (3 * a + 2) * n + s]};
             if (!((io >> a) & 1u)) {
                 const u32 t0 = q[0], t1 = q[1];
                 q[0] = q[3]; q[1] = q[2]; q[2] = t1; q[3] = t0;
@@ -610,6 +615,7 @@ struct SpDcWs {
     unsigned char *used;
     u64 *descA, *descB;
     u32 *plane_start;   // X + 1
+    u32 *qnb;           // 9 planes of n: list positions of the 3 other cells of the quad of (cell, axis), k_sp_dc_quads -> k_sp_dc_faces
 };
 static size_t carve_sp_dc_ws(Carver &c, size_t n, size_t X, SpDcWs *out) {
     SpDcWs b;
@@ -621,6 +627,7 @@ static size_t carve_sp_dc_ws(Carver &c, size_t n, size_t X, SpDcWs *out) {
     b.used = c.take<unsigned char>(n + 1);
     b.descA = c.take<u64>(n / SPT_TILE + 2);
     b.descB = c.take<u64>(n / SPT_TILE + 2);
+    b.qnb = c.take<u32>(9 * n);
     if (out) *out = b;
     return c.bytes();
 }
@@ -835,7 +842,7 @@ int isoext_dc_sparse_count(const float *values8, const int64_t *cell_idx, int64_
     ISX_LAUNCH(k_sp_dc_solve, blocks, 128, 0, stream, cell_idx, p, (u32) n, cinfo, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
     ISX_LAUNCH(k_sp_plane_start, grid_for(X, 256, sms * 4), 256, 0, stream, cell_idx, (u32) n, p, b.plane_start);
     ISX_LAUNCH(k_sp_dc_quads, blocks, 128, 0, stream, values8, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.used, (u32) emit_begin,
-               (u32) emit_end);
+               (u32) emit_end, b.qnb);
     ISX_LAUNCH(k_sp_fold_used, grid_for(n, 256, sms * 16), 256, 0, stream, (u32) n, b.used, b.dinfo);
     ISX_LAUNCH(k_sp_scan2, scan_blocks(sms), 256, 0, stream, (u32) n, b.counters, b.dinfo, 0, 7u, 8, 1u, b.quad_off, b.cand_off, b.descA, b.descB,
                (int) C_Q, (int) C_VC, (int) C_TICKET_D);
@@ -872,7 +879,7 @@ int isoext_dc_sparse_emit(const int64_t *cell_idx, int64_t n, int64_t X, int64_t
     // dual vertices: one candidate per cell, segmented by grid layer (0.39 ms vs 0.76 ms for the global radix sort at
     // 2.4 M; at 38.7 M the radix sort is the faster one: 29.1 vs 38.0 ms for the whole call)
     rc = sort_weld_faces(s, nc, p.g, b.counters, x_lo_threshold, x_hi_threshold, V, stream, h, sp_use_seg(nc), [&]() {
-        ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.plane_start, b.dinfo, b.quad_off, b.cand_off,
+        ISX_LAUNCH(k_sp_dc_faces, grid_for(n, 128, sms * 16), 128, 0, stream, cell_idx, p, (u32) n, cinfo, b.qnb, b.dinfo, b.quad_off, b.cand_off,
                    cellslot, s.cand_rank, dual_v, F, quads_out);
     });
     if (rc != OK) return rc;
