@@ -286,7 +286,8 @@ __device__ __forceinline__ bool cell_is_used(const DenseParams &p, u32 xg, u32 y
 
 __global__ void __launch_bounds__(128) k_dc_quads(DenseParams p, const uint2 *__restrict__ entries, u32 S,
                                                   const u32 *__restrict__ row_start, const u32 *__restrict__ cellslot,
-                                                  unsigned char *__restrict__ qmask, unsigned char *__restrict__ used) {
+                                                  unsigned char *__restrict__ qmask, unsigned char *__restrict__ used,
+                                                  u32 *__restrict__ qslots) {
     const u32 Y = (u32) p.g.Y;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
         const uint2 e = entries[s];
@@ -301,7 +302,11 @@ __global__ void __launch_bounds__(128) k_dc_quads(DenseParams p, const uint2 *__
             for (int a = 0; a < 3; a++) {
                 if (!((own >> a) & 1u)) continue;
                 u32 q[4];
-                if (quad_cells(p, entries, row_start, cellslot, e.x, ent_z(e.y), a, q)) m |= 1u << a;
+                if (quad_cells(p, entries, row_start, cellslot, e.x, ent_z(e.y), a, q)) {
+                    m |= 1u << a;          // the face kernel reads the four slots back instead of searching again
+#pragma unroll
+                    for (int k = 0; k < 4; k++) qslots[(size_t) (4 * a + k) * S + s] = q[k];
+                }
             }
         }
         qmask[s] = (unsigned char) m;
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(256) k_dc_keys(u32 n_cells, const u32 *__restr
 }
 
 __global__ void __launch_bounds__(128) k_dc_faces(DenseParams p, const uint2 *__restrict__ entries, u32 S,
-                                                  const u32 *__restrict__ row_start, const u32 *__restrict__ cellslot,
+                                                  const u32 *__restrict__ qslots, const u32 *__restrict__ cellslot,
                                                   const unsigned char *__restrict__ qmask, const unsigned char *__restrict__ isout,
                                                   const u32 *__restrict__ quad_off, const u32 *__restrict__ cand_of_cell,
                                                   const u32 *__restrict__ cand_rank, const float *__restrict__ dual_v,
@@ -394,7 +399,8 @@ __global__ void __launch_bounds__(128) k_dc_faces(DenseParams p, const uint2 *__
         for (int a = 0; a < 3; a++) {
             if (!((m >> a) & 1u)) continue;
             u32 q[4];
-            quad_cells(p, entries, row_start, cellslot, e.x, ent_z(e.y), a, q);
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = qslots[(size_t) (4 * a + k) * S + s];
             if (!((io >> a) & 1u)) {   // edge points inward: reverse the loop (src/dc.cu:123-127)
                 const u32 t0 = q[0], t1 = q[1];
                 q[0] = q[3]; q[1] = q[2]; q[2] = t1; q[3] = t0;
@@ -428,6 +434,7 @@ struct DcWs {
     unsigned char *used;    // n_cells
     u32 *quad_off;          // S
     u32 *cand_of_cell;      // n_cells
+    u32 *qslots;            // 12 planes of S: the 4 cell slots of the quad of (entry, axis), k_dc_quads -> k_dc_faces
     u64 *descQ, *descU;
 };
 static size_t carve_dc_ws(Carver &c, size_t S, size_t n_cells, DcWs *out) {
@@ -439,6 +446,7 @@ static size_t carve_dc_ws(Carver &c, size_t S, size_t n_cells, DcWs *out) {
     b.cand_of_cell = c.take<u32>(n_cells + 1);
     b.descQ = c.take<u64>(S / IT_TILE + 2);
     b.descU = c.take<u64>(S / IT_TILE + 2);
+    b.qslots = c.take<u32>(12 * (S + 1));
     if (out) *out = b;
     return c.bytes();
 }
@@ -640,7 +648,7 @@ int isoext_dc_dense_count(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int
     ISX_CUDA(cudaMemsetAsync(b.descQ, 0, ((size_t) S / IT_TILE + 2) * sizeof(u64), stream));
     ISX_CUDA(cudaMemsetAsync(b.descU, 0, ((size_t) S / IT_TILE + 2) * sizeof(u64), stream));
     ISX_LAUNCH(k_dc_solve, sms * 8, 128, 0, stream, p, ent, S, cellslot, its_off, points, normals, reg, svd_tol, dual_v);
-    ISX_LAUNCH(k_dc_quads, sms * 8, 128, 0, stream, p, ent, S, row_start, cellslot, b.qmask, b.used);
+    ISX_LAUNCH(k_dc_quads, sms * 8, 128, 0, stream, p, ent, S, row_start, cellslot, b.qmask, b.used, b.qslots);
     ISX_LAUNCH(k_dc_scan, scan_blocks(sms), 256, 0, stream, S, b.counters, cellslot, b.qmask, b.used, b.quad_off, b.cand_of_cell, b.descQ, b.descU);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
@@ -680,7 +688,7 @@ int isoext_dc_dense_emit(int64_t X, int64_t Y, int64_t Z, int64_t x_offset, int6
     ISX_CUDA(radix_sort96(s.kx, s.ky, s.kz, nc, s.radix, stream));
     ISX_LAUNCH(k_unique, scan_blocks(sms), 256, 0, stream, nc, s.radix.perm[0], s.kx, s.ky, s.kz, s.cand_rank, V, b.counters, s.descV,
                host_float_key(x_lo_threshold), host_float_key(x_hi_threshold));
-    ISX_LAUNCH(k_dc_faces, sms * 8, 128, 0, stream, p, ent, S, row_start, cellslot, b.qmask, isout, b.quad_off, b.cand_of_cell,
+    ISX_LAUNCH(k_dc_faces, sms * 8, 128, 0, stream, p, ent, S, b.qslots, cellslot, b.qmask, isout, b.quad_off, b.cand_of_cell,
                s.cand_rank, dual_v, F, quads_out);
     ISX_CUDA(cudaGetLastError());
     u32 h[C_COUNT];
