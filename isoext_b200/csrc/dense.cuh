@@ -994,18 +994,30 @@ __device__ __forceinline__ void load_cell_positions(const DenseParams &p, u32 r,
 // the point is at least eps * cell - 2 ulp away from both end points along the edge axis, while a point on
 // another edge through the same corner stays within 1 ulp of the corner along that axis.  eps * cell = 16 ulp of
 // the largest coordinate (make_dense_params), so the two differ.  NaN fails the comparisons -> not plain.
-__device__ __forceinline__ bool cell_is_plain(const CellData &c, u32 status, const DenseParams &p) {
+__device__ __forceinline__ bool cell_is_plain(const CellData &c, u32 status, float level, const float (&eps2)[3]) {
     bool plain = true;
 #pragma unroll
     for (int k = 0; k < 12; k++)
         if ((status >> k) & 1u) {
             const int p0 = edge_c0(k), p1 = edge_c1(k);
             const int axis = (p0 ^ p1) == 4 ? 0 : ((p0 ^ p1) == 2 ? 1 : 2);
-            const float a = fabsf(__fsub_rn(p.level, c.v[p0])), d = fabsf(__fsub_rn(c.v[p1], c.v[p0]));
-            const float e2 = p.eps2[axis];
+            const float a = fabsf(__fsub_rn(level, c.v[p0])), d = fabsf(__fsub_rn(c.v[p1], c.v[p0]));
+            const float e2 = eps2[axis];
             plain = plain && (a >= e2 * d) && (a <= (1.0f - e2) * d);
         }
     return plain;
+}
+__device__ __forceinline__ bool cell_is_plain(const CellData &c, u32 status, const DenseParams &p) {
+    return cell_is_plain(c, status, p.level, p.eps2);
+}
+// eps2 of an axis (host): 2 * 16 ulp of the largest coordinate of the axis, relative to the cell size (see cell_is_plain)
+static inline float plain_eps2(float amin, float asize, i64 res) {
+    const double lo = amin, hi = (double) amin + (double) asize;
+    const double big = fabs(lo) > fabs(hi) ? fabs(lo) : fabs(hi);
+    const double cell = res > 1 ? fabs((double) asize) / (double) (res - 1) : 0.0;
+    double e2 = cell > 0.0 ? 2.0 * 16.0 * big * 1.1920928955078125e-7 / cell : 1.0;
+    if (!(e2 < 0.25)) e2 = 1.0;   // cells of a few ulp (or NaN boxes): every cell takes the exact path
+    return (float) e2;
 }
 template <bool IMPLICIT = false>
 __device__ __forceinline__ void load_cell(const float *__restrict__ values, const DenseParams &p, u32 r, u32 z, CellData &c) {

@@ -577,14 +577,7 @@ int make_dense_params(i64 X, i64 Y, i64 Z, i64 x_off, i64 Xg, const float *amin,
     p.ystep = (u32) ((Y + p.gy - 1) / p.gy);
     {   // k_cell_tris fast path (dense.cuh: cell_is_plain): eps * cell = 16 ulp of the largest coordinate of the axis
         const i64 res[3] = {Xg, Y, Z};
-        for (int a = 0; a < 3; a++) {
-            const double lo = p.g.amin[a], hi = (double) p.g.amin[a] + (double) p.g.asize[a];
-            const double big = fabs(lo) > fabs(hi) ? fabs(lo) : fabs(hi);
-            const double cell = res[a] > 1 ? fabs((double) p.g.asize[a]) / (double) (res[a] - 1) : 0.0;
-            double e2 = cell > 0.0 ? 2.0 * 16.0 * big * 1.1920928955078125e-7 / cell : 1.0;
-            if (!(e2 < 0.25)) e2 = 1.0;   // cells of a few ulp (or NaN boxes): every cell takes the exact path
-            p.eps2[a] = (float) e2;
-        }
+        for (int a = 0; a < 3; a++) p.eps2[a] = plain_eps2(p.g.amin[a], p.g.asize[a], res[a]);
     }
     *out = p;
     return OK;

@@ -26,6 +26,7 @@ struct SparseParams {
     Geom g;          // X,Y,Z = points per axis of the enclosing uniform grid
     i64 cy, cz;      // cells per axis along y and z  (Y-1, Z-1)
     float level;
+    float eps2[3];   // plain-cell test of marching cubes (dense.cuh: cell_is_plain)
 };
 
 __device__ __forceinline__ void cell_coords(const SparseParams &p, i64 idx, u32 &x, u32 &y, u32 &z) {
@@ -103,13 +104,22 @@ __global__ void __launch_bounds__(128) k_sp_mc_classify(const float *__restrict_
             continue;
         }
         const u32 status = edge_mask_of_case(cs);
+        const u64 word = method == 0 ? kTriWords_nagae[cs] : kTriWords_lorensen[cs];
+        const u32 nt = (u32) (word >> 60);
+        u32 mask = 0, used = 0;
+        if (cell_is_plain(c, status, p.level, p.eps2)) {
+            // no crossing is near a cell corner, so no two crossing points can be bit-equal: every LUT triangle is kept and
+            // every sign-change edge is used, without evaluating a position (the fast path of the dense k_cell_tris)
+            mask = (1u << nt) - 1u;
+            used = status;
+            if (s < emit_begin || s >= emit_end) mask = 0;
+            cinfo[s] = cs | (mask << 8) | (used << 16);
+            continue;
+        }
         float ex[12], ey[12], ez[12];
 #pragma unroll
         for (int k = 0; k < 12; k++)
             if ((status >> k) & 1u) cell_edge_point(c, k, p.level, ex[k], ey[k], ez[k]);
-        const u64 word = method == 0 ? kTriWords_nagae[cs] : kTriWords_lorensen[cs];
-        const u32 nt = (u32) (word >> 60);
-        u32 mask = 0, used = 0;
         for (u32 k = 0; k < nt; k++) {
             const u32 a = (u32) (word >> (12 * k)) & 15u, b = (u32) (word >> (12 * k + 4)) & 15u, d = (u32) (word >> (12 * k + 8)) & 15u;
             const bool ab = ex[a] != ex[b] || ey[a] != ey[b] || ez[a] != ez[b];
@@ -641,6 +651,8 @@ static int make_sparse_params(i64 X, i64 Y, i64 Z, const float *amin, const floa
     for (int a = 0; a < 3; a++) { p.g.amin[a] = amin[a]; p.g.asize[a] = amax[a] - amin[a]; }
     p.cy = Y - 1; p.cz = Z - 1;
     p.level = level;
+    const i64 res[3] = {X, Y, Z};
+    for (int a = 0; a < 3; a++) p.eps2[a] = plain_eps2(p.g.amin[a], p.g.asize[a], res[a]);
     *out = p;
     return OK;
 }
